@@ -1,0 +1,169 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product path.
+//
+// C-ABI wrapper around the UNMODIFIED reference decimator.  oracle/Makefile compiles
+// /root/reference/src/dsd_decimator.cpp (+ filters.cpp through its #include) and
+// dsd_sample_reader.cpp where they lie, against oracle/ref_shim, together with this file,
+// into oracle/_ref/libdsdref.so.  This file adds only (1) an in-memory DsdSampleReader whose
+// step() follows dsf_file_reader.cpp:83-103 and (2) drivers shaped like main.cpp:169-191.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+// The lookup table is a private member (dsd_decimator.h:139); the unit tests want to compare
+// it entry by entry, so open the class up for this translation unit only.
+#define private public
+#include "dsd_decimator.h"
+#undef private
+
+namespace {
+
+class MemoryReader : public DsdSampleReader {
+public:
+    MemoryReader(const uint8_t* planar, int nch, int64_t nbytes, int64_t lengthSamples,
+                 uint32_t fs, bool msbFirstFlag, uint8_t idle)
+        : data_(planar), nch_(nch), nbytes_(nbytes), len_(lengthSamples), fs_(fs),
+          msb_(msbFirstFlag), idle_(idle) {
+        samplesPerChar = 8;
+        valid = true;
+        posMarker = -1;
+        allocateBuffer();
+        rewind();
+    }
+    dsf2flac_uint32 getSamplingFreq() { return fs_; }
+    dsf2flac_uint32 getNumChannels() { return (dsf2flac_uint32)nch_; }
+    dsf2flac_int64 getLength() { return len_; }
+    bool msbIsPlayedFirst() { return msb_; }
+    dsf2flac_uint8 getIdleSample() { return idle_; }
+    void rewind() { posMarker = -1; clearBuffer(); }
+    // same shape as DsfFileReader::step(): availability is tested BEFORE the marker moves, so
+    // the byte at index L/8 is still fetched when L is a multiple of 8 (SURVEY 8a edge case).
+    bool step() {
+        bool ok = samplesAvailable();
+        const int64_t k = posMarker + 1;
+        for (int c = 0; c < nch_; ++c) {
+            uint8_t b = idle_;
+            if (ok && k >= 0 && k < nbytes_) b = data_[(int64_t)c * nbytes_ + k];
+            circularBuffers[c].push_front(b);
+        }
+        posMarker++;
+        return ok;
+    }
+private:
+    const uint8_t* data_;
+    int nch_;
+    int64_t nbytes_, len_;
+    uint32_t fs_;
+    bool msb_;
+    uint8_t idle_;
+};
+
+}  // namespace
+
+extern "C" {
+
+// Geometry the reference derives for (dsd_fs, out_fs).  Returns 0 if the pair is rejected.
+int dsdref_info(uint32_t dsd_fs, uint32_t out_fs, int64_t length_samples, int32_t* ratio,
+                int32_t* nlut, int32_t* nstep, int32_t* tzero, double* first_valid,
+                double* last_valid, int64_t* length_pcm) {
+    uint8_t dummy = 0;
+    MemoryReader rd(&dummy, 1, 0, length_samples, dsd_fs, true, 0x69);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) return 0;
+    *ratio = (int32_t)dec.getDecimationRatio();
+    *nlut = (int32_t)dec.nLookupTable;
+    *nstep = (int32_t)dec.nStep;
+    *tzero = (int32_t)dec.tzero;
+    *first_valid = dec.getFirstValidSample();
+    *last_valid = dec.getLastValidSample();
+    *length_pcm = dec.getLength();
+    return 1;
+}
+
+// Copies the reference's lookup table, lut[t*256 + s].  Returns nLookupTable (0 = invalid).
+int dsdref_lut(uint32_t dsd_fs, uint32_t out_fs, int msb_flag, double* lut, int cap_tables) {
+    uint8_t dummy = 0;
+    MemoryReader rd(&dummy, 1, 0, 0, dsd_fs, msb_flag != 0, 0x69);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) return 0;
+    int n = (int)dec.nLookupTable;
+    for (int t = 0; t < n && t < cap_tables; ++t)
+        for (int s = 0; s < 256; ++s) lut[t * 256 + s] = (double)dec.lookupTable[t][s];
+    return n;
+}
+
+// Raw operator: rewind, `pre_steps` x step(), then getSamples in calls of `chunk_frames` frames
+// (0 = one call).  reseed != 0 -> srand(1) first, i.e. the dither stream of a fresh process.
+// out_i32 and/or out_f64 (either may be NULL) are [nframes][nch].  Returns 0 on success.
+int dsdref_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                   uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs,
+                   int64_t pre_steps, int64_t nframes, int64_t chunk_frames, double scale,
+                   double dither, double clip, int reseed, int32_t* out_i32, double* out_f64) {
+    MemoryReader rd(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) return 1;
+    if (reseed) srand(1);
+    for (int64_t i = 0; i < pre_steps; ++i) dec.step();
+    if (chunk_frames <= 0) chunk_frames = nframes;
+    // out_f64 is produced from a second, identically driven decimator so both views see the
+    // same dither draws only when dither == 0; with dither on ask for one view at a time.
+    if (out_i32) {
+        for (int64_t f = 0; f < nframes; f += chunk_frames) {
+            int64_t n = nframes - f < chunk_frames ? nframes - f : chunk_frames;
+            dec.getSamples(out_i32 + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
+        }
+    }
+    if (out_f64) {
+        MemoryReader rd2(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+        DsdDecimator dec2(&rd2, out_fs);
+        if (reseed) srand(1);
+        for (int64_t i = 0; i < pre_steps; ++i) dec2.step();
+        for (int64_t f = 0; f < nframes; f += chunk_frames) {
+            int64_t n = nframes - f < chunk_frames ? nframes - f : chunk_frames;
+            dec2.getSamples(out_f64 + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
+        }
+    }
+    return 0;
+}
+
+// Whole-track conversion with the loop shape of pcm_track_helper (main.cpp:169-191) for the
+// --onefile case: startPos = getFirstValidSample(), endPos = getLastValidSample()
+// (main.cpp:249-258).  Returns frames written, or -1 (invalid) / -2 (out too small).
+int64_t dsdref_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                       uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs,
+                       double scale, double dither, double clip, int reseed, int32_t* out,
+                       int64_t out_cap_frames) {
+    MemoryReader rd(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) return -1;
+    if (reseed) srand(1);
+    double startPos = dec.getFirstValidSample();
+    double endPos = dec.getLastValidSample();
+    if (startPos > dec.getLength() - 1) startPos = dec.getLength() - 1;
+    if (endPos > dec.getLength()) endPos = dec.getLength();
+    const int block = 1024;
+    while (dec.getPosition() < startPos) dec.step();
+    int64_t done = 0;
+    std::vector<int32_t> buf((size_t)nch * block);
+    while (dec.getPosition() <= endPos - block) {
+        dec.getSamples(buf.data(), (dsf2flac_uint32)(nch * block), scale, dither, clip);
+        if (done + block > out_cap_frames) return -2;
+        std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch * block);
+        done += block;
+    }
+    while (dec.getPosition() <= endPos) {
+        dec.getSamples(buf.data(), (dsf2flac_uint32)nch, scale, dither, clip);
+        if (done + 1 > out_cap_frames) return -2;
+        std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch);
+        done += 1;
+    }
+    return done;
+}
+
+// libc rand() as the reference sees it: srand(1) then n draws (pins the restated generator).
+void dsdref_libc_rand(int32_t* out, int64_t n) {
+    srand(1);
+    for (int64_t i = 0; i < n; ++i) out[i] = rand();
+}
+
+}  // extern "C"
