@@ -1,0 +1,674 @@
+// dsdgpu.cu -- sm_100a kernels + the C ABI of include/dsdgpu.h.
+//
+// Hot path replaced: DsdDecimator::getSamplesInternal (reference src/dsd_decimator.cpp:173-222)
+// -- the per-byte lookup-table FIR (:194-198) fused with scale / TPDF dither / clip / round
+// (:199-216).  Kernels:
+//   decimate_skew_kernel    bank-conflict-free lane-skewed LUT gather (divide-by-32 filters),
+//                           persistent CTAs, LUT image + double-buffered byte tiles in smem
+//   decimate_direct_kernel  one thread per output sample, tables [t][byte] in smem; any
+//                           geometry, used for /16 and /8 filters and as a cross-check
+//   glibc_rand_*            positional reconstruction of the reference's dither stream
+//                           (unseeded glibc rand(), dsd_decimator.cpp:203-204)
+// There is no CPU fallback anywhere in this file.
+#include "dsdgpu.h"
+#include "skew_core.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using namespace dsdgpu;
+
+thread_local char g_create_error[256] = "";
+
+// ---------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------
+struct DecimateArgs {
+    const uint8_t* in;       // planar [nch][in_stride]
+    long long in_stride;
+    long long in_first;      // stream index of in[c][0]
+    long long in_count;      // valid bytes per channel
+    long long p0;            // stream index of the newest byte of frame 0
+    long long nframes;
+    int nch;
+    unsigned fill;
+    const void* lut;         // kernel specific layout
+    const double* dither;    // (r1 - r2) per output sample [nframes*nch], or nullptr
+    double scale, dither_amp, clip;
+    void* out;
+    int out_kind;
+};
+
+// dsd_decimator.cpp:199-216: scale, dither, clip.  No FMA contraction: the reference is x86-64
+// -O3 without FMA, so sum*scale and (r1-r2)*amp are each rounded before the add.
+__device__ __forceinline__ double quantise_tail(double sum, double scale, double amp, double dith,
+                                                double clip) {
+    double v = __dmul_rn(sum, scale);
+    if (amp > 0.0) v = __dadd_rn(v, __dmul_rn(dith, amp));
+    if (clip > 0.0) {
+        if (v > clip) v = clip;
+        else if (v < -clip) v = -clip;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void store_sample(const DecimateArgs& a, long long frame, int c, double sum) {
+    const long long m = frame * a.nch + c;
+    const double dith = (a.dither != nullptr) ? a.dither[m] : 0.0;
+    const double v = quantise_tail(sum, a.scale, a.dither_amp, dith, a.clip);
+    if (a.out_kind == DSDGPU_OUT_INT32) {
+        // C round(): half away from zero (dsd_decimator.cpp:213-214)
+        reinterpret_cast<int32_t*>(a.out)[m] = __double2int_rz(round(v));
+    } else {
+        reinterpret_cast<double*>(a.out)[m] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// direct kernel: reference loop order, one thread per (channel, frame)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+decimate_direct_kernel(DecimateArgs a, int nlut, int nstep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* lut_s = reinterpret_cast<double*>(smem_raw);
+    const double* lut_g = reinterpret_cast<const double*>(a.lut);
+    for (int i = threadIdx.x; i < nlut * 256; i += blockDim.x) lut_s[i] = lut_g[i];
+    __syncthreads();
+    const long long total = a.nframes * a.nch;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / a.nframes);
+        const long long f = idx - (long long)c * a.nframes;
+        const long long p = a.p0 + f * nstep;
+        const uint8_t* src = a.in + (long long)c * a.in_stride;
+        double sum = 0.0;
+        for (int t = 0; t < nlut; ++t) {
+            const long long o = p - t - a.in_first;
+            const unsigned b = (o >= 0 && o < a.in_count) ? (unsigned)src[o] : a.fill;
+            sum = __dadd_rn(sum, lut_s[t * 256 + b]);
+        }
+        store_sample(a, f, c, sum);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// skewed kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <class G>
+__device__ __forceinline__ void skew_tile_geometry(const DecimateArgs& a, long long tile,
+                                                   long long tiles_per_ch, int& c, long long& f0,
+                                                   long long& t0, int& a_tile) {
+    c = (int)(tile / tiles_per_ch);
+    f0 = (tile - (long long)c * tiles_per_ch) * G::NT;
+    skew_tile_origin<G>(a.p0, a.in_first, f0, t0, a_tile);
+}
+
+// Stage the tile's bytes [t0, t0 + TILE_BYTES) of channel c.  Interior chunks go through
+// cp.async (LDGSTS, 16 B, coalesced); chunks that touch the ends of the source are assembled
+// byte by byte with the fill value.
+template <class G>
+__device__ __forceinline__ void skew_stage_tile(const DecimateArgs& a, int c, long long t0,
+                                                unsigned char* dst, bool aligned16) {
+    const uint8_t* src = a.in + (long long)c * a.in_stride;
+    const long long o0 = t0 - a.in_first;
+    for (int k = threadIdx.x; k < G::TILE_BYTES / 16; k += G::NTHR) {
+        const long long o = o0 + 16LL * k;
+        unsigned char* d = dst + 16 * k;
+        if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
+            cp_async16(d, src + o);
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const long long ob = o + 4 * q + b;
+                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)src[ob] : a.fill;
+                    v |= byte << (8 * b);
+                }
+                w[q] = v;
+            }
+            *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::NTHR, 1) decimate_skew_kernel(DecimateArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [0, LUT_BYTES): table image; then two byte tiles.
+    const int tid = threadIdx.x;
+    {
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
+        for (int k = tid; k < G::LUT_BYTES / 16; k += G::NTHR) cp_async16(smem + 16 * k, img + 16 * k);
+    }
+    const long long tiles_per_ch = (a.nframes + G::NT - 1) / G::NT;
+    const long long ntiles = tiles_per_ch * a.nch;
+    const bool aligned16 = ((reinterpret_cast<unsigned long long>(a.in) | (unsigned long long)a.in_stride) & 15ULL) == 0;
+
+    long long tile = blockIdx.x;
+    int buf = 0;
+    int c; long long f0, t0; int a_tile;
+    if (tile < ntiles) {
+        skew_tile_geometry<G>(a, tile, tiles_per_ch, c, f0, t0, a_tile);
+        skew_stage_tile<G>(a, c, t0, smem + G::LUT_BYTES, aligned16);
+    }
+    cp_async_commit();
+    while (tile < ntiles) {
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+            int cn; long long f0n, t0n; int an;
+            skew_tile_geometry<G>(a, next, tiles_per_ch, cn, f0n, t0n, an);
+            skew_stage_tile<G>(a, cn, t0n, smem + G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES, aligned16);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();          // everything but the group just committed has landed
+        __syncthreads();
+
+        const long long fbase = f0 + tid;
+        skew_tile_lane<G>(smem, (uint32_t)(G::LUT_BYTES + buf * G::TILE_BYTES), tid, a_tile,
+                          [&](int k, double sum) {
+                              const long long f = fbase + (long long)k * G::NTHR;
+                              if (f < a.nframes) store_sample(a, f, c, sum);
+                          },
+                          NoTrace());
+        __syncthreads();             // tile `buf` is free again
+        tile = next;
+        buf ^= 1;
+        if (tile < ntiles) skew_tile_geometry<G>(a, tile, tiles_per_ch, c, f0, t0, a_tile);
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// glibc rand() by position.  r[i] = r[i-31] + r[i-3] (mod 2^32) for i >= 34, draw k = r[344+k]>>1.
+// With x^31 = x^28 + 1:  r[3+m+i] = sum_k c_k r[3+i+k],  c = x^m mod (x^31 - x^28 - 1).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRandDeg = 31;
+constexpr int kRandPowBits = 48;
+constexpr int kRandChunkValues = 62 * 32;               // values per chunk thread (2 per sample)
+constexpr int kRandChunkSamples = kRandChunkValues / 2;
+
+__host__ __device__ inline void rand_poly_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    uint32_t t[2 * kRandDeg - 1];
+    for (int i = 0; i < 2 * kRandDeg - 1; ++i) t[i] = 0;
+    for (int i = 0; i < kRandDeg; ++i) {
+        const uint32_t ai = a[i];
+        if (ai == 0) continue;
+        for (int k = 0; k < kRandDeg; ++k) t[i + k] += ai * b[k];
+    }
+    for (int d = 2 * kRandDeg - 2; d >= kRandDeg; --d) {   // x^d = x^(d-3) + x^(d-31)
+        t[d - 3] += t[d];
+        t[d - kRandDeg] += t[d];
+    }
+    for (int i = 0; i < kRandDeg; ++i) out[i] = t[i];
+}
+
+// one thread per chunk: the 31 words preceding value index n = first_value + chunk*CH
+__global__ void glibc_rand_states_kernel(const uint32_t* __restrict__ pow2, const uint32_t* __restrict__ base,
+                                         unsigned long long first_value, int nchunks, uint32_t* __restrict__ states) {
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= nchunks) return;
+    const unsigned long long n = first_value + (unsigned long long)chunk * kRandChunkValues;  // r index
+    unsigned long long m = n - 34ULL;         // r[n-31+i] = r[3 + m + i]
+    uint32_t c[kRandDeg];
+    for (int i = 0; i < kRandDeg; ++i) c[i] = 0;
+    c[0] = 1;
+    for (int b = 0; b < kRandPowBits && m != 0; ++b, m >>= 1)
+        if (m & 1ULL) {
+            uint32_t p[kRandDeg], o[kRandDeg];
+            for (int i = 0; i < kRandDeg; ++i) p[i] = pow2[b * kRandDeg + i];
+            rand_poly_mul(c, p, o);
+            for (int i = 0; i < kRandDeg; ++i) c[i] = o[i];
+        }
+    for (int i = 0; i < kRandDeg; ++i) {
+        uint32_t acc = 0;
+        for (int k = 0; k < kRandDeg; ++k) acc += c[k] * base[i + k];
+        states[(size_t)chunk * kRandDeg + i] = acc;
+    }
+}
+
+// one thread per chunk: run the recurrence from the chunk's state, emit (r1 - r2) per sample
+__global__ void __launch_bounds__(128)
+glibc_rand_fill_kernel(const uint32_t* __restrict__ states, int nchunks, long long count, double* __restrict__ out) {
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= nchunks) return;
+    uint32_t ring[kRandDeg];                    // ring[i] = r[n - 31 + i]
+#pragma unroll
+    for (int i = 0; i < kRandDeg; ++i) ring[i] = states[(size_t)chunk * kRandDeg + i];
+    const long long s0 = (long long)chunk * kRandChunkSamples;
+    const double rmax = 2147483647.0;
+    for (int blk = 0; blk < kRandChunkValues / 62; ++blk) {
+        const long long sb = s0 + blk * 31;
+        if (sb >= count) break;
+        uint32_t prev = 0;
+#pragma unroll
+        for (int k = 0; k < 62; ++k) {
+            const int slot = k % kRandDeg;
+            const uint32_t v = ring[slot] + ring[(slot + 28) % kRandDeg];   // r[i-31] + r[i-3]
+            ring[slot] = v;
+            const uint32_t draw = v >> 1;
+            if (k & 1) {
+                const long long s = sb + (k >> 1);
+                if (s < count) {
+                    const double r1 = __ddiv_rn((double)(int)prev, rmax);
+                    const double r2 = __ddiv_rn((double)(int)draw, rmax);
+                    out[s] = __dsub_rn(r1, r2);
+                }
+            } else {
+                prev = draw;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct dsdgpu_slot {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_in = nullptr;
+    size_t in_cap = 0;
+    void* d_out = nullptr;
+    size_t out_cap = 0;
+    double* d_dither = nullptr;
+    size_t dither_cap = 0;
+    uint32_t* d_states = nullptr;
+    size_t states_cap = 0;
+    bool busy = false;
+};
+
+struct dsdgpu_ctx {
+    int device = 0, nch = 0, nlut = 0, nstep = 0, lut_precision = 64;
+    int sm_count = 0;
+    int kernel = DSDGPU_KERNEL_AUTO;
+    int threads = 512;
+    long long chunk_frames = 1LL << 21;
+    double* d_lut_direct = nullptr;          // [nlut][256]
+    unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
+    uint32_t* d_rand_pow2 = nullptr;
+    uint32_t* d_rand_base = nullptr;
+    cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
+    dsdgpu_slot slots[2];
+    dsdgpu_slot own;                         // scratch for the device entry point
+    unsigned long long launches = 0;
+    char err[256] = "";
+};
+
+namespace {
+
+using Skew512 = SkewGeom<72, 4, 512, 12>;
+using Skew1024 = SkewGeom<72, 4, 1024, 6>;
+
+int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail((ctx), DSDGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+void free_slot(dsdgpu_slot& s) {
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.d_dither) cudaFree(s.d_dither);
+    if (s.d_states) cudaFree(s.d_states);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = dsdgpu_slot();
+}
+
+template <class T>
+int ensure(dsdgpu_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (*cap >= need) return DSDGPU_OK;
+    if (*p) CUDA_TRY(ctx, cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 8 + 256;
+    CUDA_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(p), want));
+    *cap = want;
+    return DSDGPU_OK;
+}
+
+// glibc's seed-1 initial words r[0..64] (restated from the published TYPE_3 algorithm)
+void glibc_initial_words(uint32_t* r, int n) {
+    int32_t w[34];
+    w[0] = 1;
+    for (int i = 1; i < 31; ++i) {
+        long long hi = w[i - 1] / 127773, lo = w[i - 1] % 127773;
+        long long v = 16807 * lo - 2836 * hi;
+        if (v < 0) v += 2147483647;
+        w[i] = (int32_t)v;
+    }
+    for (int i = 31; i < 34; ++i) w[i] = w[i - 31];
+    for (int i = 0; i < 34 && i < n; ++i) r[i] = (uint32_t)w[i];
+    for (int i = 34; i < n; ++i) r[i] = r[i - 31] + r[i - 3];
+}
+
+int launch_dither(dsdgpu_ctx* ctx, dsdgpu_slot& s, unsigned long long first_sample, long long count,
+                  double* d_out, cudaStream_t st) {
+    if (count <= 0) return DSDGPU_OK;
+    const int nchunks = (int)((count + kRandChunkSamples - 1) / kRandChunkSamples);
+    int rc = ensure(ctx, &s.d_states, &s.states_cap, (size_t)nchunks * kRandDeg * sizeof(uint32_t));
+    if (rc) return rc;
+    const unsigned long long first_value = 344ULL + 2ULL * first_sample;
+    glibc_rand_states_kernel<<<(nchunks + 127) / 128, 128, 0, st>>>(ctx->d_rand_pow2, ctx->d_rand_base,
+                                                                    first_value, nchunks, s.d_states);
+    glibc_rand_fill_kernel<<<(nchunks + 127) / 128, 128, 0, st>>>(s.d_states, nchunks, count, d_out);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+template <class G>
+int launch_skew(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
+    const int smem = G::LUT_BYTES + 2 * G::TILE_BYTES;
+    static thread_local int configured_device = -1;
+    if (configured_device != ctx->device) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_skew_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_device = ctx->device;
+    }
+    const long long tiles = ((a.nframes + G::NT - 1) / G::NT) * a.nch;
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    decimate_skew_kernel<G><<<grid, G::NTHR, smem, st>>>(a);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+int launch_direct(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
+    const int smem = ctx->nlut * 256 * (int)sizeof(double);
+    static thread_local int configured_device = -1;
+    if (configured_device != ctx->device) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 256 * 8));
+        configured_device = ctx->device;
+    }
+    const long long total = a.nframes * a.nch;
+    long long blocks = (total + 1023) / 1024;
+    if (blocks > ctx->sm_count) blocks = ctx->sm_count;
+    decimate_direct_kernel<<<(int)blocks, 1024, smem, st>>>(a, ctx->nlut, ctx->nstep);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+int check_call(dsdgpu_ctx* ctx, const void* in, int64_t in_count, int64_t nframes, int out_kind, const void* out) {
+    if (!ctx) return DSDGPU_ERR_ARG;
+    if (nframes < 0 || in_count < 0) return fail(ctx, DSDGPU_ERR_ARG, "negative size");
+    if (nframes > 0 && !out) return fail(ctx, DSDGPU_ERR_ARG, "null output buffer");
+    if (in_count > 0 && !in) return fail(ctx, DSDGPU_ERR_ARG, "null input buffer");
+    if (out_kind != DSDGPU_OUT_INT32 && out_kind != DSDGPU_OUT_FLOAT64)
+        return fail(ctx, DSDGPU_ERR_ARG, "unknown output kind %d", out_kind);
+    return DSDGPU_OK;
+}
+
+// enqueue dither fill (if any) + the decimation kernel on `st`
+int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in, size_t in_stride,
+                     int64_t in_first, int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes,
+                     double scale, double dither_amp, double clip, uint64_t dither_first_sample,
+                     int out_kind, void* d_out, cudaStream_t st) {
+    if (nframes == 0) return DSDGPU_OK;
+    DecimateArgs a;
+    a.in = d_in; a.in_stride = (long long)in_stride; a.in_first = in_first; a.in_count = in_count;
+    a.p0 = p0; a.nframes = nframes; a.nch = ctx->nch; a.fill = fill;
+    a.dither = nullptr; a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
+    a.out = d_out; a.out_kind = out_kind;
+    if (dither_amp > 0.0) {
+        const long long count = nframes * ctx->nch;
+        int rc = ensure(ctx, &scratch.d_dither, &scratch.dither_cap, (size_t)count * sizeof(double));
+        if (rc) return rc;
+        rc = launch_dither(ctx, scratch, dither_first_sample, count, scratch.d_dither, st);
+        if (rc) return rc;
+        a.dither = scratch.d_dither;
+    }
+    const bool skew_ok = (ctx->nlut == 72 && ctx->nstep == 4 && ctx->d_lut_skew != nullptr);
+    int kernel = ctx->kernel;
+    if (kernel == DSDGPU_KERNEL_AUTO) kernel = skew_ok ? DSDGPU_KERNEL_SKEW : DSDGPU_KERNEL_DIRECT;
+    if (kernel == DSDGPU_KERNEL_SKEW) {
+        if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
+        a.lut = ctx->d_lut_skew;
+        return ctx->threads == 1024 ? launch_skew<Skew1024>(ctx, a, st) : launch_skew<Skew512>(ctx, a, st);
+    }
+    a.lut = ctx->d_lut_direct;
+    return launch_direct(ctx, a, st);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, const double* lut,
+                  int lut_precision) {
+    if (!out) return fail(nullptr, DSDGPU_ERR_ARG, "null ctx pointer");
+    *out = nullptr;
+    if (nch < 1 || nlut < 1 || nlut > 96 || nstep < 1 || !lut)
+        return fail(nullptr, DSDGPU_ERR_ARG, "bad geometry nch=%d nlut=%d nstep=%d", nch, nlut, nstep);
+    if (lut_precision != 64 && lut_precision != 32)
+        return fail(nullptr, DSDGPU_ERR_ARG, "lut_precision must be 64 or 32");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(nullptr, DSDGPU_ERR_NODEVICE, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, DSDGPU_ERR_NODEVICE, "device %d out of range (%d devices)", device, ndev);
+    dsdgpu_ctx* ctx = new (std::nothrow) dsdgpu_ctx();
+    if (!ctx) return fail(nullptr, DSDGPU_ERR_ARG, "out of host memory");
+    ctx->device = device; ctx->nch = nch; ctx->nlut = nlut; ctx->nstep = nstep;
+    ctx->lut_precision = lut_precision;
+#define CREATE_TRY(call)                                                                       \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fail(nullptr, DSDGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));    \
+            dsdgpu_destroy(ctx);                                                               \
+            return DSDGPU_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) CREATE_TRY(cudaStreamCreateWithFlags(&ctx->slots[s].stream, cudaStreamNonBlocking));
+
+    // tables: fp32 variant = every entry rounded to fp32, then widened (accumulation stays fp64)
+    std::vector<double> tab((size_t)nlut * 256);
+    for (size_t i = 0; i < tab.size(); ++i) tab[i] = (lut_precision == 32) ? (double)(float)lut[i] : lut[i];
+    CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_direct), tab.size() * sizeof(double)));
+    CREATE_TRY(cudaMemcpy(ctx->d_lut_direct, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (nlut == 72 && nstep == 4) {
+        std::vector<unsigned char> img(Skew512::LUT_BYTES);
+        skew_build_lut_image<Skew512>(tab.data(), img.data());
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_skew), img.size()));
+        CREATE_TRY(cudaMemcpy(ctx->d_lut_skew, img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
+    // dither generator constants
+    {
+        uint32_t words[3 + 62];
+        glibc_initial_words(words, 3 + 62);
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_base), 62 * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(ctx->d_rand_base, words + 3, 62 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        std::vector<uint32_t> pow2((size_t)kRandPowBits * kRandDeg, 0);
+        uint32_t cur[kRandDeg] = {0};
+        cur[1] = 1;                               // x^(2^0)
+        for (int b = 0; b < kRandPowBits; ++b) {
+            memcpy(&pow2[(size_t)b * kRandDeg], cur, sizeof(cur));
+            uint32_t sq[kRandDeg];
+            rand_poly_mul(cur, cur, sq);
+            memcpy(cur, sq, sizeof(cur));
+        }
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_pow2), pow2.size() * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(ctx->d_rand_pow2, pow2.data(), pow2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+#undef CREATE_TRY
+    *out = ctx;
+    return DSDGPU_OK;
+}
+
+void dsdgpu_destroy(dsdgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int s = 0; s < 2; ++s) free_slot(ctx->slots[s]);
+    free_slot(ctx->own);
+    if (ctx->d_lut_direct) cudaFree(ctx->d_lut_direct);
+    if (ctx->d_lut_skew) cudaFree(ctx->d_lut_skew);
+    if (ctx->d_rand_pow2) cudaFree(ctx->d_rand_pow2);
+    if (ctx->d_rand_base) cudaFree(ctx->d_rand_base);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* dsdgpu_last_error(const dsdgpu_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
+    if (!ctx || !key) return DSDGPU_ERR_ARG;
+    if (!strcmp(key, "kernel")) {
+        if (value < DSDGPU_KERNEL_AUTO || value > DSDGPU_KERNEL_SKEW) return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
+        ctx->kernel = (int)value;
+    } else if (!strcmp(key, "threads")) {
+        if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
+        ctx->threads = (int)value;
+    } else if (!strcmp(key, "chunk_frames")) {
+        if (value < 1) return fail(ctx, DSDGPU_ERR_ARG, "chunk_frames must be >= 1");
+        ctx->chunk_frames = value;
+    } else {
+        return fail(ctx, DSDGPU_ERR_ARG, "unknown option '%s'", key);
+    }
+    return DSDGPU_OK;
+}
+
+unsigned long long dsdgpu_kernel_launches(const dsdgpu_ctx* ctx) { return ctx ? ctx->launches : 0ULL; }
+
+void* dsdgpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void dsdgpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_stride, int64_t in_first,
+                           int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
+                           double dither_amp, double clip, uint64_t dither_first_sample, int out_kind,
+                           void* d_out, void* cuda_stream) {
+    int rc = check_call(ctx, d_in, in_count, nframes, out_kind, d_out);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    rc = enqueue_decimate(ctx, ctx->own, d_in, in_stride, in_first, in_count, fill, p0, nframes, scale,
+                          dither_amp, clip, dither_first_sample, out_kind, d_out, st);
+    if (rc) return rc;
+    if (!cuda_stream) CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return DSDGPU_OK;
+}
+
+int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride, int64_t in_first,
+                  int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
+                  double dither_amp, double clip, uint64_t dither_first_sample, int out_kind, void* out) {
+    int rc = check_call(ctx, in, in_count, nframes, out_kind, out);
+    if (rc) return rc;
+    if (slot < 0 || slot > 1) return fail(ctx, DSDGPU_ERR_ARG, "slot must be 0 or 1");
+    dsdgpu_slot& s = ctx->slots[slot];
+    if (s.busy) return fail(ctx, DSDGPU_ERR_STATE, "slot %d is still in flight", slot);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (nframes == 0) { s.busy = true; return DSDGPU_OK; }
+    // bytes this run of frames can touch, clipped to what the caller has
+    int64_t lo = p0 - (ctx->nlut - 1), hi = p0 + (nframes - 1) * ctx->nstep + 1;   // [lo, hi)
+    if (lo < in_first) lo = in_first;
+    if (hi > in_first + in_count) hi = in_first + in_count;
+    int64_t n = hi > lo ? hi - lo : 0;
+    const size_t dstride = ((size_t)n + 255) & ~(size_t)255;
+    rc = ensure(ctx, &s.d_in, &s.in_cap, dstride * ctx->nch + 256);
+    if (rc) return rc;
+    const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
+    const size_t out_bytes = (size_t)nframes * ctx->nch * elem;
+    rc = ensure(ctx, reinterpret_cast<unsigned char**>(&s.d_out), &s.out_cap, out_bytes);
+    if (rc) return rc;
+    if (n > 0)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
+                                        (size_t)ctx->nch, cudaMemcpyHostToDevice, s.stream));
+    rc = enqueue_decimate(ctx, s, s.d_in, dstride, lo, n, fill, p0, nframes, scale, dither_amp, clip,
+                          dither_first_sample, out_kind, s.d_out, s.stream);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    s.busy = true;
+    return DSDGPU_OK;
+}
+
+int dsdgpu_wait(dsdgpu_ctx* ctx, int slot) {
+    if (!ctx) return DSDGPU_ERR_ARG;
+    if (slot < 0 || slot > 1) return fail(ctx, DSDGPU_ERR_ARG, "slot must be 0 or 1");
+    dsdgpu_slot& s = ctx->slots[slot];
+    if (!s.busy) return fail(ctx, DSDGPU_ERR_STATE, "slot %d has nothing in flight", slot);
+    s.busy = false;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s.stream));
+    return DSDGPU_OK;
+}
+
+int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first,
+                         int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
+                         double dither_amp, double clip, uint64_t dither_first_sample, int out_kind,
+                         void* out) {
+    int rc = check_call(ctx, in, in_count, nframes, out_kind, out);
+    if (rc) return rc;
+    const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
+    const long long chunk = ctx->chunk_frames;
+    long long k = 0;
+    bool inflight[2] = {false, false};
+    for (int64_t f = 0; f < nframes; f += chunk, ++k) {
+        const int slot = (int)(k & 1);
+        if (inflight[slot]) { rc = dsdgpu_wait(ctx, slot); inflight[slot] = false; if (rc) break; }
+        const int64_t n = nframes - f < chunk ? nframes - f : chunk;
+        rc = dsdgpu_submit(ctx, slot, in, in_stride, in_first, in_count, fill, p0 + f * ctx->nstep, n, scale,
+                           dither_amp, clip, dither_first_sample + (uint64_t)f * ctx->nch, out_kind,
+                           static_cast<unsigned char*>(out) + (size_t)f * ctx->nch * elem);
+        if (rc) break;
+        inflight[slot] = true;
+    }
+    for (int s = 0; s < 2; ++s)
+        if (inflight[s]) { int r2 = dsdgpu_wait(ctx, s); if (!rc) rc = r2; }
+    return rc;
+}
+
+int dsdgpu_dither_fill_device(dsdgpu_ctx* ctx, uint64_t first_sample, int64_t count, double* d_out, void* cuda_stream) {
+    if (!ctx) return DSDGPU_ERR_ARG;
+    if (count < 0 || (count > 0 && !d_out)) return fail(ctx, DSDGPU_ERR_ARG, "bad dither request");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    int rc = launch_dither(ctx, ctx->own, first_sample, count, d_out, st);
+    if (rc) return rc;
+    if (!cuda_stream) CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return DSDGPU_OK;
+}
+
+}  // extern "C"

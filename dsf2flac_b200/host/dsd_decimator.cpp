@@ -1,0 +1,328 @@
+// dsd_decimator.cpp -- host side of the B200 drop-in DsdDecimator.
+//
+// Reference behaviour reproduced here (reference src/dsd_decimator.cpp):
+//   :44-72    ratio = dsdFs/outFs, nStep = ratio/8, filter by ratio, "Sorry, incompatible ..."
+//   :85-101   getLength / getPosition / getFirstValidSample / getLastValidSample
+//   :117-151  initLookupTable -> buildTables()
+//   :153-172  getSamples<int16|int32|int64|float32|float64>
+//   :182-186  bufferLen not a multiple of the channel count -> message on stderr + exit
+//   :191-221  the FIR + scale/dither/clip/round loop -> GPU, via include/dsdgpu.h
+// What differs by design: the reader is drained ahead of the consumer (a block of frames per
+// GPU round trip), so this class keeps its own LOGICAL position: step() and getSamples() move
+// `pos` exactly as reader->step() moved the reference's posMarker, and every position query is
+// answered from `pos`, never from how far the reader has been drained.
+#include "dsd_decimator.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "dsdgpu.h"
+
+namespace {
+
+struct FirSpec { int ratio, ntaps, tzero; const dsf2flac_uint64* bits; };
+
+#define DSD_FILTER_BEGIN(tag, ratio_, taps_, tzero_) \
+    const int tag##_ratio = ratio_, tag##_taps = taps_, tag##_tzero = tzero_; \
+    const dsf2flac_uint64 tag##_bits[taps_] = {
+#define DSD_FILTER_END(tag) };
+#include "dsd_filter_bits.inc"
+
+const FirSpec kFilters[3] = {
+    {div8_ratio, div8_taps, div8_tzero, div8_bits},
+    {div16_ratio, div16_taps, div16_tzero, div16_bits},
+    {div32_ratio, div32_taps, div32_tzero, div32_bits},
+};
+
+const FirSpec* findFilter(dsf2flac_uint32 ratio) {
+    for (const FirSpec& f : kFilters)
+        if ((dsf2flac_uint32)f.ratio == ratio) return &f;
+    return nullptr;
+}
+
+inline double tapValue(const FirSpec* f, int i) {
+    double d;
+    std::memcpy(&d, &f->bits[i], sizeof d);
+    return d;
+}
+
+const dsf2flac_uint32 kDefaultReadAhead = 1u << 20;
+
+}  // namespace
+
+DsdDecimator::DsdDecimator(DsdSampleReader *r, dsf2flac_uint32 rate)
+    : reader(r), outputSampleRate(rate), nLookupTable(0), tzero(0), ratio(0), nStep(0), valid(true),
+      gpu(nullptr), lutBits(64), pos(-1), harvested(0), samplesOut(0), bytes(nullptr), bytesStride(0),
+      bytesCap(0), bytesFirst(0), bytesCount(0), block(nullptr), blockCap(0), blockKind(0), blockPos(0),
+      blockFrames(0), blockSample0(0), blockScale(0), blockDither(0), blockClip(0),
+      readAhead(kDefaultReadAhead)
+{
+    ratio = rate ? r->getSamplingFreq() / rate : 0;
+    nStep = ratio / 8;
+    const FirSpec* f = findFilter(ratio);
+    if (!f) {
+        valid = false;
+        errorMsg = "Sorry, incompatible sample rate combination";
+        return;
+    }
+    tzero = (dsf2flac_uint32)f->tzero;
+    nLookupTable = (dsf2flac_uint32)((f->ntaps + 7) / 8);
+    buildTables(r->msbIsPlayedFirst() ? 1 : 0);
+    if (nLookupTable > reader->getBufferLength())
+        reader->setBufferLength(nLookupTable);
+    // logical marker = the reader's marker at hand-over (-1 right after rewind())
+    pos = reader->getPosition() / 8;
+    harvested = pos + 1;
+    bytesFirst = harvested;
+    openGpu(lutBits);
+}
+
+DsdDecimator::~DsdDecimator()
+{
+    if (gpu) dsdgpu_destroy(gpu);
+    if (bytes) dsdgpu_host_free(bytes);
+    if (block) dsdgpu_host_free(block);
+}
+
+// One 256-entry table per 8 taps; entries are the signed tap sums in bit order 0..k-1, tap
+// 8t+bit pairing with byte bit 7-bit when the reader says msbIsPlayedFirst, else with bit `bit`.
+void DsdDecimator::buildTables(int msbFlag)
+{
+    const FirSpec* f = findFilter(ratio);
+    tables.assign((size_t)nLookupTable * 256, 0.0);
+    for (dsf2flac_uint32 t = 0; t < nLookupTable; ++t) {
+        int k = f->ntaps - (int)t * 8;
+        if (k > 8) k = 8;
+        for (int seq = 0; seq < 256; ++seq) {
+            double acc = 0.0;
+            for (int bit = 0; bit < k; ++bit) {
+                const int on = msbFlag ? (seq >> (7 - bit)) & 1 : (seq >> bit) & 1;
+                const double val = -1 + 2 * (double)on;
+                acc += val * tapValue(f, (int)t * 8 + bit);
+            }
+            tables[(size_t)t * 256 + seq] = acc;
+        }
+    }
+}
+
+bool DsdDecimator::openGpu(int bits)
+{
+    if (gpu) { dsdgpu_destroy(gpu); gpu = nullptr; }
+    int device = 0;
+    if (const char* env = std::getenv("DSDGPU_DEVICE")) device = std::atoi(env);
+    const int rc = dsdgpu_create(&gpu, device, (int)reader->getNumChannels(), (int)nLookupTable, (int)nStep,
+                                 tables.data(), bits);
+    if (rc != DSDGPU_OK) {
+        fail(std::string("DsdDecimator: GPU path unavailable: ") + dsdgpu_last_error(nullptr));
+        gpu = nullptr;
+        return false;
+    }
+    lutBits = bits;
+    blockFrames = 0;
+    return true;
+}
+
+void DsdDecimator::fail(const std::string& why)
+{
+    valid = false;
+    errorMsg = why;
+}
+
+bool DsdDecimator::isValid() { return valid; }
+std::string DsdDecimator::getErrorMsg() { return errorMsg; }
+dsf2flac_uint32 DsdDecimator::getOutputSampleRate() { return outputSampleRate; }
+
+dsf2flac_int64 DsdDecimator::getLength() { return reader->getLength() / ratio; }
+
+dsf2flac_float64 DsdDecimator::getPosition()
+{
+    const dsf2flac_int64 dsdPos = pos * 8;
+    return (dsf2flac_float64)(dsdPos - tzero) / ratio;
+}
+
+dsf2flac_float64 DsdDecimator::getFirstValidSample()
+{
+    return (dsf2flac_float64)nLookupTable / nStep - (dsf2flac_float64)tzero / ratio;
+}
+
+dsf2flac_float64 DsdDecimator::getLastValidSample()
+{
+    return (dsf2flac_float64)getLength() - (dsf2flac_float64)tzero / ratio;
+}
+
+void DsdDecimator::step() { pos += 1; }
+
+void DsdDecimator::setReadAheadFrames(dsf2flac_uint32 frames) { readAhead = frames ? frames : 1; }
+
+bool DsdDecimator::setLutPrecision(int bits)
+{
+    if (bits != 64 && bits != 32) return false;
+    if (!valid && !gpu) return false;
+    return openGpu(bits);
+}
+
+// Pull bytes out of the reader until stream byte `hi` has been seen, keeping [lo, hi] (and
+// whatever later bytes were already drained) contiguous in `bytes`.  The reader can only move
+// forward one byte per step(), so anything before `lo` that was not drained yet is stepped over.
+void DsdDecimator::harvest(dsf2flac_int64 lo, dsf2flac_int64 hi)
+{
+    const dsf2flac_uint32 nch = reader->getNumChannels();
+    if (lo < bytesFirst) lo = bytesFirst;              // older bytes are gone (never needed again)
+    dsf2flac_int64 last = bytesFirst + bytesCount;      // one past the newest stored byte
+    if (hi < last - 1) hi = last - 1;
+    const size_t need = (size_t)(hi - lo + 1);
+    if (need > bytesStride) {
+        // grow: new pinned block, carry the still-needed tail over
+        const size_t stride = (need + need / 4 + 4095) & ~(size_t)4095;
+        dsf2flac_uint8* fresh = static_cast<dsf2flac_uint8*>(dsdgpu_host_alloc(stride * nch));
+        if (!fresh) { fail("DsdDecimator: pinned host allocation failed"); return; }
+        const dsf2flac_int64 keepFrom = lo < last ? lo : last;
+        const size_t keep = (size_t)(last - keepFrom);
+        for (dsf2flac_uint32 c = 0; c < nch; ++c)
+            if (keep) std::memcpy(fresh + c * stride, bytes + c * bytesStride + (keepFrom - bytesFirst), keep);
+        if (bytes) dsdgpu_host_free(bytes);
+        bytes = fresh; bytesStride = stride; bytesCap = stride * nch;
+        bytesFirst = keepFrom; bytesCount = (dsf2flac_int64)keep;
+    } else if ((size_t)(hi - bytesFirst + 1) > bytesStride) {
+        // slide the still-needed tail to the front
+        const dsf2flac_int64 keepFrom = lo < last ? lo : last;
+        const size_t keep = (size_t)(last - keepFrom);
+        for (dsf2flac_uint32 c = 0; c < nch; ++c)
+            if (keep) std::memmove(bytes + c * bytesStride, bytes + c * bytesStride + (keepFrom - bytesFirst), keep);
+        bytesFirst = keepFrom; bytesCount = (dsf2flac_int64)keep;
+    }
+    DsdByteRing* dummy = nullptr; (void)dummy;
+    auto* rings = reader->getBuffer();
+    while (harvested <= hi) {
+        reader->step();                                  // pushes byte number `harvested` of every channel
+        if (harvested >= lo) {
+            if (bytesCount == 0) bytesFirst = harvested;
+            const size_t k = (size_t)(harvested - bytesFirst);
+            for (dsf2flac_uint32 c = 0; c < nch; ++c) bytes[c * bytesStride + k] = rings[c][0];
+            bytesCount = (dsf2flac_int64)k + 1;
+        }
+        ++harvested;
+    }
+}
+
+bool DsdDecimator::refill(dsf2flac_uint32 wantFrames, dsf2flac_float64 scale, dsf2flac_float64 dither,
+                          dsf2flac_float64 clip, int outKind)
+{
+    if (!gpu) return false;
+    const dsf2flac_uint32 nch = reader->getNumChannels();
+    // how far ahead is worth computing: past the end of the data every byte is the idle byte
+    dsf2flac_int64 frames = readAhead;
+    const dsf2flac_int64 lastDataByte = reader->getLength() / 8 + 1;
+    dsf2flac_int64 useful = (lastDataByte + (dsf2flac_int64)nLookupTable - pos) / (dsf2flac_int64)nStep + 1;
+    if (useful < 1) useful = 1;
+    if (frames > useful) frames = useful;
+    if (frames < (dsf2flac_int64)wantFrames) frames = wantFrames;
+
+    const dsf2flac_int64 lo = pos - ((dsf2flac_int64)nLookupTable - 1);
+    const dsf2flac_int64 hi = pos + (frames - 1) * (dsf2flac_int64)nStep;
+    harvest(lo, hi);
+    if (!valid) return false;
+
+    const size_t elem = outKind == DSDGPU_OUT_INT32 ? sizeof(dsf2flac_int32) : sizeof(double);
+    const size_t needOut = (size_t)frames * nch * elem;
+    if (needOut > blockCap) {
+        if (block) dsdgpu_host_free(block);
+        block = dsdgpu_host_alloc(needOut);
+        blockCap = block ? needOut : 0;
+        if (!block) { fail("DsdDecimator: pinned host allocation failed"); return false; }
+    }
+    const int rc = dsdgpu_decimate_host(gpu, bytes, bytesStride, bytesFirst, bytesCount, reader->getIdleSample(),
+                                        pos, frames, scale, dither, clip, samplesOut, outKind, block);
+    if (rc != DSDGPU_OK) {
+        fail(std::string("DsdDecimator: GPU decimation failed: ") + dsdgpu_last_error(gpu));
+        blockFrames = 0;
+        return false;
+    }
+    blockKind = outKind; blockPos = pos; blockFrames = frames; blockSample0 = samplesOut;
+    blockScale = scale; blockDither = dither; blockClip = clip;
+    return true;
+}
+
+template <typename T, typename Conv>
+void DsdDecimator::serve(T* buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 dither,
+                         dsf2flac_float64 clip, int outKind, Conv conv)
+{
+    const dsf2flac_uint32 nch = reader->getNumChannels();
+    const ldiv_t d = ldiv(bufferLen, nch);
+    if (d.rem) {
+        fputs("Buffer length is not a multiple of getNumChannels()", stderr);
+        exit(EXIT_FAILURE);
+    }
+    dsf2flac_uint32 frames = (dsf2flac_uint32)d.quot, done = 0;
+    while (done < frames) {
+        // is the current position inside the cached block, on its frame grid, same parameters,
+        // and at the same place in the dither stream?
+        dsf2flac_int64 idx = -1;
+        if (blockFrames > 0 && blockKind == outKind && blockScale == scale && blockDither == dither &&
+            blockClip == clip && pos >= blockPos && (pos - blockPos) % nStep == 0) {
+            idx = (pos - blockPos) / nStep;
+            if (idx >= blockFrames || blockSample0 + (dsf2flac_uint64)idx * nch != samplesOut) idx = -1;
+        }
+        if (idx < 0) {
+            if (!refill(frames - done, scale, dither, clip, outKind)) {
+                // GPU path failed: there is deliberately no CPU fallback; hand back silence
+                for (dsf2flac_uint32 i = done * nch; i < frames * nch; ++i) buffer[i] = T(0);
+                pos += (dsf2flac_int64)(frames - done) * nStep;
+                samplesOut += (dsf2flac_uint64)(frames - done) * nch;
+                return;
+            }
+            idx = 0;
+        }
+        dsf2flac_int64 n = blockFrames - idx;
+        if (n > (dsf2flac_int64)(frames - done)) n = frames - done;
+        conv(buffer + (size_t)done * nch, block, (size_t)idx * nch, (size_t)n * nch);
+        done += (dsf2flac_uint32)n;
+        pos += n * (dsf2flac_int64)nStep;
+        samplesOut += (dsf2flac_uint64)n * nch;
+    }
+}
+
+namespace {
+template <typename T>
+struct RoundFromDouble {          // static_cast<T>(round(sum)), reference dsd_decimator.cpp:213-214
+    void operator()(T* dst, const void* blk, size_t first, size_t count) const {
+        const double* src = static_cast<const double*>(blk) + first;
+        for (size_t i = 0; i < count; ++i) dst[i] = static_cast<T>(std::round(src[i]));
+    }
+};
+template <typename T>
+struct CastFromDouble {           // static_cast<T>(sum), reference dsd_decimator.cpp:215-216
+    void operator()(T* dst, const void* blk, size_t first, size_t count) const {
+        const double* src = static_cast<const double*>(blk) + first;
+        for (size_t i = 0; i < count; ++i) dst[i] = static_cast<T>(src[i]);
+    }
+};
+struct CopyInt32 {                // rounded on the GPU already
+    void operator()(dsf2flac_int32* dst, const void* blk, size_t first, size_t count) const {
+        std::memcpy(dst, static_cast<const dsf2flac_int32*>(blk) + first, count * sizeof(dsf2flac_int32));
+    }
+};
+}  // namespace
+
+template<> void DsdDecimator::getSamples(dsf2flac_int16 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
+{
+    serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_FLOAT64, RoundFromDouble<dsf2flac_int16>());
+}
+template<> void DsdDecimator::getSamples(dsf2flac_int32 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
+{
+    serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_INT32, CopyInt32());
+}
+template<> void DsdDecimator::getSamples(dsf2flac_int64 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
+{
+    serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_FLOAT64, RoundFromDouble<dsf2flac_int64>());
+}
+template<> void DsdDecimator::getSamples(dsf2flac_float32 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
+{
+    serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_FLOAT64, CastFromDouble<dsf2flac_float32>());
+}
+template<> void DsdDecimator::getSamples(dsf2flac_float64 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
+{
+    serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_FLOAT64, CastFromDouble<dsf2flac_float64>());
+}

@@ -1,0 +1,100 @@
+// dsd_decimator.h -- B200 drop-in for the reference's DsdDecimator.
+//
+// The public section is the reference's operator surface (reference src/dsd_decimator.h:62-127):
+// same class name, same member names, same argument meaning, so main.cpp, the DSF/DSDIFF
+// readers, the DoP packer, tag conversion and the FLAC encode loop compile and link unchanged
+// against this header + dsd_decimator.cpp + libdsdgpu.so.  Everything below
+// `private:` is new: the FIR no longer runs in getSamples() on the CPU, it runs on the GPU
+// through the C ABI of include/dsdgpu.h, a large block of frames at a time.
+#ifndef DSDDECIMATOR_H
+#define DSDDECIMATOR_H
+
+#include <string>
+#include <vector>
+
+#include "dsd_sample_reader.h"
+
+struct dsdgpu_ctx;
+
+class DsdDecimator
+{
+public:
+    // reference dsd_decimator.h:72 -- reader must be valid; rate must divide the DSD rate by 8, 16 or 32
+    DsdDecimator(DsdSampleReader *reader, dsf2flac_uint32 outputSampleRate);
+    virtual ~DsdDecimator();
+
+    bool isValid();
+    std::string getErrorMsg();
+
+    dsf2flac_uint32 getOutputSampleRate();
+    dsf2flac_uint32 getDecimationRatio() { return ratio; }
+    dsf2flac_int64 getLength();                                   // PCM samples
+    dsf2flac_uint32 getNumChannels() { return reader->getNumChannels(); }
+    dsf2flac_float64 getPosition();                               // PCM samples
+    dsf2flac_float64 getPositionInSeconds() { return getPosition() / outputSampleRate; }
+    dsf2flac_float64 getPositionAsPercent() { return getPosition() / getLength() * 100; }
+    dsf2flac_float64 getFirstValidSample();
+    dsf2flac_float64 getLastValidSample();
+    void step();                                                  // forward by 8 DSD samples
+
+    // bufferLen = frames * getNumChannels(), interleaved; int16/int32/int64 round half away from
+    // zero, float32/float64 are not rounded (reference dsd_decimator.h:96-121, .cpp:153-172)
+    template <typename sampleType> void getSamples(
+            sampleType *buffer,
+            dsf2flac_uint32 bufferLen,
+            dsf2flac_float64 scale,
+            dsf2flac_float64 tpdfDitherPeakAmplitude = 0,
+            dsf2flac_float64 clipAmplitude = 0);
+
+    // --- additions (not in the reference) ---------------------------------------------------
+    // Frames decimated per GPU round trip; larger = fewer, bigger transfers. Default 1<<20.
+    void setReadAheadFrames(dsf2flac_uint32 frames);
+    // 64 (default, bit-exact) or 32 (fp32 tables, fp64 accumulate). Takes effect immediately.
+    bool setLutPrecision(int bits);
+
+private:
+    void buildTables(int msbFlag);
+    bool openGpu(int lutBits);
+    void fail(const std::string& why);
+    // make stream bytes [lo, hi] of every channel available in `bytes`
+    void harvest(dsf2flac_int64 lo, dsf2flac_int64 hi);
+    // run the GPU over `frames` frames starting at logical position pos into `block`
+    bool refill(dsf2flac_uint32 wantFrames, dsf2flac_float64 scale, dsf2flac_float64 dither,
+                dsf2flac_float64 clip, int outKind);
+    // copy `frames` frames at the current position out of `block`, refilling as needed
+    template <typename T, typename Conv>
+    void serve(T* buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 dither,
+               dsf2flac_float64 clip, int outKind, Conv conv);
+
+    DsdSampleReader *reader;
+    dsf2flac_uint32 outputSampleRate;
+    dsf2flac_uint32 nLookupTable;
+    dsf2flac_uint32 tzero;
+    dsf2flac_uint32 ratio;
+    dsf2flac_uint32 nStep;
+    bool valid;
+    std::string errorMsg;
+
+    std::vector<double> tables;          // [nLookupTable][256], built as the reference builds them
+    dsdgpu_ctx* gpu;
+    int lutBits;
+
+    dsf2flac_int64 pos;                  // logical reader marker: newest byte the consumer has reached
+    dsf2flac_int64 harvested;            // reader->step() calls made so far (bytes 0..harvested-1 seen)
+    dsf2flac_uint64 samplesOut;          // output samples handed out (dither stream position)
+
+    dsf2flac_uint8* bytes;               // pinned, planar [nch][bytesStride]; bytes[c][k] = stream byte bytesFirst+k
+    size_t bytesStride, bytesCap;
+    dsf2flac_int64 bytesFirst, bytesCount;
+
+    void* block;                         // pinned output of the last GPU run
+    size_t blockCap;
+    int blockKind;                       // DSDGPU_OUT_*
+    dsf2flac_int64 blockPos;             // logical position of frame 0 of the block
+    dsf2flac_int64 blockFrames;
+    dsf2flac_uint64 blockSample0;        // samplesOut at frame 0
+    dsf2flac_float64 blockScale, blockDither, blockClip;
+    dsf2flac_uint32 readAhead;
+};
+
+#endif // DSDDECIMATOR_H

@@ -1,0 +1,141 @@
+/*
+ * dsdgpu.h -- C ABI of the B200 (sm_100a) DSD->PCM decimation path.
+ *
+ * This is the whole boundary between a C++ host (dsf2flac's DsdDecimator, see
+ * dsf2flac_b200/host/dsd_decimator.cpp and INTEGRATION.md) and the CUDA side
+ * (dsf2flac_b200/csrc/dsdgpu.cu).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * The operator it implements is the body of the reference's
+ *   DsdDecimator::getSamplesInternal            (reference src/dsd_decimator.cpp:173-222)
+ * for frames i = 0..nframes-1 and channels c = 0..nch-1:
+ *
+ *   p_i  = p0 + i*nstep                                   (index of the newest byte of frame i)
+ *   sum  = 0.0; for t = 0..nlut-1: sum += lut[t][ B_c(p_i - t) ]   (fp64, this order)
+ *   v    = sum*scale;  if dither_amp>0: v += (r1-r2)*dither_amp;  if clip>0: clamp to +-clip
+ *   out[i*nch + c] = (int32) round(v)        (half away from zero)   |  = v   (f64 output)
+ *
+ * B_c(j) is byte j of channel c of the packed DSD stream: in[c*in_stride + (j - in_first)] for
+ * in_first <= j < in_first+in_count and `fill` everywhere else (the reference reader's idle
+ * byte 0x69 before the start and after the end of data, dsd_sample_reader.h:122,
+ * dsf_file_reader.cpp:94-97).  r1, r2 are the glibc rand() draws number 2m and 2m+1
+ * (divided by RAND_MAX), m = dither_first_sample + i*nch + c, i.e. exactly what an unseeded
+ * reference process draws for its m-th output sample (dsd_decimator.cpp:201-206).
+ *
+ * Every function returns 0 on success and a non-zero code on failure; the text is available
+ * from dsdgpu_last_error().  There is no CPU fallback: without a usable CUDA device create
+ * fails.  A context is not thread-safe; use one per host thread / per GPU.  No global state.
+ */
+#ifndef DSDGPU_H
+#define DSDGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dsdgpu_ctx dsdgpu_ctx;
+
+enum {
+    DSDGPU_OK = 0,
+    DSDGPU_ERR_ARG = 1,      /* bad argument (also: bufferLen not a multiple of nch upstream) */
+    DSDGPU_ERR_CUDA = 2,     /* a CUDA runtime call failed */
+    DSDGPU_ERR_NODEVICE = 3, /* no CUDA device / device is not usable */
+    DSDGPU_ERR_STATE = 4     /* wait without submit, slot busy, ... */
+};
+
+enum { DSDGPU_OUT_INT32 = 0, DSDGPU_OUT_FLOAT64 = 1 };
+
+/* Kernel selection, for tests and benchmarking (dsdgpu_set_option "kernel"). */
+enum {
+    DSDGPU_KERNEL_AUTO = 0,   /* skewed kernel when the geometry supports it, else direct */
+    DSDGPU_KERNEL_DIRECT = 1, /* one thread per output sample, tables [t][byte] in smem */
+    DSDGPU_KERNEL_SKEW = 2    /* bank-conflict-free lane-skewed kernel (divide-by-32 filters) */
+};
+
+/*
+ * Replaces: DsdDecimator::DsdDecimator + initLookupTable (dsd_decimator.cpp:44-72,117-151).
+ * The caller builds the nlut x 256 table on the host exactly as initLookupTable does and hands
+ * it over; the context uploads it (re-laid out for shared memory) and owns all device state.
+ *   device        CUDA device ordinal
+ *   nch           channels (>=1)
+ *   nlut, nstep   nLookupTable and nStep of the reference (72/4, 30/2, 12/1; any nlut<=96 works)
+ *   lut           [nlut][256] doubles, row t = table t
+ *   lut_precision 64: tables kept in fp64 (bit-exact path); 32: tables rounded to fp32 and
+ *                 accumulated in fp64 (within +-1 LSB at 24 bit)
+ */
+int dsdgpu_create(dsdgpu_ctx** ctx, int device, int nch, int nlut, int nstep, const double* lut,
+                  int lut_precision);
+
+/* Replaces: DsdDecimator::~DsdDecimator (dsd_decimator.cpp:74-83). NULL is allowed. */
+void dsdgpu_destroy(dsdgpu_ctx* ctx);
+
+/* Last error text of this context (ctx == NULL: of the last failed dsdgpu_create in this thread).
+ * Maps to DsdDecimator::getErrorMsg (dsd_decimator.cpp:113-115). */
+const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
+
+/* Tuning knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk),
+ * "threads" (skew kernel CTA size, 512 or 1024). Unknown keys are an error. */
+int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+unsigned long long dsdgpu_kernel_launches(const dsdgpu_ctx* ctx);
+
+/* Pinned host memory for the buffers handed to the *_host / submit calls (pageable memory
+ * works too, pinned memory is what lets the copies overlap the kernel). */
+void* dsdgpu_host_alloc(size_t bytes);
+void dsdgpu_host_free(void* p);
+
+/*
+ * Replaces: the loop body of getSamplesInternal (dsd_decimator.cpp:191-221) for a whole run of
+ * frames, with every pointer a DEVICE pointer.  Asynchronous on `cuda_stream` (a cudaStream_t
+ * passed as void*; NULL = the context's own stream, which is then synchronised before return).
+ *   d_in, in_stride, in_first, in_count, fill   the byte source B_c(j) as defined above
+ *   p0, nframes                                 first frame position and number of frames
+ *   scale, dither_amp, clip                     as main.cpp:239-245 computes them
+ *   dither_first_sample                         m of the first output sample (frame-major)
+ *   out_kind, d_out                             DSDGPU_OUT_INT32 -> int32[nframes][nch],
+ *                                               DSDGPU_OUT_FLOAT64 -> double[nframes][nch]
+ */
+int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_stride,
+                           int64_t in_first, int64_t in_count, uint8_t fill, int64_t p0,
+                           int64_t nframes, double scale, double dither_amp, double clip,
+                           uint64_t dither_first_sample, int out_kind, void* d_out,
+                           void* cuda_stream);
+
+/*
+ * Same operator with HOST buffers: uploads the bytes, runs the kernel, downloads the PCM,
+ * internally cut into chunks that are double-buffered over two slots so that the upload of
+ * chunk k+1, the kernel of chunk k and the download of chunk k-1 overlap.  Synchronous.
+ * This is what DsdDecimator::getSamples calls (dsd_decimator.cpp:157-159).
+ */
+int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first,
+                         int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes,
+                         double scale, double dither_amp, double clip,
+                         uint64_t dither_first_sample, int out_kind, void* out);
+
+/*
+ * The two halves of the above for callers that want to overlap their own work (reader drain,
+ * FLAC encode) with the GPU: submit() enqueues upload + kernel + download of one chunk on slot
+ * 0 or 1 and returns at once; wait() blocks until that slot's output is in `out`.
+ * Host buffers must stay untouched between submit and wait.
+ */
+int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride,
+                  int64_t in_first, int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes,
+                  double scale, double dither_amp, double clip, uint64_t dither_first_sample,
+                  int out_kind, void* out);
+int dsdgpu_wait(dsdgpu_ctx* ctx, int slot);
+
+/*
+ * Fills d_out[0..count) (device doubles) with the dither term (r1 - r2) of output samples
+ * first_sample .. first_sample+count-1, r = rand()/RAND_MAX of an unseeded glibc process
+ * (dsd_decimator.cpp:203-204).  Exposed for tests of the generator.
+ */
+int dsdgpu_dither_fill_device(dsdgpu_ctx* ctx, uint64_t first_sample, int64_t count, double* d_out,
+                              void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSDGPU_H */
