@@ -1,0 +1,41 @@
+# Builds everything in-tree (the .so files are git-ignored but travel to the GPU box).
+#   make gpu     dsf2flac_b200/libdsdgpu.so    CUDA kernels + the C ABI of include/dsdgpu.h (sm_100a)
+#   make host    dsf2flac_b200/libdsdhost.so   drop-in DsdDecimator + a C-ABI driver for the tests
+#   make oracle  oracle/_build, oracle/_ref    the CPU checkers (test infrastructure only)
+#   make tests   tests/cpp/_build/*            lane emulator, CPU stand-in of the C ABI for host-logic tests
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+PKG := dsf2flac_b200
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall \
+           -I include -I $(PKG)/csrc
+HOSTSRC := $(PKG)/host/dsd_decimator.cpp $(PKG)/host/dsdhost_capi.cpp $(PKG)/host/dsd_synth.cpp
+HOSTHDR := $(wildcard $(PKG)/host/*.h) $(PKG)/host/dsd_filter_bits.inc include/dsdgpu.h
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -I include -I $(PKG)/host
+
+all: gpu host oracle tests
+
+gpu: $(PKG)/libdsdgpu.so
+$(PKG)/libdsdgpu.so: $(wildcard $(PKG)/csrc/*.cpp) $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.h) $(wildcard $(PKG)/csrc/*.cuh) include/dsdgpu.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cpp)
+
+host: $(PKG)/libdsdhost.so
+$(PKG)/libdsdhost.so: $(HOSTSRC) $(HOSTHDR) $(PKG)/libdsdgpu.so
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) -L$(PKG) -ldsdgpu -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle all
+
+tests: tests/cpp/_build/emu_skew tests/cpp/_build/libdsdhost_cpu.so
+tests/cpp/_build/emu_skew: tests/cpp/emu_skew.cpp $(PKG)/csrc/skew_core.h
+	mkdir -p tests/cpp/_build
+	$(CXX) -O2 -std=c++17 -I $(PKG)/csrc -o $@ tests/cpp/emu_skew.cpp
+# the same host sources linked against a CPU stand-in of the C ABI (tests only, never shipped)
+tests/cpp/_build/libdsdhost_cpu.so: $(HOSTSRC) $(HOSTHDR) tests/cpp/standin_dsdgpu.cpp
+	mkdir -p tests/cpp/_build
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) tests/cpp/standin_dsdgpu.cpp
+
+clean:
+	rm -rf $(PKG)/*.so tests/cpp/_build
+	$(MAKE) -C oracle clean
+
+.PHONY: all gpu host oracle tests clean

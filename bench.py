@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- DSD->PCM decimation throughput on B200 (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2]
+
+A step is one pass of the hot path (reference DsdDecimator::getSamples, dsd_decimator.cpp:173-222,
+as main.cpp:169-191 drives it for one whole file) over one synthetic sigma-delta stream per GPU.
+Default workload: BASELINE.json configs[1] -- DSD128 stereo, 60 s -> 24 bit / 176.4 kHz, fp64
+tables, TPDF dither off (the bit-exact parity setting).  Weak scaling: every rank converts its
+own stream, no data-path collective (shards are independent).
+
+Printed (rank 0, one JSON line):
+  value   whole-job DSD Mbit/s, inputs resident in HBM, K steps timed with CUDA events
+  e2e     the same through dsdgpu_decimate_host: pinned host bytes in, host PCM out, copies timed
+  roofline  the decimation kernel against the shared-memory (LUT gather) roofline + HBM figures
+  cpu_baseline  the reference's own decimator (oracle/_ref, or the oracle port) on the host cores
+--impl reference times that CPU path alone on the same workload (rank 0 only).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DSD64 = 2822400
+WORKLOADS = {
+    # name: (dsd_fs, out_fs, nch, seconds, bits, description)
+    "c1": (DSD64, 88200, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/88.2 kHz (BASELINE configs[0])"),
+    "c2": (2 * DSD64, 176400, 2, 60, 24, "DSD128 stereo 60 s -> 24-bit/176.4 kHz, fp64 LUT (BASELINE configs[1])"),
+}
+SMEM_BYTES_PER_CLK_PER_SM = 128
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def synth_stream(dsd_fs, nch, seconds, lsb_first=1):
+    """One second of 2nd-order sigma-delta sine per channel (host/dsd_synth.cpp), tiled."""
+    from dsf2flac_b200 import capi
+    host = capi.host_lib()
+    sec = dsd_fs // 8
+    one = np.empty((nch, sec), dtype=np.uint8)
+    for c in range(nch):
+        host.dsdhost_synth_sdm(one[c].ctypes.data, sec, float(dsd_fs), 1000.0 + 500.0 * c, 0.5, lsb_first)
+    return np.ascontiguousarray(np.tile(one, (1, seconds)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 8] or [r for (_, r) in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+# ---- CPU baseline (test infrastructure: oracle/_ref = the unmodified reference decimator) -----
+
+_CPU_DATA = None        # inherited by the forked workers (no pickling of the stream)
+
+
+def _cpu_worker(args):
+    seg_bytes, k, dsd_fs, out_fs, nlut, nstep, scale, clip = args
+    data = _CPU_DATA
+    from tests.oracle_lib import Oracle, REF_SO
+    orc = Oracle(reference=os.path.exists(REF_SO))
+    lo = k * seg_bytes
+    sub = np.ascontiguousarray(data[:, lo:lo + seg_bytes])
+    nframes = (seg_bytes - nlut) // nstep
+    t0 = time.perf_counter()
+    orc.run_raw(sub, 1 << 40, 1, dsd_fs, out_fs, nlut + 1, nframes, scale, 0.0, clip)
+    return nframes * nstep * 8 * data.shape[0], time.perf_counter() - t0
+
+
+def cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, sample_seconds, pool=None):
+    """The reference's CPU decimator (getSamples loop only, like the GPU arm: no FLAC, no file
+    parsing) over the first `sample_seconds` of the stream, one process per core (the reference
+    is single threaded and keeps process-global state, so cores = processes).  -> (Mbit/s, bits)"""
+    from tests.oracle_lib import REF_SO
+    nbytes = min(data.shape[1], int(dsd_fs // 8 * sample_seconds))
+    seg = nbytes // cores // 4 * 4
+    jobs = [(seg, k, dsd_fs, out_fs, fir.nlut, fir.nstep, scale, clip) for k in range(cores)]
+    own = pool is None
+    if own:
+        global _CPU_DATA
+        _CPU_DATA = data
+        pool = mp.get_context("fork").Pool(cores)
+        pool.map(abs, range(cores))                        # workers up before the clock starts
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    if own:
+        pool.close()
+    bits = sum(r[0] for r in res)
+    return bits / wall / 1e6, bits, ("reference" if os.path.exists(REF_SO) else "port")
+
+
+def run_reference_arm(args, wl):
+    dsd_fs, out_fs, nch, seconds, bits_depth, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dsf2flac_b200 import filters
+    fir = filters.pick(dsd_fs, out_fs)
+    scale, _, clip = filters.app_params(bits_depth, dither=False)
+    cores = len(os.sched_getaffinity(0))
+    global _CPU_DATA
+    data = _CPU_DATA = synth_stream(dsd_fs, nch, min(seconds, 20))
+    pool = mp.get_context("fork").Pool(cores)
+    # size the per-step sample so that the whole run stays within ~2 minutes
+    probe, _, kind = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, 1.0, pool)
+    budget_s = 100.0 / max(1, args.steps + args.warmup)
+    sample_seconds = max(0.25, min(data.shape[1] * 8 / dsd_fs, budget_s * probe * 1e6 / (dsd_fs * nch)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, sample_seconds, pool)
+    t0 = time.perf_counter()
+    total_bits = 0
+    for _ in range(args.steps):
+        _, b, _ = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, sample_seconds, pool)
+        total_bits += b
+    wall = time.perf_counter() - t0
+    pool.close()
+    v = total_bits / wall / 1e6
+    sample = f"first {sample_seconds:.2f} s of the stream per step, split over {cores} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": "dsd_mbit_per_s", "value": v, "unit": "Mbit/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "x_realtime": v * 1e6 / (dsd_fs * nch),
+        "config": {"workload": desc, "dither": False, "lut": "fp64"},
+        "cpu_baseline": {"value": v, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------
+
+def run_gpu_arm(args, wl):
+    import torch
+    import torch.distributed as dist
+    from dsf2flac_b200 import capi, filters
+
+    dsd_fs, out_fs, nch, seconds, bits_depth, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fir = filters.pick(dsd_fs, out_fs)
+    lut = filters.build_lut(fir, 1)
+    scale, amp, clip = filters.app_params(bits_depth, dither=args.dither)
+    data = synth_stream(dsd_fs, nch, seconds)
+    nbytes = data.shape[1]
+    nframes = filters.app_frames(nbytes * 8, fir)
+    bits_per_step = nbytes * 8 * nch                       # DSD bits consumed per step per GPU
+    g = capi.DsdGpu(lut, nch, fir.nstep, device=local, lut_precision=args.lut)
+    if args.kernel:
+        g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2}[args.kernel])
+    if args.threads:
+        g.set_option("threads", args.threads)
+
+    # device-resident ring of distinct input/output buffers, larger than L2 in total, so no step
+    # finds its bytes in L2 from the step before
+    in_bytes, out_bytes = nch * nbytes, nframes * nch * 4
+    ring = max(2, -(-2 * L2_BYTES // (in_bytes + out_bytes)))
+    d_in = [torch.from_numpy(np.roll(data, 4096 * k, axis=1)).cuda() for k in range(ring)]
+    d_out = [torch.empty((nframes, nch), dtype=torch.int32, device="cuda") for _ in range(ring)]
+    stream = torch.cuda.Stream()
+
+    def step(k):
+        g.decimate_device(d_in[k % ring], nbytes, 0, nbytes, 0x69, fir.nlut, nframes, scale, amp, clip, 0, capi.OUT_INT32,
+                          d_out[k % ring], stream=stream.cuda_stream)
+
+    with torch.cuda.stream(stream):
+        for k in range(args.warmup):
+            step(k)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = g.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for k in range(args.steps):
+            step(k)
+            ev[k + 1].record(stream)
+    stream.synchronize()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = g.launches - launches0
+    dev_ms = ev[0].elapsed_time(ev[-1])
+    per_step = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
+    total_ms = max_over_ranks(dev_ms)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---- end to end: host bytes -> PCM on the host, through the C ABI with host buffers -------
+    pin_in = capi.PinnedBuffer((nch, nbytes), np.uint8)
+    pin_in.array[:] = data
+    pin_out = capi.PinnedBuffer((nframes, nch), np.int32)
+
+    def e2e_step():
+        g.decimate_host_raw(pin_in.ptr, nbytes, 0, nbytes, 0x69, fir.nlut, nframes, scale, amp, clip, 0, capi.OUT_INT32,
+                            pin_out.ptr)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()                                         # synchronous: returns when the PCM is on the host
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    checksum = int(pin_out.array[:: max(1, nframes // 65536)].astype(np.int64).sum())
+
+    # ---- the drop-in class itself (reader drained byte by byte, as dsf2flac would run it) -----
+    plugin = None
+    if rank == 0 and args.plugin_seconds > 0:
+        host = capi.host_lib()
+        pb = min(nbytes, int(dsd_fs // 8 * args.plugin_seconds))
+        cap = pb + 2048
+        out = np.empty((cap, nch), dtype=np.int32)
+        t0 = time.perf_counter()
+        n = host.dsdhost_run_app(pin_in.ptr, nch, nbytes, pb * 8, 0x69, 1, dsd_fs, out_fs, scale, amp, clip, args.lut, 0,
+                                 out.ctypes.data, cap)
+        dt = time.perf_counter() - t0
+        if n > 0:
+            plugin = {"value": pb * 8 * nch / dt / 1e6, "unit": "Mbit/s", "sample": f"first {args.plugin_seconds:g} s",
+                      "note": "DsdDecimator::getSamples in 1024-frame calls over a byte-at-a-time DsdSampleReader"}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        value = bits_per_step * args.steps * world / (total_ms * 1e-3) / 1e6
+        kernel_ms = per_step[len(per_step) // 2]
+        samples_per_launch = nframes * nch
+        lut_elem = 8 if args.lut == 64 else 4
+        smem_bytes = samples_per_launch * fir.nlut * lut_elem          # algorithmic LUT bytes per launch
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        smem_peak = n_sm * SMEM_BYTES_PER_CLK_PER_SM * peaks["sm_max_mhz"] * 1e6 / 1e9
+        achieved = smem_bytes / (kernel_ms * 1e-3) / 1e9
+        hbm_bytes = samples_per_launch * (fir.nstep + 4)
+        roof = {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+                "traffic": None, "peak_source": f"{n_sm} SMs x 128 B/clk x sm_max_mhz ({peak_src})",
+                "algorithmic_bytes_per_sample": fir.nlut * lut_elem, "samples_per_launch": samples_per_launch,
+                "kernel_ms": kernel_ms,
+                "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "algorithmic_bytes_per_sample": fir.nstep + 4, "peak_source": peak_src}}
+        if clocks and clocks.get("sm_mhz"):
+            roof["frac_at_sampled_clock"] = achieved / (n_sm * SMEM_BYTES_PER_CLK_PER_SM * clocks["sm_mhz"] * 1e6 / 1e9)
+        # CPU baseline: bounded sample on the host cores
+        cores = len(os.sched_getaffinity(0))
+        cpu = None
+        if world == 1 and args.cpu_seconds > 0:
+            v, b, kind = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, args.cpu_seconds)
+            v1, b1, _ = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, 1, min(args.cpu_seconds, 4.0))
+            cpu = {"value": v, "unit": "Mbit/s", "cores": cores, "kind": kind,
+                   "sample": f"first {args.cpu_seconds:g} s of the stream, one process per core, decimator only",
+                   "one_core": {"value": v1, "unit": "Mbit/s", "cores": 1, "x_realtime": v1 * 1e6 / (dsd_fs * nch)}}
+        e2e_value = bits_per_step * args.steps * world / e2e_s / 1e6
+        print(json.dumps({
+            "metric": "dsd_mbit_per_s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "per_gpu_mbit_per_s": value / world, "x_realtime": value * 1e6 / (dsd_fs * nch) / 1.0,
+            "config": {"workload": desc, "dither": bool(args.dither), "lut": f"fp{args.lut}",
+                       "kernel": args.kernel or "auto", "frames_per_step": nframes, "channels": nch,
+                       "l2": f"ring of {ring} distinct in/out buffer sets ({(in_bytes + out_bytes) * ring >> 20} MiB) > L2",
+                       "parallelism": f"{world} x independent streams, no collective"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": e2e_s / args.steps * 1e3, "x_realtime": e2e_value * 1e6 / (dsd_fs * nch),
+                    "api": "dsdgpu_decimate_host (pinned host buffers, double-buffered chunks)", "checksum": checksum},
+            "plugin": plugin, "gpu_launches": launches, "clocks": clocks,
+        }), flush=True)
+    pin_in.free()
+    pin_out.free()
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--dither", type=int, default=0)
+    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew"])
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="length of the CPU-baseline sample (stream seconds)")
+    ap.add_argument("--plugin-seconds", type=float, default=2.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_gpu_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

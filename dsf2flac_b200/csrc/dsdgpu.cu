@@ -42,7 +42,8 @@ struct DecimateArgs {
     int nch;
     unsigned fill;
     const void* lut;         // kernel specific layout
-    const double* dither;    // (r1 - r2) per output sample [nframes*nch], or nullptr
+    const double* dither;    // (r1 - r2) per output sample, [frame*dither_stride + c], or nullptr
+    long long dither_stride; // samples per frame of the whole stream (>= nch)
     double scale, dither_amp, clip;
     void* out;
     int out_kind;
@@ -63,7 +64,7 @@ __device__ __forceinline__ double quantise_tail(double sum, double scale, double
 
 __device__ __forceinline__ void store_sample(const DecimateArgs& a, long long frame, int c, double sum) {
     const long long m = frame * a.nch + c;
-    const double dith = (a.dither != nullptr) ? a.dither[m] : 0.0;
+    const double dith = (a.dither != nullptr) ? a.dither[frame * a.dither_stride + c] : 0.0;
     const double v = quantise_tail(sum, a.scale, a.dither_amp, dith, a.clip);
     if (a.out_kind == DSDGPU_OUT_INT32) {
         // C round(): half away from zero (dsd_decimator.cpp:213-214)
@@ -303,6 +304,7 @@ struct dsdgpu_ctx {
     int sm_count = 0;
     int kernel = DSDGPU_KERNEL_AUTO;
     int threads = 512;
+    int dither_stride = 0;                   // 0 = nch
     long long chunk_frames = 1LL << 21;
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
@@ -437,10 +439,11 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     DecimateArgs a;
     a.in = d_in; a.in_stride = (long long)in_stride; a.in_first = in_first; a.in_count = in_count;
     a.p0 = p0; a.nframes = nframes; a.nch = ctx->nch; a.fill = fill;
-    a.dither = nullptr; a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
+    a.dither = nullptr; a.dither_stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
+    a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
     a.out = d_out; a.out_kind = out_kind;
     if (dither_amp > 0.0) {
-        const long long count = nframes * ctx->nch;
+        const long long count = (nframes - 1) * a.dither_stride + ctx->nch;
         int rc = ensure(ctx, &scratch.d_dither, &scratch.dither_cap, (size_t)count * sizeof(double));
         if (rc) return rc;
         rc = launch_dither(ctx, scratch, dither_first_sample, count, scratch.d_dither, st);
@@ -556,6 +559,9 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "threads")) {
         if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
         ctx->threads = (int)value;
+    } else if (!strcmp(key, "dither_stride")) {
+        if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");
+        ctx->dither_stride = (int)value;
     } else if (!strcmp(key, "chunk_frames")) {
         if (value < 1) return fail(ctx, DSDGPU_ERR_ARG, "chunk_frames must be >= 1");
         ctx->chunk_frames = value;
@@ -650,7 +656,7 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
         if (inflight[slot]) { rc = dsdgpu_wait(ctx, slot); inflight[slot] = false; if (rc) break; }
         const int64_t n = nframes - f < chunk ? nframes - f : chunk;
         rc = dsdgpu_submit(ctx, slot, in, in_stride, in_first, in_count, fill, p0 + f * ctx->nstep, n, scale,
-                           dither_amp, clip, dither_first_sample + (uint64_t)f * ctx->nch, out_kind,
+                           dither_amp, clip, dither_first_sample + (uint64_t)f * (uint64_t)(ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch), out_kind,
                            static_cast<unsigned char*>(out) + (size_t)f * ctx->nch * elem);
         if (rc) break;
         inflight[slot] = true;

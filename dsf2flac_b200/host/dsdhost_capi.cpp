@@ -1,0 +1,98 @@
+// dsdhost_capi.cpp -- C-callable drivers around the drop-in DsdDecimator, shaped like its one
+// caller in the reference (pcm_track_helper, reference src/main.cpp:111-210), so tests/ and
+// bench.py can run "what dsf2flac would run" through ctypes: an in-memory DsdSampleReader feeds
+// the decimator byte by byte exactly as the DSF/DSDIFF readers do, the decimator drains it in
+// blocks and runs the FIR on the GPU through include/dsdgpu.h.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dsd_decimator.h"
+#include "memory_sample_reader.h"
+
+namespace {
+thread_local std::string g_error;
+}
+
+extern "C" {
+
+const char* dsdhost_last_error() { return g_error.c_str(); }
+
+// Geometry as the decimator reports it (reference dsd_decimator.cpp:44-72,85-101).
+// Returns 1 if the rate pair is accepted, 0 if not ("Sorry, incompatible ..."); a missing GPU
+// does not matter here: the getters do not depend on it.
+int dsdhost_info(uint32_t dsd_fs, uint32_t out_fs, int64_t length_samples, int32_t* ratio,
+                 double* first_valid, double* last_valid, int64_t* length_pcm) {
+    uint8_t dummy = 0;
+    MemorySampleReader rd(&dummy, 1, 0, length_samples, dsd_fs, true);
+    DsdDecimator dec(&rd, out_fs);
+    g_error = dec.getErrorMsg();
+    if (dec.getDecimationRatio() != 8 && dec.getDecimationRatio() != 16 && dec.getDecimationRatio() != 32) return 0;
+    *ratio = (int32_t)dec.getDecimationRatio();
+    *first_valid = dec.getFirstValidSample();
+    *last_valid = dec.getLastValidSample();
+    *length_pcm = dec.getLength();
+    return 1;
+}
+
+// rewind, `pre_steps` x step(), then getSamples in calls of `chunk_frames` frames (0 = one call).
+// Exactly one of out_i32 / out_f64 is filled ([nframes][nch]).  Returns 0, or 1 with the
+// decimator's error message in dsdhost_last_error().
+int dsdhost_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                    uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, int64_t pre_steps,
+                    int64_t nframes, int64_t chunk_frames, double scale, double dither, double clip,
+                    int lut_bits, uint32_t read_ahead, int32_t* out_i32, double* out_f64) {
+    MemorySampleReader rd(planar, (uint32_t)nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return 1; }
+    if (lut_bits != 64 && !dec.setLutPrecision(lut_bits)) { g_error = dec.getErrorMsg(); return 1; }
+    if (read_ahead) dec.setReadAheadFrames(read_ahead);
+    for (int64_t i = 0; i < pre_steps; ++i) dec.step();
+    if (chunk_frames <= 0) chunk_frames = nframes;
+    for (int64_t f = 0; f < nframes; f += chunk_frames) {
+        const int64_t n = nframes - f < chunk_frames ? nframes - f : chunk_frames;
+        if (out_i32) dec.getSamples(out_i32 + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
+        else dec.getSamples(out_f64 + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
+    }
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return 1; }
+    return 0;
+}
+
+// One whole track, --onefile bounds (reference main.cpp:249-258) and the loop of
+// main.cpp:169-191: creep with step(), blocks of 1024 frames, then single frames.
+// Returns frames written, -1 on error, -2 if `out` is too small.
+int64_t dsdhost_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                        uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, double scale,
+                        double dither, double clip, int lut_bits, uint32_t read_ahead, int32_t* out,
+                        int64_t out_cap_frames) {
+    MemorySampleReader rd(planar, (uint32_t)nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    if (lut_bits != 64 && !dec.setLutPrecision(lut_bits)) { g_error = dec.getErrorMsg(); return -1; }
+    if (read_ahead) dec.setReadAheadFrames(read_ahead);
+    double startPos = dec.getFirstValidSample();
+    double endPos = dec.getLastValidSample();
+    if (startPos > dec.getLength() - 1) startPos = dec.getLength() - 1;
+    if (endPos > dec.getLength()) endPos = dec.getLength();
+    const int block = 1024;
+    while (dec.getPosition() < startPos) dec.step();
+    int64_t done = 0;
+    std::vector<int32_t> buf((size_t)nch * block);
+    while (dec.getPosition() <= endPos - block) {
+        dec.getSamples(buf.data(), (dsf2flac_uint32)(nch * block), scale, dither, clip);
+        if (done + block > out_cap_frames) return -2;
+        std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch * block);
+        done += block;
+    }
+    while (dec.getPosition() <= endPos) {
+        dec.getSamples(buf.data(), (dsf2flac_uint32)nch, scale, dither, clip);
+        if (done + 1 > out_cap_frames) return -2;
+        std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch);
+        done += 1;
+    }
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    return done;
+}
+
+}  // extern "C"

@@ -75,8 +75,11 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx);
  * Maps to DsdDecimator::getErrorMsg (dsd_decimator.cpp:113-115). */
 const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
 
-/* Tuning knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk),
- * "threads" (skew kernel CTA size, 512 or 1024). Unknown keys are an error. */
+/* Knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk), "threads"
+ * (skew kernel CTA size, 512 or 1024), "dither_stride" (output samples per frame of the WHOLE
+ * stream when this context only holds a channel subset of it: sample m of frame i, local channel
+ * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default). Unknown keys are an
+ * error. */
 int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
@@ -134,6 +137,28 @@ int dsdgpu_wait(dsdgpu_ctx* ctx, int slot);
  */
 int dsdgpu_dither_fill_device(dsdgpu_ctx* ctx, uint64_t first_sample, int64_t count, double* d_out,
                               void* cuda_stream);
+
+/*
+ * Multi-GPU partitioning (no reference counterpart: the reference is one thread, its only batch
+ * notion is the serial loop of scripts/batch_dsf2flac.sh:16-19).  Output sample (job, channel,
+ * frame) depends only on nlut bytes of its own channel (dsd_decimator.cpp:193-198), so a batch
+ * of streams is cut into independent shards: by file, by channel, and by time segment with an
+ * (nlut-1)-byte input halo.  The batch is laid out as one line of work -- job-major, then
+ * channel, then frame, each frame of job k weighing job_cost[k] -- and rank r owns the r-th of
+ * `world` equal-cost pieces, cut on multiples of align_frames.  Adjacent channels of one job
+ * that cover the same frame range are merged into one shard.  Pure host arithmetic; every rank
+ * computes the same plan; there is no data-path collective.
+ * Returns the number of shards of `rank` (written to out[0..cap) as far as they fit), or -1 on
+ * bad arguments.
+ */
+typedef struct {
+    int32_t job, ch_first, ch_count, reserved;
+    int64_t frame_first, frame_count;
+} dsdgpu_shard;
+
+int64_t dsdgpu_plan_shards(const int64_t* job_frames, const int32_t* job_nch, const int32_t* job_cost,
+                           int njobs, int rank, int world, int64_t align_frames, dsdgpu_shard* out,
+                           int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -18,13 +18,16 @@ public:
     void push_front(const T& v) {
         const std::size_t cap = slots_.size();
         if (cap == 0) return;
-        head_ = (head_ + cap - 1) % cap;
+        head_ = (head_ == 0 ? cap : head_) - 1;
         slots_[head_] = v;
         if (count_ < cap) ++count_;
     }
-    T& operator[](std::size_t i) { return slots_[(head_ + i) % slots_.size()]; }
-    const T& operator[](std::size_t i) const { return slots_[(head_ + i) % slots_.size()]; }
+    // Boost indexes with a compare-and-subtract wrap, not a division; do the same so that the
+    // reference timed through this stand-in is not slowed down by it.
+    T& operator[](std::size_t i) { return slots_[wrap(head_ + i)]; }
+    const T& operator[](std::size_t i) const { return slots_[wrap(head_ + i)]; }
 private:
+    std::size_t wrap(std::size_t k) const { return k < slots_.size() ? k : k - slots_.size(); }
     std::vector<T> slots_;
     std::size_t head_, count_;
 };

@@ -1,0 +1,99 @@
+// TEST INFRASTRUCTURE ONLY -- a CPU stand-in for the C ABI of include/dsdgpu.h.
+//
+// Linked with dsf2flac_b200/host/dsd_decimator.cpp into tests/cpp/_build/libdsdhost_cpu.so so
+// that the HOST logic of the drop-in DsdDecimator (logical position, reader draining, block
+// cache, dither-stream bookkeeping, loop termination) can be tested where there is no GPU.
+// It is never built into, linked with or loaded by the product (dsf2flac_b200/*.so).
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "dsdgpu.h"
+
+struct dsdgpu_ctx {
+    int nch, nlut, nstep;
+    std::vector<double> lut;
+    unsigned long long launches = 0;
+    long long chunk_frames = 1 << 20;
+    long long dither_stride = 0;
+    char err[128] = "";
+};
+
+namespace {
+// glibc rand() draws by position: srand(1), skip, draw (tests are small, so the skip is cheap)
+void dither_terms(uint64_t first_sample, int64_t count, std::vector<double>& out) {
+    out.resize((size_t)count);
+    srand(1);
+    for (uint64_t k = 0; k < 2 * first_sample; ++k) (void)rand();
+    for (int64_t i = 0; i < count; ++i) {
+        const double r1 = (double)rand() / (double)RAND_MAX;
+        const double r2 = (double)rand() / (double)RAND_MAX;
+        out[(size_t)i] = r1 - r2;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int dsdgpu_create(dsdgpu_ctx** ctx, int, int nch, int nlut, int nstep, const double* lut, int lut_precision) {
+    dsdgpu_ctx* c = new dsdgpu_ctx();
+    c->nch = nch; c->nlut = nlut; c->nstep = nstep;
+    c->lut.assign(lut, lut + (size_t)nlut * 256);
+    if (lut_precision == 32) for (auto& v : c->lut) v = (double)(float)v;
+    *ctx = c;
+    return DSDGPU_OK;
+}
+void dsdgpu_destroy(dsdgpu_ctx* ctx) { delete ctx; }
+const char* dsdgpu_last_error(const dsdgpu_ctx* ctx) { return ctx ? ctx->err : "stand-in"; }
+int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
+    if (!strcmp(key, "chunk_frames")) ctx->chunk_frames = value;
+    if (!strcmp(key, "dither_stride")) ctx->dither_stride = value;
+    return DSDGPU_OK;
+}
+unsigned long long dsdgpu_kernel_launches(const dsdgpu_ctx* ctx) { return ctx->launches; }
+void* dsdgpu_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void dsdgpu_host_free(void* p) { free(p); }
+
+int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first,
+                         int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
+                         double dither_amp, double clip, uint64_t dither_first_sample, int out_kind,
+                         void* out) {
+    std::vector<double> dith;
+    const long long stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
+    if (dither_amp > 0 && nframes > 0) dither_terms(dither_first_sample, (nframes - 1) * stride + ctx->nch, dith);
+    for (int64_t i = 0; i < nframes; ++i)
+        for (int c = 0; c < ctx->nch; ++c) {
+            const int64_t p = p0 + i * ctx->nstep;
+            double sum = 0.0;
+            for (int t = 0; t < ctx->nlut; ++t) {
+                const int64_t o = p - t - in_first;
+                const unsigned b = (o >= 0 && o < in_count) ? in[(size_t)c * in_stride + (size_t)o] : fill;
+                sum += ctx->lut[(size_t)t * 256 + b];
+            }
+            sum = sum * scale;
+            if (dither_amp > 0) sum = sum + dith[(size_t)(i * stride + c)] * dither_amp;
+            if (clip > 0) { if (sum > clip) sum = clip; else if (sum < -clip) sum = -clip; }
+            if (out_kind == DSDGPU_OUT_INT32) static_cast<int32_t*>(out)[i * ctx->nch + c] = (int32_t)round(sum);
+            else static_cast<double*>(out)[i * ctx->nch + c] = sum;
+        }
+    ctx->launches += 1;
+    return DSDGPU_OK;
+}
+
+int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t*, size_t, int64_t, int64_t, uint8_t, int64_t,
+                           int64_t, double, double, double, uint64_t, int, void*, void*) {
+    snprintf(ctx->err, sizeof ctx->err, "stand-in has no device");
+    return DSDGPU_ERR_NODEVICE;
+}
+int dsdgpu_submit(dsdgpu_ctx* ctx, int, const uint8_t*, size_t, int64_t, int64_t, uint8_t, int64_t, int64_t,
+                  double, double, double, uint64_t, int, void*) {
+    snprintf(ctx->err, sizeof ctx->err, "stand-in has no device");
+    return DSDGPU_ERR_NODEVICE;
+}
+int dsdgpu_wait(dsdgpu_ctx*, int) { return DSDGPU_ERR_STATE; }
+int dsdgpu_dither_fill_device(dsdgpu_ctx*, uint64_t, int64_t, double*, void*) { return DSDGPU_ERR_NODEVICE; }
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+"""TEST INFRASTRUCTURE: ctypes access to the two CPU checkers built by oracle/Makefile.
+
+  Oracle()                oracle/_build/libdsdoracle.so  (C restatement, oracle/dsd_oracle.c)
+  Oracle(reference=True)  oracle/_ref/libdsdref.so       (the unmodified reference decimator)
+
+Both expose the same calls.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs use this module; the product never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libdsdoracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libdsdref.so")
+
+_i64, _u32, _dbl, _vp = C.c_int64, C.c_uint32, C.c_double, C.c_void_p
+
+
+class Oracle:
+    def __init__(self, reference=False):
+        self.reference = reference
+        self.prefix = "dsdref_" if reference else "dsdoracle_"
+        self.lib = C.CDLL(REF_SO if reference else ORACLE_SO)
+        f = self._fn("info")
+        f.restype = C.c_int
+        f.argtypes = [_u32, _u32, _i64] + [C.POINTER(C.c_int32)] * 4 + [C.POINTER(_dbl)] * 2 + [C.POINTER(_i64)]
+        f = self._fn("lut")
+        f.restype = C.c_int
+        f.argtypes = [_u32, _u32, C.c_int, _vp, C.c_int]
+        f = self._fn("run_raw")
+        f.restype = C.c_int
+        if reference:   # (..., pre_steps, nframes, chunk_frames, scale, dither, clip, reseed, out_i32, out_f64)
+            f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _u32, _u32, _i64, _i64, _i64, _dbl, _dbl, _dbl,
+                          C.c_int, _vp, _vp]
+        else:           # (..., pre_steps, nframes, rand_skip, scale, dither, clip, out_i32, out_f64)
+            f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _u32, _u32, _i64, _i64, _i64, _dbl, _dbl, _dbl,
+                          _vp, _vp]
+        f = self._fn("run_app")
+        f.restype = _i64
+        if reference:
+            f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _u32, _u32, _dbl, _dbl, _dbl, C.c_int, _vp, _i64]
+        else:
+            f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _u32, _u32, _dbl, _dbl, _dbl, _vp, _i64]
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def info(self, dsd_fs, out_fs, length_samples=0):
+        r = [C.c_int32() for _ in range(4)]
+        d = [_dbl(), _dbl()]
+        n = _i64()
+        ok = self._fn("info")(dsd_fs, out_fs, length_samples, *[C.byref(x) for x in r], *[C.byref(x) for x in d],
+                              C.byref(n))
+        if not ok:
+            return None
+        return dict(ratio=r[0].value, nlut=r[1].value, nstep=r[2].value, tzero=r[3].value, first_valid=d[0].value,
+                    last_valid=d[1].value, length_pcm=n.value)
+
+    def lut(self, dsd_fs, out_fs, msb_flag):
+        buf = np.zeros((96, 256), dtype=np.float64)
+        n = self._fn("lut")(dsd_fs, out_fs, int(msb_flag), buf.ctypes.data, 96)
+        return buf[:n].copy() if n else None
+
+    def run_raw(self, planar, length_samples, msb_flag, dsd_fs, out_fs, pre_steps, nframes, scale, dither=0.0,
+                clip=0.0, idle=0x69, want="i32", chunk_frames=0, rand_skip=0):
+        """Raw operator: rewind, pre_steps x step(), nframes frames.  The dither stream is that of
+        a fresh process (reference: srand(1) first), optionally `rand_skip` draws in (oracle only)."""
+        planar = np.ascontiguousarray(planar, dtype=np.uint8)
+        nch, nbytes = planar.shape
+        out = np.zeros((nframes, nch), dtype=np.int32 if want == "i32" else np.float64)
+        pi = out.ctypes.data if want == "i32" else None
+        pf = out.ctypes.data if want != "i32" else None
+        if self.reference:
+            assert rand_skip == 0
+            rc = self._fn("run_raw")(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), dsd_fs,
+                                     out_fs, pre_steps, nframes, chunk_frames, scale, dither, clip, 1, pi, pf)
+        else:
+            rc = self._fn("run_raw")(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), dsd_fs,
+                                     out_fs, pre_steps, nframes, rand_skip, scale, dither, clip, pi, pf)
+        if rc != 0:
+            raise RuntimeError("oracle rejected the rate pair")
+        return out
+
+    def run_app(self, planar, length_samples, msb_flag, dsd_fs, out_fs, scale, dither=0.0, clip=0.0, idle=0x69):
+        """Whole-track conversion with main.cpp's loop shape.  Returns int32 [frames, nch]."""
+        planar = np.ascontiguousarray(planar, dtype=np.uint8)
+        nch, nbytes = planar.shape
+        cap = length_samples // 8 + 2048
+        out = np.zeros((cap, nch), dtype=np.int32)
+        if self.reference:
+            n = self._fn("run_app")(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), dsd_fs,
+                                    out_fs, scale, dither, clip, 1, out.ctypes.data, cap)
+        else:
+            n = self._fn("run_app")(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), dsd_fs,
+                                    out_fs, scale, dither, clip, out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError(f"oracle run_app failed ({n})")
+        return out[:n].copy()
+
+    def rand(self, n, skip=0):
+        out = np.zeros(n, dtype=np.int32)
+        if self.reference:
+            assert skip == 0
+            self.lib.dsdref_libc_rand.argtypes = [_vp, _i64]
+            self.lib.dsdref_libc_rand(out.ctypes.data, n)
+        else:
+            self.lib.dsdoracle_rand.argtypes = [_vp, _i64, _i64]
+            self.lib.dsdoracle_rand(out.ctypes.data, n, skip)
+        return out
+
+
+DSD64 = 2822400
+
+
+def seeded_bytes(nch, nbytes, seed):
+    return np.random.default_rng(seed).integers(0, 256, size=(nch, nbytes), dtype=np.uint8)

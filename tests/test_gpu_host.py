@@ -1,0 +1,53 @@
+"""The drop-in DsdDecimator (host/dsd_decimator.cpp + libdsdgpu.so) driven the way main.cpp
+drives the reference class, byte-by-byte reader underneath, against the oracle's run of the
+same loops.  Bit-exact."""
+import numpy as np
+import pytest
+
+from dsf2flac_b200 import capi, filters
+from tests.oracle_lib import DSD64, seeded_bytes
+
+pytestmark = pytest.mark.gpu
+RATES = {32: 88200, 16: 176400, 8: 352800}
+
+
+def run_app(data, L, msb, fs, scale, dither, clip, read_ahead=0, lut_bits=64, dsd_fs=DSD64):
+    host = capi.host_lib()
+    nch, nbytes = data.shape
+    cap = L // 8 + 2048
+    out = np.zeros((cap, nch), dtype=np.int32)
+    n = host.dsdhost_run_app(data.ctypes.data, nch, nbytes, L, 0x69, int(msb), dsd_fs, fs, scale, dither, clip, lut_bits,
+                             read_ahead, out.ctypes.data, cap)
+    assert n >= 0, host.dsdhost_last_error()
+    return out[:n]
+
+
+@pytest.mark.parametrize("msb", [0, 1])
+@pytest.mark.parametrize("ratio", [32, 16, 8])
+def test_dropin_matches_oracle_app_loop(oracle, ratio, msb):
+    data = seeded_bytes(2, 120000, ratio + msb)
+    for L, bits, dither, ra in ((120000 * 8, 24, False, 0), (120000 * 8 - 9, 16, True, 10000), (100000 * 8, 20, True, 1)):
+        scale, amp, clip = filters.app_params(bits, dither=dither)
+        if ra == 1:
+            data_, L_ = data[:, :3000], 3000 * 8       # one GPU round trip per frame: keep it short
+        else:
+            data_, L_ = data, L
+        want = oracle.run_app(data_, L_, msb, DSD64, RATES[ratio], scale, amp, clip)
+        got = run_app(data_, L_, msb, RATES[ratio], scale, amp, clip, read_ahead=ra)
+        assert np.array_equal(got, want), (L, bits, dither, ra)
+
+
+def test_dropin_dsd128_six_channels(oracle):
+    data = seeded_bytes(6, 60000, 66)
+    scale, amp, clip = filters.app_params(24, dither=True)
+    want = oracle.run_app(data, 60000 * 8, 0, 2 * DSD64, 176400, scale, amp, clip)
+    got = run_app(data, 60000 * 8, 0, 176400, scale, amp, clip, dsd_fs=2 * DSD64)
+    assert np.array_equal(got, want)
+
+
+def test_dropin_fp32_tables(oracle):
+    data = seeded_bytes(2, 50000, 12)
+    scale, _, clip = filters.app_params(24)
+    want = oracle.run_app(data, 50000 * 8, 1, DSD64, 88200, scale, 0.0, clip)
+    got = run_app(data, 50000 * 8, 1, 88200, scale, 0.0, clip, lut_bits=32)
+    assert np.abs(got.astype(np.int64) - want).max() <= 1

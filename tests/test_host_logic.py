@@ -1,0 +1,85 @@
+"""Host logic without a GPU: the drop-in DsdDecimator (host/dsd_decimator.cpp) linked against a
+CPU stand-in of the C ABI (tests/cpp/standin_dsdgpu.cpp) must behave, call for call, like the
+reference class: logical position, creep/step, block read-ahead of any size, getSamples call
+sizes, dither stream continuity, loop termination and frame counts."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from dsf2flac_b200 import capi, filters
+from tests.oracle_lib import DSD64, seeded_bytes
+
+CPU_HOST = os.path.join(os.path.dirname(__file__), "cpp", "_build", "libdsdhost_cpu.so")
+RATES = {32: 88200, 16: 176400, 8: 352800}
+
+
+@pytest.fixture(scope="module")
+def host():
+    return capi.host_lib(CPU_HOST)
+
+
+def run_app(host, data, L, msb, fs, scale, dither, clip, read_ahead=0, lut_bits=64):
+    nch, nbytes = data.shape
+    cap = L // 8 + 2048
+    out = np.zeros((cap, nch), dtype=np.int32)
+    n = host.dsdhost_run_app(data.ctypes.data, nch, nbytes, L, 0x69, int(msb), DSD64, fs, scale, dither, clip, lut_bits,
+                             read_ahead, out.ctypes.data, cap)
+    assert n >= 0, host.dsdhost_last_error()
+    return out[:n]
+
+
+def run_raw(host, data, L, msb, fs, pre, nframes, chunk, scale, dither, clip, read_ahead=0, want="i32"):
+    nch, nbytes = data.shape
+    out = np.zeros((nframes, nch), dtype=np.int32 if want == "i32" else np.float64)
+    rc = host.dsdhost_run_raw(data.ctypes.data, nch, nbytes, L, 0x69, int(msb), DSD64, fs, pre, nframes, chunk, scale,
+                              dither, clip, 64, read_ahead, out.ctypes.data if want == "i32" else None,
+                              out.ctypes.data if want != "i32" else None)
+    assert rc == 0, host.dsdhost_last_error()
+    return out
+
+
+def test_info_matches_oracle(host, oracle):
+    for ratio, fs in RATES.items():
+        r, a, b, n = C.c_int32(), C.c_double(), C.c_double(), C.c_int64()
+        assert host.dsdhost_info(DSD64, fs, 999 * 8, C.byref(r), C.byref(a), C.byref(b), C.byref(n)) == 1
+        info = oracle.info(DSD64, fs, 999 * 8)
+        assert (r.value, a.value, b.value, n.value) == (info["ratio"], info["first_valid"], info["last_valid"],
+                                                        info["length_pcm"])
+    assert host.dsdhost_info(DSD64 * 8, 352800, 0, C.byref(r), C.byref(a), C.byref(b), C.byref(n)) == 0
+    assert b"incompatible sample rate" in host.dsdhost_last_error()
+
+
+@pytest.mark.parametrize("ratio", list(RATES))
+@pytest.mark.parametrize("read_ahead", [1, 7, 1024, 5000, 0])
+def test_app_loop_any_read_ahead(host, oracle, ratio, read_ahead):
+    fs = RATES[ratio]
+    data = seeded_bytes(2, 6000, ratio)
+    for L in (6000 * 8, 6000 * 8 - 5, 5000 * 8):
+        scale, amp, clip = filters.app_params(24, dither=True)
+        want = oracle.run_app(data, L, 1, DSD64, fs, scale, amp, clip)
+        got = run_app(host, data, L, 1, fs, scale, amp, clip, read_ahead)
+        assert np.array_equal(got, want)
+
+
+def test_call_sizes_and_steps_interleaved(host, oracle):
+    # getSamples in odd-sized calls after an odd creep: the dither stream and the position carry on
+    data = seeded_bytes(3, 4000, 9)
+    scale, amp, clip = filters.app_params(16, dither=True)
+    for chunk in (1, 3, 100, 0):
+        want = oracle.run_raw(data, 4000 * 8, 0, DSD64, 88200, 75, 700, scale, amp, clip)
+        got = run_raw(host, data, 4000 * 8, 0, 88200, 75, 700, chunk, scale, amp, clip, read_ahead=64)
+        assert np.array_equal(got, want)
+    # float output is the unrounded value
+    want = oracle.run_raw(data, 4000 * 8, 0, DSD64, 176400, 0, 300, 2.5, want="f64")
+    got = run_raw(host, data, 4000 * 8, 0, 176400, 0, 300, 7, 2.5, 0.0, 0.0, want="f64")
+    assert want.tobytes() == got.tobytes()
+
+
+def test_fp32_tables_within_one_lsb(host, oracle):
+    data = seeded_bytes(2, 5000, 5)
+    scale, _, clip = filters.app_params(24)
+    want = oracle.run_app(data, 5000 * 8, 1, DSD64, 88200, scale, 0.0, clip)
+    got = run_app(host, data, 5000 * 8, 1, 88200, scale, 0.0, clip, lut_bits=32)
+    assert np.abs(got.astype(np.int64) - want).max() <= 1
