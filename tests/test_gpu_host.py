@@ -29,7 +29,7 @@ def test_dropin_matches_oracle_app_loop(oracle, ratio, msb):
     for L, bits, dither, ra in ((120000 * 8, 24, False, 0), (120000 * 8 - 9, 16, True, 10000), (100000 * 8, 20, True, 1)):
         scale, amp, clip = filters.app_params(bits, dither=dither)
         if ra == 1:
-            data_, L_ = data[:, :3000], 3000 * 8       # one GPU round trip per frame: keep it short
+            data_, L_ = np.ascontiguousarray(data[:, :3000]), 3000 * 8       # one GPU round trip per frame: keep it short
         else:
             data_, L_ = data, L
         want = oracle.run_app(data_, L_, msb, DSD64, RATES[ratio], scale, amp, clip)
