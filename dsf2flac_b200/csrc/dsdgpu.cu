@@ -87,8 +87,8 @@ decimate_direct_kernel(DecimateArgs a, int nlut, int nstep) {
     const long long total = a.nframes * a.nch;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx / a.nframes);
-        const long long f = idx - (long long)c * a.nframes;
+        const long long f = idx / a.nch;               // idx is the output index: stores coalesce
+        const int c = (int)(idx - f * a.nch);
         const long long p = a.p0 + f * nstep;
         const uint8_t* src = a.in + (long long)c * a.in_stride;
         double sum = 0.0;
@@ -112,12 +112,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// Tiles are numbered channel-fastest: the CTAs that run side by side write the same frames of
+// neighbouring channels, so the 4-byte slots of one 32-byte output sector meet in L2 before the
+// sector goes to HBM (frame-major interleaved output, dsd_decimator.cpp:213).
 template <class G>
 __device__ __forceinline__ void skew_tile_geometry(const DecimateArgs& a, long long tile,
                                                    long long tiles_per_ch, int& c, long long& f0,
                                                    long long& t0, int& a_tile) {
-    c = (int)(tile / tiles_per_ch);
-    f0 = (tile - (long long)c * tiles_per_ch) * G::NT;
+    (void)tiles_per_ch;
+    c = (int)(tile % a.nch);
+    f0 = (tile / a.nch) * G::NT;
     skew_tile_origin<G>(a.p0, a.in_first, f0, t0, a_tile);
 }
 
