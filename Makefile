@@ -25,10 +25,13 @@ $(PKG)/libdsdhost.so: $(HOSTSRC) $(HOSTHDR) $(PKG)/libdsdgpu.so
 oracle:
 	$(MAKE) -C oracle all
 
-tests: tests/cpp/_build/emu_skew tests/cpp/_build/libdsdhost_cpu.so
+tests: tests/cpp/_build/emu_skew tests/cpp/_build/emu_ring tests/cpp/_build/libdsdhost_cpu.so
 tests/cpp/_build/emu_skew: tests/cpp/emu_skew.cpp $(PKG)/csrc/skew_core.h
 	mkdir -p tests/cpp/_build
 	$(CXX) -O2 -std=c++17 -I $(PKG)/csrc -o $@ tests/cpp/emu_skew.cpp
+tests/cpp/_build/emu_ring: tests/cpp/emu_ring.cpp $(PKG)/csrc/ring_core.h
+	mkdir -p tests/cpp/_build
+	$(CXX) -O2 -std=c++17 -I $(PKG)/csrc -o $@ tests/cpp/emu_ring.cpp
 # the same host sources linked against a CPU stand-in of the C ABI (tests only, never shipped)
 tests/cpp/_build/libdsdhost_cpu.so: $(HOSTSRC) $(HOSTHDR) tests/cpp/standin_dsdgpu.cpp
 	mkdir -p tests/cpp/_build

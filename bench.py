@@ -211,21 +211,31 @@ def run_gpu_arm(args, wl):
     bits_per_step = nbytes * 8 * nch                       # DSD bits consumed per step per GPU
     g = capi.DsdGpu(lut, nch, fir.nstep, device=local, lut_precision=args.lut)
     if args.kernel:
-        g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2}[args.kernel])
+        g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2, "ring": 3}[args.kernel])
     if args.threads:
         g.set_option("threads", args.threads)
 
     # device-resident ring of distinct input/output buffers, larger than L2 in total, so no step
     # finds its bytes in L2 from the step before
+    # The stream sits in its device buffer behind `front` reader-idle bytes (what the reader's ring
+    # holds before byte 0, dsd_sample_reader.h:122), chosen so that the frame grid is 4-byte aligned
+    # to the buffer ((p0 - in_first + 1) % 4 == 0): the kernel's window loads are then conflict free.
     in_bytes, out_bytes = nch * nbytes, nframes * nch * 4
     ring = max(2, -(-2 * L2_BYTES // (in_bytes + out_bytes)))
-    d_in = [torch.from_numpy(np.roll(data, 4096 * k, axis=1)).cuda() for k in range(ring)]
+    front = (fir.nlut + 1) % 4 if args.align else 0
+    front = (4 - front) % 4
+    stride = (nbytes + front + 255) // 256 * 256
+    d_in = []
+    for k in range(ring):
+        t = torch.full((nch, stride), 0x69, dtype=torch.uint8)
+        t[:, front:front + nbytes] = torch.from_numpy(np.roll(data, 4096 * k, axis=1))
+        d_in.append(t.cuda())
     d_out = [torch.empty((nframes, nch), dtype=torch.int32, device="cuda") for _ in range(ring)]
     stream = torch.cuda.Stream()
 
     def step(k):
-        g.decimate_device(d_in[k % ring], nbytes, 0, nbytes, 0x69, fir.nlut, nframes, scale, amp, clip, 0, capi.OUT_INT32,
-                          d_out[k % ring], stream=stream.cuda_stream)
+        g.decimate_device(d_in[k % ring], stride, -front, nbytes + front, 0x69, fir.nlut, nframes, scale, amp, clip, 0,
+                          capi.OUT_INT32, d_out[k % ring], stream=stream.cuda_stream)
 
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
@@ -345,7 +355,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
     ap.add_argument("--dither", type=int, default=0)
-    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew"])
+    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring"])
+    ap.add_argument("--align", type=int, default=1, help="0: device buffer starts at stream byte 0 (frame grid off by one byte)")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="length of the CPU-baseline sample (stream seconds)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)

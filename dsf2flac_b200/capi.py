@@ -18,7 +18,7 @@ GPU_LIB = os.path.join(_HERE, "libdsdgpu.so")
 HOST_LIB = os.path.join(_HERE, "libdsdhost.so")
 
 OUT_INT32, OUT_FLOAT64 = 0, 1
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SKEW = 0, 1, 2
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SKEW, KERNEL_RING = 0, 1, 2, 3
 ERR_NODEVICE = 3
 
 _u8p = C.POINTER(C.c_uint8)

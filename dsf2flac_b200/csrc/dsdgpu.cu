@@ -3,8 +3,12 @@
 // Hot path replaced: DsdDecimator::getSamplesInternal (reference src/dsd_decimator.cpp:173-222)
 // -- the per-byte lookup-table FIR (:194-198) fused with scale / TPDF dither / clip / round
 // (:199-216).  Kernels:
-//   decimate_skew_kernel    bank-conflict-free lane-skewed LUT gather (divide-by-32 filters),
-//                           persistent CTAs, LUT image + double-buffered byte tiles in smem
+//   decimate_ring_kernel    the production kernel for the divide-by-32 filters: bank-conflict-
+//                           free lane-skewed LUT gather with no idle taps, 4 frames per lane,
+//                           persistent CTAs, LUT image + double-buffered byte tiles in smem,
+//                           frame-pair-coalesced int32 stores (ring_core.h)
+//   decimate_skew_kernel    its predecessor (80-step periods with 8 pad taps, 1 frame per lane);
+//                           kept selectable for A/B measurements (skew_core.h)
 //   decimate_direct_kernel  one thread per output sample, tables [t][byte] in smem; any
 //                           geometry, used for /16 and /8 filters and as a cross-check
 //   glibc_rand_*            positional reconstruction of the reference's dither stream
@@ -12,6 +16,7 @@
 // There is no CPU fallback anywhere in this file.
 #include "dsdgpu.h"
 #include "skew_core.h"
+#include "ring_core.h"
 
 #include <cuda_runtime.h>
 
@@ -204,6 +209,138 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_skew_kernel(DecimateArgs 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ring kernel
+// ---------------------------------------------------------------------------------------------
+// Stage both halves of a tile: bytes [t0_h, t0_h + HALF_BYTES) of channel c_h.
+template <class G>
+__device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const RingTile& tl, unsigned char* dst,
+                                                bool aligned16) {
+    constexpr int CHUNKS = G::HALF_BYTES / 16;
+    for (int k = threadIdx.x; k < 2 * CHUNKS; k += G::NTHR) {
+        const int h = k >= CHUNKS ? 1 : 0;
+        const int kk = k - h * CHUNKS;
+        long long t0; int a_tile;
+        ring_half_origin<G>(a.p0, a.in_first, h ? tl.f0[1] : tl.f0[0], t0, a_tile);
+        const uint8_t* src = a.in + (long long)(h ? tl.c[1] : tl.c[0]) * a.in_stride;
+        const long long o = t0 - a.in_first + 16LL * kk;
+        unsigned char* d = dst + h * G::HALF_BYTES + 16 * kk;
+        if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
+            cp_async16(d, src + o);
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const long long ob = o + 4 * q + b;
+                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)src[ob] : a.fill;
+                    v |= byte << (8 * b);
+                }
+                w[q] = v;
+            }
+            *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+__device__ __forceinline__ int quantise_i32(const DecimateArgs& a, long long frame, int c, double sum) {
+    const double dith = (a.dither != nullptr) ? a.dither[frame * a.dither_stride + c] : 0.0;
+    return __double2int_rz(round(quantise_tail(sum, a.scale, a.dither_amp, dith, a.clip)));
+}
+
+// Four consecutive frames fb..fb+3 of channel c held by this lane; its partner (lane ^ 16) holds
+// the same frames of channel c+1 (pair tile) or the frames NTP further on (single tile).
+template <class G>
+__device__ __forceinline__ void ring_emit(const DecimateArgs& a, const RingTile& tl, int h, long long fb,
+                                          const double (&sums)[4], bool out_aligned16) {
+    const int c = h ? tl.c[1] : tl.c[0];
+    if (a.out_kind != DSDGPU_OUT_INT32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (fb + k < a.nframes) store_sample(a, fb + k, c, sums[k]);
+        return;
+    }
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (fb + k < a.nframes) ? quantise_i32(a, fb + k, c, sums[k]) : 0;
+    int32_t* out = reinterpret_cast<int32_t*>(a.out);
+    const bool pair = tl.c[1] != tl.c[0];
+    if (pair && (a.nch & 1) == 0) {
+        // trade halves: lane h=0 ends up with frames fb, fb+1 of both channels, lane h=1 with fb+2, fb+3
+        const int s0 = __shfl_xor_sync(0xffffffffu, h ? v[0] : v[2], 16);
+        const int s1 = __shfl_xor_sync(0xffffffffu, h ? v[1] : v[3], 16);
+        const long long f = fb + 2 * h;
+        const int c0 = tl.c[0];
+        const int2 lo2 = h ? make_int2(s0, v[2]) : make_int2(v[0], s0);
+        const int2 hi2 = h ? make_int2(s1, v[3]) : make_int2(v[1], s1);
+        if (a.nch == 2 && out_aligned16 && f + 1 < a.nframes) {
+            *reinterpret_cast<int4*>(out + f * 2) = make_int4(lo2.x, lo2.y, hi2.x, hi2.y);
+        } else {
+            if (f < a.nframes) *reinterpret_cast<int2*>(out + f * a.nch + c0) = lo2;
+            if (f + 1 < a.nframes) *reinterpret_cast<int2*>(out + (f + 1) * a.nch + c0) = hi2;
+        }
+    } else if (a.nch == 1 && out_aligned16 && fb + 3 < a.nframes) {
+        *reinterpret_cast<int4*>(out + fb) = make_int4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (fb + k < a.nframes) out[(fb + k) * a.nch + c] = v[k];
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [0, LUT_BYTES): table image; then two tiles of two byte buffers each.
+    const int tid = threadIdx.x;
+    {
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
+        for (int k = tid; k < G::LUT_BYTES / 16; k += G::NTHR) cp_async16(smem + 16 * k, img + 16 * k);
+    }
+    const long long ntiles = ring_tile_count<G>(a.nframes, a.nch);
+    const bool aligned16 = ((reinterpret_cast<unsigned long long>(a.in) | (unsigned long long)a.in_stride) & 15ULL) == 0;
+    const bool out_aligned16 = (reinterpret_cast<unsigned long long>(a.out) & 15ULL) == 0;
+    int a_tile;
+    {
+        long long t0;
+        ring_half_origin<G>(a.p0, a.in_first, 0, t0, a_tile);   // the same for every half of the launch
+    }
+    const int l = tid & 31, w = tid >> 5, h = l >> 4;
+
+    long long tile = blockIdx.x;
+    int buf = 0;
+    RingTile tl;
+    if (tile < ntiles) {
+        tl = ring_tile_at<G>(tile, a.nframes, a.nch);
+        ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16);
+    }
+    cp_async_commit();
+    while (tile < ntiles) {
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+            const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
+            ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES, aligned16);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();          // everything but the group just committed has landed
+        __syncthreads();
+
+        const long long fbase = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
+        ring_tile_lane<G>(smem, (uint32_t)(G::LUT_BYTES + buf * G::TILE_BYTES), tid, a_tile,
+                          [&](int round, const double (&sums)[4]) {
+                              ring_emit<G>(a, tl, h, fbase + 4LL * round * G::BLK_PER_ROUND, sums, out_aligned16);
+                          },
+                          RingNoTrace());
+        __syncthreads();             // tile `buf` is free again
+        tile = next;
+        buf ^= 1;
+        if (tile < ntiles) tl = ring_tile_at<G>(tile, a.nframes, a.nch);
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // glibc rand() by position.  r[i] = r[i-31] + r[i-3] (mod 2^32) for i >= 34, draw k = r[344+k]>>1.
 // With x^31 = x^28 + 1:  r[3+m+i] = sum_k c_k r[3+i+k],  c = x^m mod (x^31 - x^28 - 1).
 // ---------------------------------------------------------------------------------------------
@@ -312,6 +449,7 @@ struct dsdgpu_ctx {
     long long chunk_frames = 1LL << 21;
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
+    unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only)
     uint32_t* d_rand_pow2 = nullptr;
     uint32_t* d_rand_base = nullptr;
     cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
@@ -325,6 +463,7 @@ namespace {
 
 using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
+using Ring16x3 = RingGeom<16, 3>;
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -408,6 +547,22 @@ int launch_skew(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     return DSDGPU_OK;
 }
 
+template <class G>
+int launch_ring(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
+    const int smem = G::LUT_BYTES + 2 * G::TILE_BYTES;
+    static thread_local int configured_device = -1;
+    if (configured_device != ctx->device) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_ring_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_device = ctx->device;
+    }
+    const long long tiles = ring_tile_count<G>(a.nframes, a.nch);
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    decimate_ring_kernel<G><<<grid, G::NTHR, smem, st>>>(a);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
 int launch_direct(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     const int smem = ctx->nlut * 256 * (int)sizeof(double);
     static thread_local int configured_device = -1;
@@ -455,8 +610,15 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         a.dither = scratch.d_dither;
     }
     const bool skew_ok = (ctx->nlut == 72 && ctx->nstep == 4 && ctx->d_lut_skew != nullptr);
+    const bool ring_ok = (ctx->nlut == 72 && ctx->nstep == 4 && ctx->d_lut_ring != nullptr);
     int kernel = ctx->kernel;
-    if (kernel == DSDGPU_KERNEL_AUTO) kernel = skew_ok ? DSDGPU_KERNEL_SKEW : DSDGPU_KERNEL_DIRECT;
+    if (kernel == DSDGPU_KERNEL_AUTO)
+        kernel = ring_ok ? DSDGPU_KERNEL_RING : skew_ok ? DSDGPU_KERNEL_SKEW : DSDGPU_KERNEL_DIRECT;
+    if (kernel == DSDGPU_KERNEL_RING) {
+        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs nlut=72, nstep=4 and tables without -0.0 entries");
+        a.lut = ctx->d_lut_ring;
+        return launch_ring<Ring16x3>(ctx, a, st);
+    }
     if (kernel == DSDGPU_KERNEL_SKEW) {
         if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
         a.lut = ctx->d_lut_skew;
@@ -516,6 +678,17 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
         skew_build_lut_image<Skew512>(tab.data(), img.data());
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_skew), img.size()));
         CREATE_TRY(cudaMemcpy(ctx->d_lut_skew, img.data(), img.size(), cudaMemcpyHostToDevice));
+        // The ring kernel restarts an accumulator as fma(acc, 0.0, x): that is 0.0 + x bit for bit
+        // unless x is -0.0 (or anything is non-finite).  No real filter has such a table entry;
+        // a table that does simply keeps the older kernels.
+        bool plain = true;
+        for (double v : tab) plain = plain && std::isfinite(v) && !(v == 0.0 && std::signbit(v));
+        if (plain) {
+            std::vector<unsigned char> rimg(Ring16x3::LUT_BYTES);
+            ring_build_lut_image<Ring16x3>(tab.data(), rimg.data());
+            CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
+            CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
+        }
     }
     // dither generator constants
     {
@@ -547,6 +720,7 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     free_slot(ctx->own);
     if (ctx->d_lut_direct) cudaFree(ctx->d_lut_direct);
     if (ctx->d_lut_skew) cudaFree(ctx->d_lut_skew);
+    if (ctx->d_lut_ring) cudaFree(ctx->d_lut_ring);
     if (ctx->d_rand_pow2) cudaFree(ctx->d_rand_pow2);
     if (ctx->d_rand_base) cudaFree(ctx->d_rand_base);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -558,7 +732,7 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx) { return ctx ? ctx->err : g
 int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     if (!ctx || !key) return DSDGPU_ERR_ARG;
     if (!strcmp(key, "kernel")) {
-        if (value < DSDGPU_KERNEL_AUTO || value > DSDGPU_KERNEL_SKEW) return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
+        if (value < DSDGPU_KERNEL_AUTO || value > DSDGPU_KERNEL_RING) return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
         ctx->kernel = (int)value;
     } else if (!strcmp(key, "threads")) {
         if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
@@ -616,17 +790,26 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
     if (lo < in_first) lo = in_first;
     if (hi > in_first + in_count) hi = in_first + in_count;
     int64_t n = hi > lo ? hi - lo : 0;
-    const size_t dstride = ((size_t)n + 255) & ~(size_t)255;
+    // Place the bytes so that (p0 - first + 1) is a multiple of 16, `first` being the stream index
+    // of the first byte of the device buffer: the ring kernel's window loads are then bank-conflict
+    // free (ring_core.h).  The pad bytes in front count as part of the source (d_in stays 16-byte
+    // aligned): either they are older than anything a frame of this run reads, or -- when the run
+    // starts before the caller's first byte -- they are set to the fill byte they stand for.
+    const int64_t pad = ((lo - p0 - 1) % 16 + 16) % 16;
+    const bool reads_before_source = p0 - (ctx->nlut - 1) < lo;
+    const size_t dstride = ((size_t)(n + pad) + 255) & ~(size_t)255;
     rc = ensure(ctx, &s.d_in, &s.in_cap, dstride * ctx->nch + 256);
     if (rc) return rc;
     const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
     const size_t out_bytes = (size_t)nframes * ctx->nch * elem;
     rc = ensure(ctx, reinterpret_cast<unsigned char**>(&s.d_out), &s.out_cap, out_bytes);
     if (rc) return rc;
+    if (pad > 0 && reads_before_source)
+        CUDA_TRY(ctx, cudaMemset2DAsync(s.d_in, dstride, fill, (size_t)pad, (size_t)ctx->nch, s.stream));
     if (n > 0)
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in + pad, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
                                         (size_t)ctx->nch, cudaMemcpyHostToDevice, s.stream));
-    rc = enqueue_decimate(ctx, s, s.d_in, dstride, lo, n, fill, p0, nframes, scale, dither_amp, clip,
+    rc = enqueue_decimate(ctx, s, s.d_in, dstride, lo - pad, n + pad, fill, p0, nframes, scale, dither_amp, clip,
                           dither_first_sample, out_kind, s.d_out, s.stream);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));

@@ -1,0 +1,314 @@
+// ring_core.h -- per-lane logic of the "ring" decimation kernel (divide-by-32 filters, 72 tables).
+//
+// Shared between the CUDA kernel (dsdgpu.cu) and the host-side lane emulator
+// (tests/cpp/emu_ring.cpp): a lane never talks to another lane inside this function, so running
+// it once per thread id over a byte image of the CTA's shared memory reproduces the kernel, and
+// the recorded addresses give the exact wavefront count of every shared-memory instruction.
+//
+// What it computes (reference src/dsd_decimator.cpp:194-198): for each output frame a lane owns,
+// sum = 0.0; for t = 0..71: sum += LUT[t][byte(P - t)], fp64, in this order.
+//
+// Layout.  Tables are stored entry-major, row e = 80 doubles: slots 0..71 hold LUT[t][e], slots
+// 72..79 repeat taps 64..71.  A row is 640 B, a multiple of 128 B, so the bank pair of a load
+// is (slot mod 16) whatever the byte value is.
+//
+// Schedule.  Lane j of a half-warp (j = its skew, a permutation of 0..15) runs j taps behind
+// lane 0, and every lane walks taps 0,1,...,71,0,1,... with no idle steps: at static step s of a
+// period lane j is at tap s-j of its current frame (s >= j) or at tap 72+s-j of its previous
+// frame (s < j, "wrapped").  Unwrapped lanes sit on bank pair (s-j) mod 16 -- all distinct.  A
+// wrapped lane's natural slot 72+s-j lies 8 bank pairs off that pattern (72 mod 16 = 8), which
+// would collide with lane j-8 or j+8; the two lanes of such a pair trade places: lanes j >= 8
+// read their taps 64..71 from the duplicate slots 72..79 (slot = tap + 8).  With that every
+// LDS.64 of every half-warp covers 16 distinct bank pairs: one 128-byte wavefront, and all 72
+// steps of a period are real taps (the emulator asserts both).
+//
+// Each lane carries KF = 4 consecutive frames (4 independent fp64 chains).  Frame k+1 uses at
+// step s the byte frame k used at step s-4, so one 32-bit window word feeds 16 table loads.
+// A frame ends at a lane-dependent step (s = j-1), so in steps 0..15 the accumulator is
+// captured into `stash` and restarted under the predicate (j == s): acc = fma(acc, 0 or 1, x),
+// which equals acc + x resp. 0.0 + x bit for bit (x = -0.0 aside, see dsdgpu_create).  After
+// step 15 all 32 lanes hold their finished frames in `stash` and emit together.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RING_HD __host__ __device__ __forceinline__
+#else
+#include <cmath>
+#define RING_HD inline
+#endif
+
+namespace dsdgpu {
+
+template <int NWARP_, int KR_>
+struct RingGeom {
+    static constexpr int NLUT = 72;                   // tables = steps per period
+    static constexpr int NSTEP = 4;                   // bytes between successive frames
+    static constexpr int KF = 4;                      // consecutive frames per lane
+    static constexpr int KR = KR_;                    // rounds (periods) per tile
+    static constexpr int NWARP = NWARP_;
+    static constexpr int NTHR = 32 * NWARP;
+    static constexpr int ROW = 80;                    // doubles per table row
+    static constexpr int ROW_BYTES = ROW * 8;
+    static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
+    static constexpr int LUT_BYTES = GUARD_BYTES + 256 * ROW_BYTES;
+    // a tile has two halves (lanes 0-15 / 16-31 of every warp), each with its own byte buffer
+    static constexpr int BLK_PER_ROUND = 16 * NWARP;  // 4-frame blocks per half per round
+    static constexpr int FR_PER_ROUND = KF * BLK_PER_ROUND;
+    static constexpr int NTP = KR * FR_PER_ROUND;     // frames per half per tile
+    static constexpr int HOP = NSTEP * FR_PER_ROUND;  // bytes between a lane's rounds
+    static constexpr int BACK = HOP + NLUT;           // this round's window -> previous round's tail
+    static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
+    static constexpr int HALF_BYTES = NSTEP * NTP + 256;
+    static constexpr int TILE_BYTES = 2 * HALF_BYTES;
+    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == 0, "staging chunks / bank pattern");
+    static_assert(HOP % 16 == 0 && BACK % 4 == 0, "windows of successive rounds share their byte phase");
+};
+
+RING_HD uint32_t ring_funnel_r(uint32_t lo, uint32_t hi, uint32_t shift) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> shift);
+#endif
+}
+
+RING_HD uint32_t ring_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int n = 0; n < 4; ++n) r |= (uint32_t)((v >> (8 * ((sel >> (4 * n)) & 7))) & 0xff) << (8 * n);
+    return r;
+#endif
+}
+
+template <int K>
+RING_HD uint32_t ring_byte(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0u, 0x4440u | (uint32_t)K);
+#else
+    return (x >> (8 * K)) & 0xffu;
+#endif
+}
+
+RING_HD uint32_t ring_lds_u32(const unsigned char* smem, uint32_t off) {
+    return *reinterpret_cast<const uint32_t*>(smem + off);
+}
+RING_HD double ring_lds_f64(const unsigned char* smem, uint32_t off) {
+    return *reinterpret_cast<const double*>(smem + off);
+}
+RING_HD double ring_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+RING_HD double ring_fma(double a, double m, double b) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, m, b);
+#else
+    return std::fma(a, m, b);
+#endif
+}
+
+struct RingNoTrace {
+    RING_HD void lut(int, int, int, int, uint32_t) const {}
+    RING_HD void word(int, int, int, uint32_t) const {}
+};
+
+// Skew of lane l (0..31) of a warp.  Within each half-warp the 16 values are a permutation of
+// 0..15 (conflict-free table loads); across the warp the quarter (j >> 2) is arranged so that
+// the 32 window words of one LDS.32 -- lane stride 16 B plus j bytes -- fall in 32 distinct
+// banks when the tile is 16-byte aligned to the frame grid.
+RING_HD int ring_lane_skew(int l) {
+    const int h = (l >> 4) & 1, i = l & 15;
+    const int q = 2 * (((i >> 2) & 1) ^ h) + ((i >> 3) & 1);
+    return (i & 3) + 4 * q;
+}
+
+struct RingLane {
+    double acc[4], stash[4];
+    uint32_t qn[3], qo[3];      // previous window words of the current / the wrapped frame set
+    uint32_t ln, lo;            // last aligned word loaded from either window
+    uint32_t loff;              // table offset of this lane at static step 0 (moves at j-8 and j)
+};
+
+// Steps 4*G0 .. 4*G1-1 of one period for one lane.
+//   wnew   smem byte offset of aligned word L(0) of this round's window
+//   wold   the same for the previous round's window (its groups 18.. continue here as wrapped taps)
+template <class G, int G0, int G1, class Trace>
+RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t wold,
+                         uint32_t shift, int j, uint32_t lnew, const uint32_t (&sel)[4], int tid,
+                         int period, const Trace& tr) {
+#pragma unroll
+    for (int g = G0; g < G1; ++g) {
+        uint32_t x[4];
+        {
+            const uint32_t a = wnew - 4u * (uint32_t)g;
+            const uint32_t w = ring_lds_u32(smem, a);
+            tr.word(tid, period, 2 * g, a);
+            const uint32_t v = ring_funnel_r(w, r.ln, shift);
+            r.ln = w;
+            x[0] = v; x[1] = r.qn[0]; x[2] = r.qn[1]; x[3] = r.qn[2];
+            r.qn[2] = r.qn[1]; r.qn[1] = r.qn[0]; r.qn[0] = v;
+        }
+        if (g < 4) {
+            const uint32_t a = wold - 4u * (uint32_t)(18 + g);
+            const uint32_t w = ring_lds_u32(smem, a);
+            tr.word(tid, period, 2 * g + 1, a);
+            const uint32_t v = ring_funnel_r(w, r.lo, shift);
+            r.lo = w;
+            x[0] = ring_prmt(x[0], v, sel[g]);
+            x[1] = ring_prmt(x[1], r.qo[0], sel[g]);
+            x[2] = ring_prmt(x[2], r.qo[1], sel[g]);
+            x[3] = ring_prmt(x[3], r.qo[2], sel[g]);
+            r.qo[2] = r.qo[1]; r.qo[1] = r.qo[0]; r.qo[0] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = 4 * g + u;
+            bool first = false;
+            if (s < 16) {
+                if (s < 8 && j == s + 8) r.loff += 64u;        // taps 64..71 from the duplicate slots
+                first = (j == s);
+                if (first) r.loff = lnew;                        // tap 0 of the next frame set
+            }
+            const double mult = first ? 0.0 : 1.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t e;
+                if (u == 0) e = ring_byte<3>(x[k]);
+                else if (u == 1) e = ring_byte<2>(x[k]);
+                else if (u == 2) e = ring_byte<1>(x[k]);
+                else e = ring_byte<0>(x[k]);
+                const uint32_t addr = e * (uint32_t)G::ROW_BYTES + r.loff + 8u * (uint32_t)s;
+                tr.lut(tid, period, s, k, addr);
+                const double v = ring_lds_f64(smem, addr);
+                if (s < 16) {
+                    if (first) r.stash[k] = r.acc[k];
+                    r.acc[k] = ring_fma(r.acc[k], mult, v);
+                } else {
+                    r.acc[k] = ring_add(r.acc[k], v);
+                }
+            }
+        }
+    }
+}
+
+// All KR rounds of one thread in one tile.
+//   smem      base of the CTA's shared memory; the table image sits at offset 0
+//   tile_off  byte offset of this tile's two byte buffers inside smem (multiple of 128)
+//   a_tile    pmin - t0: offset inside a half's buffer of the newest byte of the half's frame 0
+//   emit(round, sums)  once per round: sums[k] belongs to frame
+//             half_first + 4*(round*BLK_PER_ROUND + 16*warp + (lane & 15)) + k
+template <class G, class Emit, class Trace>
+RING_HD void ring_tile_lane(const unsigned char* smem, uint32_t tile_off, int tid, int a_tile,
+                            Emit&& emit, const Trace& tr) {
+    const int l = tid & 31, w = tid >> 5, h = l >> 4;
+    const int j = ring_lane_skew(l);
+    const int a0 = a_tile + 16 * (16 * w + (l & 15)) + j;      // newest byte of frame 0 at "s = j"
+    const int phi = (a0 + 1) & 3;
+    const uint32_t shift = 8u * (uint32_t)phi;
+    const uint32_t wb = tile_off + (uint32_t)(h * G::HALF_BYTES) + (uint32_t)(a0 - 3 - phi);
+    const uint32_t lnew = (uint32_t)(G::GUARD_BYTES - 8 * j);
+    const uint32_t lwrap = (uint32_t)(G::GUARD_BYTES + 8 * (G::NLUT - j));
+    uint32_t sel[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v |= (uint32_t)((4 * g + u >= j) ? 3 - u : 7 - u) << (4 * (3 - u));
+        sel[g] = v;
+    }
+
+    RingLane r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r.acc[k] = 0.0; r.stash[k] = 0.0; }
+    r.qo[0] = r.qo[1] = r.qo[2] = 0u;
+    r.lo = 0u;
+    for (int n = 0; n <= G::KR; ++n) {
+        uint32_t wnew = wb + (uint32_t)(n * G::HOP);
+        const uint32_t wold = wnew - (uint32_t)G::HOP;
+        if (n == G::KR) wnew = wold;                             // drain: stay inside the tile
+        // the three words ahead of group 0 (frames 1..3 start 4, 8, 12 bytes further on)
+        {
+            const uint32_t l4 = ring_lds_u32(smem, wnew + 16u), l3 = ring_lds_u32(smem, wnew + 12u);
+            const uint32_t l2 = ring_lds_u32(smem, wnew + 8u), l1 = ring_lds_u32(smem, wnew + 4u);
+            tr.word(tid, n, 100, wnew + 16u); tr.word(tid, n, 101, wnew + 12u);
+            tr.word(tid, n, 102, wnew + 8u); tr.word(tid, n, 103, wnew + 4u);
+            r.qn[2] = ring_funnel_r(l3, l4, shift);
+            r.qn[1] = ring_funnel_r(l2, l3, shift);
+            r.qn[0] = ring_funnel_r(l1, l2, shift);
+            r.ln = l1;
+        }
+        r.loff = lwrap;
+        ring_groups<G, 0, 4>(r, smem, wnew, wold, shift, j, lnew, sel, tid, n, tr);
+        if (n > 0) emit(n - 1, r.stash);
+        if (n == G::KR) break;
+        ring_groups<G, 4, 18>(r, smem, wnew, wold, shift, j, lnew, sel, tid, n, tr);
+        // this round's last words are the next round's wrapped history
+        r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];
+        r.lo = r.ln;
+    }
+}
+
+// Where the byte buffer of a tile half starts in the stream.  f0 = first frame of the half.
+//   t0     stream index of byte 0 of the buffer: a multiple of 16 away from in_first (so the
+//          16-byte staging chunks are aligned in the source buffer) and FRONT..FRONT+15 bytes
+//          before pmin = p0 + f0*NSTEP, the newest byte of the half's first frame
+//   a_tile pmin - t0 (the same for every tile of a launch: NTP*NSTEP is a multiple of 16)
+template <class G>
+RING_HD void ring_half_origin(long long p0, long long in_first, long long f0, long long& t0, int& a_tile) {
+    const long long pmin = p0 + f0 * G::NSTEP;
+    long long rel = pmin - G::FRONT - in_first;
+    rel = (rel >= 0) ? (rel & ~15LL) : -((-rel + 15) & ~15LL);
+    t0 = in_first + rel;
+    a_tile = (int)(pmin - t0);
+}
+
+// Tiles of a launch.  Channels are taken two at a time (the halves of a warp then hold the same
+// frames of channels c and c+1 and write whole frame pairs); an odd last channel is taken alone,
+// its halves holding consecutive frame ranges.  Pair tiles are numbered channel-pair fastest.
+struct RingTile { int c[2]; long long f0[2]; };
+
+template <class G>
+RING_HD long long ring_tile_count(long long nframes, int nch) {
+    const long long nr = (nframes + G::NTP - 1) / G::NTP, nr2 = (nframes + 2 * G::NTP - 1) / (2 * G::NTP);
+    return nr * (nch / 2) + nr2 * (nch & 1);
+}
+
+template <class G>
+RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
+    const long long nr = (nframes + G::NTP - 1) / G::NTP;
+    const int npair = nch / 2;
+    RingTile t;
+    if (tile < nr * npair) {
+        const long long rr = tile / npair;
+        const int u = (int)(tile - rr * npair);
+        t.c[0] = 2 * u; t.c[1] = 2 * u + 1;
+        t.f0[0] = t.f0[1] = rr * G::NTP;
+    } else {
+        const long long rr = tile - nr * npair;
+        t.c[0] = t.c[1] = nch - 1;
+        t.f0[0] = 2 * rr * G::NTP; t.f0[1] = t.f0[0] + G::NTP;
+    }
+    return t;
+}
+
+// Host side of the layout: writes the shared-memory image of the tables.
+//   lut   [72][256] doubles as the reference builds them (dsd_decimator.cpp:117-151)
+template <class G>
+inline void ring_build_lut_image(const double* lut, unsigned char* image) {
+    double* d = reinterpret_cast<double*>(image);
+    for (int i = 0; i < G::LUT_BYTES / 8; ++i) d[i] = 0.0;
+    double* rows = reinterpret_cast<double*>(image + G::GUARD_BYTES);
+    for (int e = 0; e < 256; ++e) {
+        for (int t = 0; t < G::NLUT; ++t) rows[e * G::ROW + t] = lut[t * 256 + e];
+        for (int m = 0; m < 8; ++m) rows[e * G::ROW + G::NLUT + m] = lut[(64 + m) * 256 + e];
+    }
+}
+
+}  // namespace dsdgpu

@@ -49,9 +49,10 @@ enum { DSDGPU_OUT_INT32 = 0, DSDGPU_OUT_FLOAT64 = 1 };
 
 /* Kernel selection, for tests and benchmarking (dsdgpu_set_option "kernel"). */
 enum {
-    DSDGPU_KERNEL_AUTO = 0,   /* skewed kernel when the geometry supports it, else direct */
+    DSDGPU_KERNEL_AUTO = 0,   /* ring kernel when the geometry supports it, else direct */
     DSDGPU_KERNEL_DIRECT = 1, /* one thread per output sample, tables [t][byte] in smem */
-    DSDGPU_KERNEL_SKEW = 2    /* bank-conflict-free lane-skewed kernel (divide-by-32 filters) */
+    DSDGPU_KERNEL_SKEW = 2,   /* lane-skewed kernel, 80-step periods (divide-by-32 filters) */
+    DSDGPU_KERNEL_RING = 3    /* lane-skewed kernel, 72-step periods, 4 frames per lane (divide-by-32) */
 };
 
 /*

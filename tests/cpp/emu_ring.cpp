@@ -1,0 +1,163 @@
+// Host-side lane emulator for the ring kernel (dsf2flac_b200/csrc/ring_core.h).
+//
+// Runs ring_tile_lane() once per thread id over a byte image of the CTA's shared memory (table
+// image + one staged tile = two byte buffers), for every tile of a small multi-channel stream, and
+//   1. compares every emitted fp64 sum, bit for bit, with the straightforward
+//      sum_{t=0..71} lut[t][B_c(p - t)] in reference order (dsd_decimator.cpp:194-198), and
+//      checks that every (channel, frame) is emitted exactly once;
+//   2. bounds-checks every shared-memory address;
+//   3. replays the recorded addresses instruction by instruction and counts wavefronts:
+//      LDS.64 is served per half-warp (16 lanes x 8 B), LDS.32 per warp (32 lanes x 4 B); a
+//      wavefront serves one 4-byte word per bank (32 banks), equal addresses broadcast.
+// Prints one JSON line; exit code 0 iff all sums match, coverage is exact and every table load
+// is conflict free.
+//
+// usage: emu_ring <nwarp:16|8> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "ring_core.h"
+
+using namespace dsdgpu;
+
+struct Access { int tid, period, tag, k; uint32_t addr; };
+
+static size_t g_smem_size = 0;
+static long long g_oob = 0;
+
+struct Recorder {
+    std::vector<Access>* lut_log;
+    std::vector<Access>* word_log;
+    void lut(int tid, int period, int s, int k, uint32_t a) const {
+        if ((size_t)a + 8 > g_smem_size || (a & 7)) ++g_oob;
+        if (lut_log) lut_log->push_back({tid, period, s, k, a});
+    }
+    void word(int tid, int period, int tag, uint32_t a) const {
+        if ((size_t)a + 4 > g_smem_size || (a & 3)) ++g_oob;
+        if (word_log) word_log->push_back({tid, period, tag, 0, a});
+    }
+};
+
+static int wavefronts(const std::vector<uint32_t>& addrs, int bytes_per_lane) {
+    std::map<int, std::vector<uint32_t>> per_bank;
+    for (uint32_t a : addrs)
+        for (int k = 0; k < bytes_per_lane / 4; ++k) {
+            uint32_t w = a / 4 + k;
+            auto& v = per_bank[w % 32];
+            bool seen = false;
+            for (uint32_t x : v) seen |= (x == w);
+            if (!seen) v.push_back(w);
+        }
+    size_t worst = 0;
+    for (auto& kv : per_bank) worst = kv.second.size() > worst ? kv.second.size() : worst;
+    return (int)worst;
+}
+
+template <class G>
+static int run(long long nframes, int nch, long long p0, long long in_first, long long in_count, unsigned seed) {
+    srand(seed);
+    std::vector<double> lut((size_t)G::NLUT * 256);
+    for (auto& v : lut) v = (rand() / (double)RAND_MAX - 0.5) * 0.35;
+    std::vector<std::vector<unsigned char>> src(nch, std::vector<unsigned char>((size_t)(in_count > 0 ? in_count : 1)));
+    for (auto& ch : src)
+        for (auto& b : ch) b = (unsigned char)(rand() & 0xff);
+    const unsigned char fill = 0x69;
+    auto stream_byte = [&](int c, long long j) -> unsigned char {
+        long long o = j - in_first;
+        return (o >= 0 && o < in_count) ? src[c][(size_t)o] : fill;
+    };
+
+    // smem image: tables, then (as in the kernel) two tile buffers; the emulated tile lives in
+    // buffer `buf`, the other one holds noise
+    std::vector<unsigned char> smem((size_t)G::LUT_BYTES + 2 * G::TILE_BYTES);
+    g_smem_size = smem.size();
+    ring_build_lut_image<G>(lut.data(), smem.data());
+    for (size_t k = G::LUT_BYTES; k < smem.size(); ++k) smem[k] = (unsigned char)(rand() & 0xff);
+
+    std::vector<std::vector<unsigned char>> seen(nch, std::vector<unsigned char>((size_t)nframes, 0));
+    long long mismatches = 0, checked = 0, dup = 0;
+    long long lut_instr = 0, lut_wavefronts = 0, word_instr = 0, word_wavefronts = 0;
+    const long long ntiles = ring_tile_count<G>(nframes, nch);
+    for (long long tile = 0; tile < ntiles; ++tile) {
+        const RingTile tl = ring_tile_at<G>(tile, nframes, nch);
+        const int buf = (int)(tile & 1);
+        const uint32_t tile_off = (uint32_t)(G::LUT_BYTES + buf * G::TILE_BYTES);
+        int a_tile = 0;
+        for (int h = 0; h < 2; ++h) {
+            long long t0; int a;
+            ring_half_origin<G>(p0, in_first, tl.f0[h], t0, a);
+            if ((t0 - in_first) % 16 != 0 || a < G::FRONT || a > G::FRONT + 15) { fprintf(stderr, "bad half origin\n"); return 2; }
+            if (h == 1 && a != a_tile) { fprintf(stderr, "halves disagree on a_tile\n"); return 2; }
+            a_tile = a;
+            for (int k = 0; k < G::HALF_BYTES; ++k) smem[(size_t)tile_off + h * G::HALF_BYTES + k] = stream_byte(tl.c[h], t0 + k);
+        }
+        std::vector<Access> lut_log, word_log;
+        const bool trace = (tile == 0 || tile == ntiles - 1);
+        Recorder rec{trace ? &lut_log : nullptr, trace ? &word_log : nullptr};
+        for (int tid = 0; tid < G::NTHR; ++tid) {
+            const int l = tid & 31, w = tid >> 5, h = l >> 4;
+            ring_tile_lane<G>(smem.data(), tile_off, tid, a_tile,
+                              [&](int round, const double (&sums)[4]) {
+                                  for (int k = 0; k < 4; ++k) {
+                                      const long long f = tl.f0[h] + 4LL * ((long long)round * G::BLK_PER_ROUND + 16 * w + (l & 15)) + k;
+                                      if (f >= nframes) continue;
+                                      const int c = tl.c[h];
+                                      const long long p = p0 + f * G::NSTEP;
+                                      double ref = 0.0;
+                                      for (int t = 0; t < G::NLUT; ++t) ref += lut[(size_t)t * 256 + stream_byte(c, p - t)];
+                                      ++checked;
+                                      if (seen[c][(size_t)f]++) ++dup;
+                                      if (memcmp(&ref, &sums[k], 8) != 0) {
+                                          if (mismatches < 5) fprintf(stderr, "mismatch c=%d f=%lld tid=%d round=%d k=%d got %.17g want %.17g\n", c, f, tid, round, k, sums[k], ref);
+                                          ++mismatches;
+                                      }
+                                  }
+                              },
+                              rec);
+        }
+        if (trace) {
+            std::map<long long, std::vector<uint32_t>> groups;
+            for (auto& a : lut_log) {
+                long long key = ((((long long)(a.tid / 16) * 64 + a.period) * 128 + a.tag) * 4 + a.k);
+                groups[key].push_back(a.addr);
+            }
+            for (auto& kv : groups) { ++lut_instr; lut_wavefronts += wavefronts(kv.second, 8); }
+            std::map<long long, std::vector<uint32_t>> wg;
+            for (auto& a : word_log) {
+                long long key = (((long long)(a.tid / 32) * 64 + a.period) * 128 + a.tag);
+                wg[key].push_back(a.addr);
+            }
+            for (auto& kv : wg) { ++word_instr; word_wavefronts += wavefronts(kv.second, 4); }
+        }
+    }
+    long long missing = 0;
+    for (auto& ch : seen)
+        for (auto v : ch) missing += (v == 0);
+    printf("{\"nwarp\": %d, \"kr\": %d, \"frames\": %lld, \"nch\": %d, \"tiles\": %lld, \"checked\": %lld, \"mismatches\": %lld, "
+           "\"missing\": %lld, \"duplicates\": %lld, \"oob\": %lld, \"lut_halfwarp_loads\": %lld, \"lut_wavefronts\": %lld, "
+           "\"word_loads\": %lld, \"word_wavefronts\": %lld}\n",
+           G::NWARP, G::KR, nframes, nch, ntiles, checked, mismatches, missing, dup, g_oob, lut_instr, lut_wavefronts,
+           word_instr, word_wavefronts);
+    if (missing || dup || checked != nframes * nch) return 3;
+    if (mismatches) return 1;
+    if (g_oob) return 5;
+    if (lut_wavefronts != lut_instr) return 4;
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 9) { fprintf(stderr, "usage: emu_ring nwarp kr nframes nch p0 in_first in_count seed\n"); return 64; }
+    const int nwarp = atoi(argv[1]), kr = atoi(argv[2]);
+    const long long nframes = atoll(argv[3]);
+    const int nch = atoi(argv[4]);
+    const long long p0 = atoll(argv[5]), in_first = atoll(argv[6]), in_count = atoll(argv[7]);
+    const unsigned seed = (unsigned)atoi(argv[8]);
+    if (nwarp == 16 && kr == 3) return run<RingGeom<16, 3>>(nframes, nch, p0, in_first, in_count, seed);
+    if (nwarp == 16 && kr == 1) return run<RingGeom<16, 1>>(nframes, nch, p0, in_first, in_count, seed);
+    if (nwarp == 8 && kr == 6) return run<RingGeom<8, 6>>(nframes, nch, p0, in_first, in_count, seed);
+    fprintf(stderr, "unsupported geometry\n");
+    return 64;
+}

@@ -50,11 +50,12 @@ def test_config2_full_properties(oracle):
     scale, amp, clip = filters.app_params(24, dither=False)
     lut = filters.build_lut(fir, 1)
     outs = {}
-    for name, k in (("skew", capi.KERNEL_SKEW), ("direct", capi.KERNEL_DIRECT)):
+    for name, k in (("ring", capi.KERNEL_RING), ("skew", capi.KERNEL_SKEW), ("direct", capi.KERNEL_DIRECT)):
         with capi.DsdGpu(lut, 2, fir.nstep) as g:
             g.set_option("kernel", k)
             outs[name] = g.decimate_host(data, fir.nlut, n, scale, amp, clip)
     assert np.array_equal(outs["skew"], outs["direct"])
+    assert np.array_equal(outs["ring"], outs["direct"])
     # 8-way time/channel shards with halos == unsharded
     job = batch.Job(data, fs, 176400, msb_flag=True, bits=24, dither=False)
     runner = batch.BatchRunner()

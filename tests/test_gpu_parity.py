@@ -14,19 +14,19 @@ pytestmark = pytest.mark.gpu
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
 RATES = {32: 88200, 16: 176400, 8: 352800}
-KERNELS = {"direct": capi.KERNEL_DIRECT, "skew": capi.KERNEL_SKEW, "auto": capi.KERNEL_AUTO}
+KERNELS = {"direct": capi.KERNEL_DIRECT, "skew": capi.KERNEL_SKEW, "ring": capi.KERNEL_RING, "auto": capi.KERNEL_AUTO}
 
 
 def make(ratio, msb, nch, kernel="auto", precision=64):
     fir = filters.FILTERS[ratio]
-    if kernel == "skew" and ratio != 32:
-        pytest.skip("the skewed kernel exists for the divide-by-32 filter only")
+    if kernel in ("skew", "ring") and ratio != 32:
+        pytest.skip("the lane-skewed kernels exist for the divide-by-32 filter only")
     g = capi.DsdGpu(filters.build_lut(fir, msb), nch, fir.nstep, lut_precision=precision)
     g.set_option("kernel", KERNELS[kernel])
     return fir, g
 
 
-@pytest.mark.parametrize("kernel", ["direct", "skew"])
+@pytest.mark.parametrize("kernel", ["direct", "skew", "ring"])
 @pytest.mark.parametrize("msb", [0, 1])
 @pytest.mark.parametrize("ratio", [32, 16, 8])
 def test_app_parity_all_depths(oracle, ratio, msb, kernel):
@@ -43,7 +43,7 @@ def test_app_parity_all_depths(oracle, ratio, msb, kernel):
     g.close()
 
 
-@pytest.mark.parametrize("kernel", ["direct", "skew"])
+@pytest.mark.parametrize("kernel", ["direct", "skew", "ring"])
 @pytest.mark.parametrize("ratio", [32, 16, 8])
 def test_fp64_sums_bit_exact_incl_idle_prefill(oracle, ratio, kernel):
     fir, g = make(ratio, 1, 3, kernel)
@@ -86,7 +86,7 @@ def test_golden_sigma_delta_both_packings():
         g.close()
 
 
-@pytest.mark.parametrize("kernel", ["direct", "skew"])
+@pytest.mark.parametrize("kernel", ["direct", "skew", "ring"])
 def test_ragged_windows_and_tiny_calls(oracle, kernel):
     fir, g = make(32, 0, 1, kernel)
     data = seeded_bytes(1, 30000, 3)
@@ -205,6 +205,9 @@ def test_option_errors():
     fir, g = make(16, 1, 2)
     with pytest.raises(capi.DsdGpuError):
         g.set_option("no_such_knob", 1)
+    g.set_option("kernel", capi.KERNEL_RING)
+    with pytest.raises(capi.DsdGpuError, match="ring kernel needs"):
+        g.decimate_host(seeded_bytes(2, 1000, 1), 30, 10, 1.0)
     g.set_option("kernel", capi.KERNEL_SKEW)
     with pytest.raises(capi.DsdGpuError, match="skew kernel needs"):
         g.decimate_host(seeded_bytes(2, 1000, 1), 30, 10, 1.0)
