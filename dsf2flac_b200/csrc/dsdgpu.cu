@@ -249,12 +249,20 @@ __device__ __forceinline__ int quantise_i32(const DecimateArgs& a, long long fra
     return __double2int_rz(round(quantise_tail(sum, a.scale, a.dither_amp, dith, a.clip)));
 }
 
-// Four consecutive frames fb..fb+3 of channel c held by this lane; its partner (lane ^ 16) holds
-// the same frames of channel c+1 (pair tile) or the frames NTP further on (single tile).
+// Where a lane's four frames of one period go: frames fb..fb+3 of channel c.  Its partner
+// (lane ^ 16) holds the same frames of channel c+1 (pair tile, c0 = the even channel) or frames
+// NTP further on of the same channel (single tile).
+struct RingDest {
+    long long fb;
+    int c, c0;
+    bool pair;
+};
+
 template <class G>
-__device__ __forceinline__ void ring_emit(const DecimateArgs& a, const RingTile& tl, int h, long long fb,
-                                          const double (&sums)[4], bool out_aligned16) {
-    const int c = h ? tl.c[1] : tl.c[0];
+__device__ __forceinline__ void ring_emit(const DecimateArgs& a, const RingDest& d, int h, const double (&sums)[4],
+                                          bool out_aligned16) {
+    const long long fb = d.fb;
+    const int c = d.c;
     if (a.out_kind != DSDGPU_OUT_INT32) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -265,20 +273,18 @@ __device__ __forceinline__ void ring_emit(const DecimateArgs& a, const RingTile&
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = (fb + k < a.nframes) ? quantise_i32(a, fb + k, c, sums[k]) : 0;
     int32_t* out = reinterpret_cast<int32_t*>(a.out);
-    const bool pair = tl.c[1] != tl.c[0];
-    if (pair && (a.nch & 1) == 0) {
+    if (d.pair && (a.nch & 1) == 0) {
         // trade halves: lane h=0 ends up with frames fb, fb+1 of both channels, lane h=1 with fb+2, fb+3
         const int s0 = __shfl_xor_sync(0xffffffffu, h ? v[0] : v[2], 16);
         const int s1 = __shfl_xor_sync(0xffffffffu, h ? v[1] : v[3], 16);
         const long long f = fb + 2 * h;
-        const int c0 = tl.c[0];
         const int2 lo2 = h ? make_int2(s0, v[2]) : make_int2(v[0], s0);
         const int2 hi2 = h ? make_int2(s1, v[3]) : make_int2(v[1], s1);
         if (a.nch == 2 && out_aligned16 && f + 1 < a.nframes) {
             *reinterpret_cast<int4*>(out + f * 2) = make_int4(lo2.x, lo2.y, hi2.x, hi2.y);
         } else {
-            if (f < a.nframes) *reinterpret_cast<int2*>(out + f * a.nch + c0) = lo2;
-            if (f + 1 < a.nframes) *reinterpret_cast<int2*>(out + (f + 1) * a.nch + c0) = hi2;
+            if (f < a.nframes) *reinterpret_cast<int2*>(out + f * a.nch + d.c0) = lo2;
+            if (f + 1 < a.nframes) *reinterpret_cast<int2*>(out + (f + 1) * a.nch + d.c0) = hi2;
         }
     } else if (a.nch == 1 && out_aligned16 && fb + 3 < a.nframes) {
         *reinterpret_cast<int4*>(out + fb) = make_int4(v[0], v[1], v[2], v[3]);
@@ -307,6 +313,9 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         ring_half_origin<G>(a.p0, a.in_first, 0, t0, a_tile);   // the same for every half of the launch
     }
     const int l = tid & 31, w = tid >> 5, h = l >> 4;
+    RingLane lane;
+    const uint32_t w0 = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lane, tid, a_tile));
+    uint32_t loff = 0;
 
     long long tile = blockIdx.x;
     int buf = 0;
@@ -316,28 +325,46 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16);
     }
     cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    RingDest prev;
+    bool have_prev = false;
     while (tile < ntiles) {
         const long long next = tile + gridDim.x;
-        if (next < ntiles) {
-            const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
-            ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES, aligned16);
+        RingDest cur;
+        cur.c = h ? tl.c[1] : tl.c[0];
+        cur.c0 = tl.c[0];
+        cur.pair = tl.c[1] != tl.c[0];
+        cur.fb = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
+#pragma unroll 1
+        for (int n = 0; n < G::KR; ++n) {
+            const uint32_t wnew = w0 + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
+            ring_head<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
+            if (have_prev) ring_emit<G>(a, prev, h, lane.p, out_aligned16);
+            if (n == 0) {
+                __syncthreads();     // nobody reads the other buffer (the previous tile) any more
+                if (next < ntiles) {
+                    const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
+                    ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES, aligned16);
+                }
+                cp_async_commit();
+            }
+            ring_tail<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
+            prev = cur;
+            have_prev = true;
+            cur.fb += 4LL * G::BLK_PER_ROUND;
         }
-        cp_async_commit();
-        cp_async_wait<1>();          // everything but the group just committed has landed
-        __syncthreads();
-
-        const long long fbase = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
-        ring_tile_lane<G>(smem, (uint32_t)(G::LUT_BYTES + buf * G::TILE_BYTES), tid, a_tile,
-                          [&](int round, const double (&sums)[4]) {
-                              ring_emit<G>(a, tl, h, fbase + 4LL * round * G::BLK_PER_ROUND, sums, out_aligned16);
-                          },
-                          RingNoTrace());
-        __syncthreads();             // tile `buf` is free again
+        cp_async_wait<0>();
+        __syncthreads();             // the next tile has landed and is visible to every lane
         tile = next;
         buf ^= 1;
         if (tile < ntiles) tl = ring_tile_at<G>(tile, a.nframes, a.nch);
     }
-    cp_async_wait<0>();
+    if (have_prev) {                 // the one drain of this CTA: 16 more steps finish the last frames
+        ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
+        ring_emit<G>(a, prev, h, lane.p, out_aligned16);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -445,6 +472,7 @@ struct dsdgpu_ctx {
     int sm_count = 0;
     int kernel = DSDGPU_KERNEL_AUTO;
     int threads = 512;
+    int ring_rounds = 3;                     // periods per tile of the ring kernel (1..3)
     int dither_stride = 0;                   // 0 = nch
     long long chunk_frames = 1LL << 21;
     double* d_lut_direct = nullptr;          // [nlut][256]
@@ -464,6 +492,8 @@ namespace {
 using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x3 = RingGeom<16, 3>;
+using Ring16x2 = RingGeom<16, 2>;
+using Ring16x1 = RingGeom<16, 1>;
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -617,6 +647,8 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     if (kernel == DSDGPU_KERNEL_RING) {
         if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs nlut=72, nstep=4 and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
+        if (ctx->ring_rounds == 1) return launch_ring<Ring16x1>(ctx, a, st);
+        if (ctx->ring_rounds == 2) return launch_ring<Ring16x2>(ctx, a, st);
         return launch_ring<Ring16x3>(ctx, a, st);
     }
     if (kernel == DSDGPU_KERNEL_SKEW) {
@@ -737,6 +769,9 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "threads")) {
         if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
         ctx->threads = (int)value;
+    } else if (!strcmp(key, "ring_rounds")) {
+        if (value < 1 || value > 3) return fail(ctx, DSDGPU_ERR_ARG, "ring_rounds must be 1, 2 or 3");
+        ctx->ring_rounds = (int)value;
     } else if (!strcmp(key, "dither_stride")) {
         if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");
         ctx->dither_stride = (int)value;

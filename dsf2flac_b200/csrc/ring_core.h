@@ -24,10 +24,14 @@
 //
 // Each lane carries KF = 4 consecutive frames (4 independent fp64 chains).  Frame k+1 uses at
 // step s the byte frame k used at step s-4, so one 32-bit window word feeds 16 table loads.
-// A frame ends at a lane-dependent step (s = j-1), so in steps 0..15 the accumulator is
-// captured into `stash` and restarted under the predicate (j == s): acc = fma(acc, 0 or 1, x),
-// which equals acc + x resp. 0.0 + x bit for bit (x = -0.0 aside, see dsdgpu_create).  After
-// step 15 all 32 lanes hold their finished frames in `stash` and emit together.
+// A frame ends at a lane-dependent step (s = j-1), so a lane keeps two sets of sums: `n` for the
+// frames started in this period and `p` for those started in the previous one.  In steps 0..15
+// each table value x goes to exactly one of them through multipliers instead of selects:
+// n = fma(x, 1 or 0, n), p = fma(x, 0 or 1, p) -- fma(x, 1, acc) is acc + x and fma(x, 0, acc) is
+// acc, bit for bit (x = -0.0 aside, see dsdgpu_create).  After step 15 every lane's `p` is
+// final and the warp emits together; at the end of the period p = n, n = 0.  The pipeline runs
+// on across tile boundaries (the previous window then lies in the other tile buffer), so there is
+// no drain except once at the very end of a CTA's work.
 #pragma once
 #include <stdint.h>
 
@@ -129,20 +133,55 @@ RING_HD int ring_lane_skew(int l) {
     return (i & 3) + 4 * q;
 }
 
+// Per-lane state.  It lives across periods AND across tiles: the pipeline never drains between
+// tiles, a lane finishes the last frames of one tile during the first 15 steps of the next.
 struct RingLane {
-    double acc[4], stash[4];
-    uint32_t qn[3], qo[3];      // previous window words of the current / the wrapped frame set
+    double n[4];                // sums of the frames started in the current period
+    double p[4];                // sums of the frames started in the previous period (finished by step 15)
+    uint32_t qn[3], qo[3];      // previous window words of the current / the previous frame set
     uint32_t ln, lo;            // last aligned word loaded from either window
-    uint32_t loff;              // table offset of this lane at static step 0 (moves at j-8 and j)
+    uint32_t wlast;             // smem offset of word L(0) of the previous period's window
+    // constants of the lane
+    int j;                      // skew
+    uint32_t shift;             // 8 * byte phase of the windows
+    uint32_t lnew, lwrap;       // table offset at static step 0: current frames / wrapped frames
+    uint32_t sel[4];            // byte selectors mixing the two windows in groups 0..3
 };
 
-// Steps 4*G0 .. 4*G1-1 of one period for one lane.
-//   wnew   smem byte offset of aligned word L(0) of this round's window
-//   wold   the same for the previous round's window (its groups 18.. continue here as wrapped taps)
+// a0 = a_tile + 16*(16*warp + (lane & 15)) + j: offset inside the half's buffer of the byte the
+// lane's frame 0 reads at its tap 0.  Returns the offset (inside the half's buffer) of L(0), the
+// aligned word holding that byte's predecessor window, for round 0.
+template <class G>
+RING_HD int ring_lane_init(RingLane& r, int tid, int a_tile) {
+    const int l = tid & 31, w = tid >> 5;
+    const int j = ring_lane_skew(l);
+    const int a0 = a_tile + 16 * (16 * w + (l & 15)) + j;
+    const int phi = (a0 + 1) & 3;
+    r.j = j;
+    r.shift = 8u * (uint32_t)phi;
+    r.lnew = (uint32_t)(G::GUARD_BYTES - 8 * j);
+    r.lwrap = (uint32_t)(G::GUARD_BYTES + 8 * (G::NLUT - j));
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v |= (uint32_t)((4 * g + u >= j) ? 3 - u : 7 - u) << (4 * (3 - u));
+        r.sel[g] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r.n[k] = 0.0; r.p[k] = 0.0; }
+    r.qo[0] = r.qo[1] = r.qo[2] = 0u;
+    r.qn[0] = r.qn[1] = r.qn[2] = 0u;
+    r.lo = r.ln = 0u;
+    r.wlast = 1024u;            // first period: the "previous window" is table bytes (finite garbage, never emitted)
+    return a0 - 3 - phi;
+}
+
+// Steps 4*G0 .. 4*G1-1 of one period.  wnew / wold: smem byte offsets of word L(0) of this
+// period's window and of the previous period's window (whose groups 18.. continue here).
 template <class G, int G0, int G1, class Trace>
-RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t wold,
-                         uint32_t shift, int j, uint32_t lnew, const uint32_t (&sel)[4], int tid,
-                         int period, const Trace& tr) {
+RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t wold, uint32_t& loff,
+                         int tid, int period, const Trace& tr) {
 #pragma unroll
     for (int g = G0; g < G1; ++g) {
         uint32_t x[4];
@@ -150,7 +189,7 @@ RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, 
             const uint32_t a = wnew - 4u * (uint32_t)g;
             const uint32_t w = ring_lds_u32(smem, a);
             tr.word(tid, period, 2 * g, a);
-            const uint32_t v = ring_funnel_r(w, r.ln, shift);
+            const uint32_t v = ring_funnel_r(w, r.ln, r.shift);
             r.ln = w;
             x[0] = v; x[1] = r.qn[0]; x[2] = r.qn[1]; x[3] = r.qn[2];
             r.qn[2] = r.qn[1]; r.qn[1] = r.qn[0]; r.qn[0] = v;
@@ -159,24 +198,28 @@ RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, 
             const uint32_t a = wold - 4u * (uint32_t)(18 + g);
             const uint32_t w = ring_lds_u32(smem, a);
             tr.word(tid, period, 2 * g + 1, a);
-            const uint32_t v = ring_funnel_r(w, r.lo, shift);
+            const uint32_t v = ring_funnel_r(w, r.lo, r.shift);
             r.lo = w;
-            x[0] = ring_prmt(x[0], v, sel[g]);
-            x[1] = ring_prmt(x[1], r.qo[0], sel[g]);
-            x[2] = ring_prmt(x[2], r.qo[1], sel[g]);
-            x[3] = ring_prmt(x[3], r.qo[2], sel[g]);
+            x[0] = ring_prmt(x[0], v, r.sel[g]);
+            x[1] = ring_prmt(x[1], r.qo[0], r.sel[g]);
+            x[2] = ring_prmt(x[2], r.qo[1], r.sel[g]);
+            x[3] = ring_prmt(x[3], r.qo[2], r.sel[g]);
             r.qo[2] = r.qo[1]; r.qo[1] = r.qo[0]; r.qo[0] = v;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
-            bool first = false;
+            double to_n = 1.0, to_p = 0.0;
             if (s < 16) {
-                if (s < 8 && j == s + 8) r.loff += 64u;        // taps 64..71 from the duplicate slots
-                first = (j == s);
-                if (first) r.loff = lnew;                        // tap 0 of the next frame set
+                // wrapped lanes (s < j) still add to their previous frames; the multipliers route
+                // each table value into exactly one of the two sums without a select:
+                // fma(x, 1, acc) == acc + x and fma(x, 0, acc) == acc, bit for bit
+                if (s < 8 && r.j == s + 8) loff += 64u;         // taps 64..71 from the duplicate slots
+                const bool cur = (s >= r.j);
+                if (r.j == s) loff = r.lnew;                     // tap 0 of the next frame set
+                to_n = cur ? 1.0 : 0.0;
+                to_p = cur ? 0.0 : 1.0;
             }
-            const double mult = first ? 0.0 : 1.0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t e;
@@ -184,75 +227,48 @@ RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, 
                 else if (u == 1) e = ring_byte<2>(x[k]);
                 else if (u == 2) e = ring_byte<1>(x[k]);
                 else e = ring_byte<0>(x[k]);
-                const uint32_t addr = e * (uint32_t)G::ROW_BYTES + r.loff + 8u * (uint32_t)s;
+                const uint32_t addr = e * (uint32_t)G::ROW_BYTES + loff + 8u * (uint32_t)s;
                 tr.lut(tid, period, s, k, addr);
                 const double v = ring_lds_f64(smem, addr);
                 if (s < 16) {
-                    if (first) r.stash[k] = r.acc[k];
-                    r.acc[k] = ring_fma(r.acc[k], mult, v);
+                    r.n[k] = ring_fma(v, to_n, r.n[k]);
+                    r.p[k] = ring_fma(v, to_p, r.p[k]);
                 } else {
-                    r.acc[k] = ring_add(r.acc[k], v);
+                    r.n[k] = ring_add(r.n[k], v);
                 }
             }
         }
     }
 }
 
-// All KR rounds of one thread in one tile.
-//   smem      base of the CTA's shared memory; the table image sits at offset 0
-//   tile_off  byte offset of this tile's two byte buffers inside smem (multiple of 128)
-//   a_tile    pmin - t0: offset inside a half's buffer of the newest byte of the half's frame 0
-//   emit(round, sums)  once per round: sums[k] belongs to frame
-//             half_first + 4*(round*BLK_PER_ROUND + 16*warp + (lane & 15)) + k
-template <class G, class Emit, class Trace>
-RING_HD void ring_tile_lane(const unsigned char* smem, uint32_t tile_off, int tid, int a_tile,
-                            Emit&& emit, const Trace& tr) {
-    const int l = tid & 31, w = tid >> 5, h = l >> 4;
-    const int j = ring_lane_skew(l);
-    const int a0 = a_tile + 16 * (16 * w + (l & 15)) + j;      // newest byte of frame 0 at "s = j"
-    const int phi = (a0 + 1) & 3;
-    const uint32_t shift = 8u * (uint32_t)phi;
-    const uint32_t wb = tile_off + (uint32_t)(h * G::HALF_BYTES) + (uint32_t)(a0 - 3 - phi);
-    const uint32_t lnew = (uint32_t)(G::GUARD_BYTES - 8 * j);
-    const uint32_t lwrap = (uint32_t)(G::GUARD_BYTES + 8 * (G::NLUT - j));
-    uint32_t sel[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v |= (uint32_t)((4 * g + u >= j) ? 3 - u : 7 - u) << (4 * (3 - u));
-        sel[g] = v;
-    }
+// First 16 steps of a period whose window word L(0) sits at smem offset wnew.  On return r.p[k]
+// holds the finished sums of the frames the lane started in the previous period.
+template <class G, class Trace>
+RING_HD void ring_head(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
+                       const Trace& tr) {
+    // the three words ahead of group 0 (frames 1..3 start 4, 8, 12 bytes further on)
+    const uint32_t l4 = ring_lds_u32(smem, wnew + 16u), l3 = ring_lds_u32(smem, wnew + 12u);
+    const uint32_t l2 = ring_lds_u32(smem, wnew + 8u), l1 = ring_lds_u32(smem, wnew + 4u);
+    tr.word(tid, period, 100, wnew + 16u); tr.word(tid, period, 101, wnew + 12u);
+    tr.word(tid, period, 102, wnew + 8u); tr.word(tid, period, 103, wnew + 4u);
+    r.qn[2] = ring_funnel_r(l3, l4, r.shift);
+    r.qn[1] = ring_funnel_r(l2, l3, r.shift);
+    r.qn[0] = ring_funnel_r(l1, l2, r.shift);
+    r.ln = l1;
+    loff = r.lwrap;
+    ring_groups<G, 0, 4>(r, smem, wnew, r.wlast, loff, tid, period, tr);
+}
 
-    RingLane r;
+// Steps 16..71 of the period, then the hand-over to the next one.
+template <class G, class Trace>
+RING_HD void ring_tail(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
+                       const Trace& tr) {
+    ring_groups<G, 4, 18>(r, smem, wnew, r.wlast, loff, tid, period, tr);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { r.acc[k] = 0.0; r.stash[k] = 0.0; }
-    r.qo[0] = r.qo[1] = r.qo[2] = 0u;
-    r.lo = 0u;
-    for (int n = 0; n <= G::KR; ++n) {
-        uint32_t wnew = wb + (uint32_t)(n * G::HOP);
-        const uint32_t wold = wnew - (uint32_t)G::HOP;
-        if (n == G::KR) wnew = wold;                             // drain: stay inside the tile
-        // the three words ahead of group 0 (frames 1..3 start 4, 8, 12 bytes further on)
-        {
-            const uint32_t l4 = ring_lds_u32(smem, wnew + 16u), l3 = ring_lds_u32(smem, wnew + 12u);
-            const uint32_t l2 = ring_lds_u32(smem, wnew + 8u), l1 = ring_lds_u32(smem, wnew + 4u);
-            tr.word(tid, n, 100, wnew + 16u); tr.word(tid, n, 101, wnew + 12u);
-            tr.word(tid, n, 102, wnew + 8u); tr.word(tid, n, 103, wnew + 4u);
-            r.qn[2] = ring_funnel_r(l3, l4, shift);
-            r.qn[1] = ring_funnel_r(l2, l3, shift);
-            r.qn[0] = ring_funnel_r(l1, l2, shift);
-            r.ln = l1;
-        }
-        r.loff = lwrap;
-        ring_groups<G, 0, 4>(r, smem, wnew, wold, shift, j, lnew, sel, tid, n, tr);
-        if (n > 0) emit(n - 1, r.stash);
-        if (n == G::KR) break;
-        ring_groups<G, 4, 18>(r, smem, wnew, wold, shift, j, lnew, sel, tid, n, tr);
-        // this round's last words are the next round's wrapped history
-        r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];
-        r.lo = r.ln;
-    }
+    for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = 0.0; }
+    r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];   // this window's last words = next period's history
+    r.lo = r.ln;
+    r.wlast = wnew;
 }
 
 // Where the byte buffer of a tile half starts in the stream.  f0 = first frame of the half.

@@ -1,7 +1,9 @@
 // Host-side lane emulator for the ring kernel (dsf2flac_b200/csrc/ring_core.h).
 //
-// Runs ring_tile_lane() once per thread id over a byte image of the CTA's shared memory (table
-// image + one staged tile = two byte buffers), for every tile of a small multi-channel stream, and
+// Walks the tiles of every CTA of a small launch exactly like decimate_ring_kernel does -- same
+// double-buffered shared-memory image, the next tile staged over the previous one at the kernel's
+// mid-tile barrier, per-lane state carried across periods and tiles, one drain at the end -- running
+// ring_head()/ring_tail() once per thread id, for a small multi-channel stream, and
 //   1. compares every emitted fp64 sum, bit for bit, with the straightforward
 //      sum_{t=0..71} lut[t][B_c(p - t)] in reference order (dsd_decimator.cpp:194-198), and
 //      checks that every (channel, frame) is emitted exactly once;
@@ -12,7 +14,7 @@
 // Prints one JSON line; exit code 0 iff all sums match, coverage is exact and every table load
 // is conflict free.
 //
-// usage: emu_ring <nwarp:16|8> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed>
+// usage: emu_ring <nwarp:16|8> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed> <grid>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,7 +59,7 @@ static int wavefronts(const std::vector<uint32_t>& addrs, int bytes_per_lane) {
 }
 
 template <class G>
-static int run(long long nframes, int nch, long long p0, long long in_first, long long in_count, unsigned seed) {
+static int run(long long nframes, int nch, long long p0, long long in_first, long long in_count, unsigned seed, int grid) {
     srand(seed);
     std::vector<double> lut((size_t)G::NLUT * 256);
     for (auto& v : lut) v = (rand() / (double)RAND_MAX - 0.5) * 0.35;
@@ -70,76 +72,108 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         return (o >= 0 && o < in_count) ? src[c][(size_t)o] : fill;
     };
 
-    // smem image: tables, then (as in the kernel) two tile buffers; the emulated tile lives in
-    // buffer `buf`, the other one holds noise
+    // smem image exactly as the kernel lays it out: tables, then two tile buffers
     std::vector<unsigned char> smem((size_t)G::LUT_BYTES + 2 * G::TILE_BYTES);
     g_smem_size = smem.size();
-    ring_build_lut_image<G>(lut.data(), smem.data());
-    for (size_t k = G::LUT_BYTES; k < smem.size(); ++k) smem[k] = (unsigned char)(rand() & 0xff);
+    const long long ntiles = ring_tile_count<G>(nframes, nch);
+    int a_tile;
+    { long long t0; ring_half_origin<G>(p0, in_first, 0, t0, a_tile); }
+    auto stage = [&](long long tile, int buf) -> int {
+        const RingTile tl = ring_tile_at<G>(tile, nframes, nch);
+        for (int h = 0; h < 2; ++h) {
+            long long t0; int a;
+            ring_half_origin<G>(p0, in_first, tl.f0[h], t0, a);
+            if ((t0 - in_first) % 16 != 0 || a != a_tile || a < G::FRONT || a > G::FRONT + 15) { fprintf(stderr, "bad half origin\n"); return 2; }
+            for (int k = 0; k < G::HALF_BYTES; ++k)
+                smem[(size_t)G::LUT_BYTES + buf * G::TILE_BYTES + h * G::HALF_BYTES + k] = stream_byte(tl.c[h], t0 + k);
+        }
+        return 0;
+    };
 
     std::vector<std::vector<unsigned char>> seen(nch, std::vector<unsigned char>((size_t)nframes, 0));
     long long mismatches = 0, checked = 0, dup = 0;
     long long lut_instr = 0, lut_wavefronts = 0, word_instr = 0, word_wavefronts = 0;
-    const long long ntiles = ring_tile_count<G>(nframes, nch);
-    for (long long tile = 0; tile < ntiles; ++tile) {
-        const RingTile tl = ring_tile_at<G>(tile, nframes, nch);
-        const int buf = (int)(tile & 1);
-        const uint32_t tile_off = (uint32_t)(G::LUT_BYTES + buf * G::TILE_BYTES);
-        int a_tile = 0;
-        for (int h = 0; h < 2; ++h) {
-            long long t0; int a;
-            ring_half_origin<G>(p0, in_first, tl.f0[h], t0, a);
-            if ((t0 - in_first) % 16 != 0 || a < G::FRONT || a > G::FRONT + 15) { fprintf(stderr, "bad half origin\n"); return 2; }
-            if (h == 1 && a != a_tile) { fprintf(stderr, "halves disagree on a_tile\n"); return 2; }
-            a_tile = a;
-            for (int k = 0; k < G::HALF_BYTES; ++k) smem[(size_t)tile_off + h * G::HALF_BYTES + k] = stream_byte(tl.c[h], t0 + k);
+    struct Dest { long long fb; int c; };
+    auto check = [&](const Dest& d, const double (&sums)[4], int tid) {
+        for (int k = 0; k < 4; ++k) {
+            const long long f = d.fb + k;
+            if (f >= nframes) continue;
+            const long long p = p0 + f * G::NSTEP;
+            double ref = 0.0;
+            for (int t = 0; t < G::NLUT; ++t) ref += lut[(size_t)t * 256 + stream_byte(d.c, p - t)];
+            ++checked;
+            if (seen[d.c][(size_t)f]++) ++dup;
+            if (memcmp(&ref, &sums[k], 8) != 0) {
+                if (mismatches < 5) fprintf(stderr, "mismatch c=%d f=%lld tid=%d k=%d got %.17g want %.17g\n", d.c, f, tid, k, sums[k], ref);
+                ++mismatches;
+            }
         }
-        std::vector<Access> lut_log, word_log;
-        const bool trace = (tile == 0 || tile == ntiles - 1);
-        Recorder rec{trace ? &lut_log : nullptr, trace ? &word_log : nullptr};
+    };
+
+    // one CTA after the other, each walking its tiles exactly like decimate_ring_kernel
+    for (int cta = 0; cta < grid && cta < ntiles; ++cta) {
+        ring_build_lut_image<G>(lut.data(), smem.data());
+        for (size_t k = G::LUT_BYTES; k < smem.size(); ++k) smem[k] = (unsigned char)(rand() & 0xff);
+        std::vector<RingLane> lanes(G::NTHR);
+        std::vector<uint32_t> w0(G::NTHR), loff(G::NTHR, 0);
+        std::vector<Dest> prev(G::NTHR);
         for (int tid = 0; tid < G::NTHR; ++tid) {
-            const int l = tid & 31, w = tid >> 5, h = l >> 4;
-            ring_tile_lane<G>(smem.data(), tile_off, tid, a_tile,
-                              [&](int round, const double (&sums)[4]) {
-                                  for (int k = 0; k < 4; ++k) {
-                                      const long long f = tl.f0[h] + 4LL * ((long long)round * G::BLK_PER_ROUND + 16 * w + (l & 15)) + k;
-                                      if (f >= nframes) continue;
-                                      const int c = tl.c[h];
-                                      const long long p = p0 + f * G::NSTEP;
-                                      double ref = 0.0;
-                                      for (int t = 0; t < G::NLUT; ++t) ref += lut[(size_t)t * 256 + stream_byte(c, p - t)];
-                                      ++checked;
-                                      if (seen[c][(size_t)f]++) ++dup;
-                                      if (memcmp(&ref, &sums[k], 8) != 0) {
-                                          if (mismatches < 5) fprintf(stderr, "mismatch c=%d f=%lld tid=%d round=%d k=%d got %.17g want %.17g\n", c, f, tid, round, k, sums[k], ref);
-                                          ++mismatches;
-                                      }
-                                  }
-                              },
-                              rec);
+            const int h = (tid & 31) >> 4;
+            w0[tid] = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lanes[tid], tid, a_tile));
         }
-        if (trace) {
-            std::map<long long, std::vector<uint32_t>> groups;
-            for (auto& a : lut_log) {
-                long long key = ((((long long)(a.tid / 16) * 64 + a.period) * 128 + a.tag) * 4 + a.k);
-                groups[key].push_back(a.addr);
+        bool have_prev = false;
+        long long tile = cta;
+        int buf = 0, period = 0;
+        if (stage(tile, 0)) return 2;
+        while (tile < ntiles) {
+            const long long next = tile + grid;
+            const RingTile tl = ring_tile_at<G>(tile, nframes, nch);
+            const bool trace = (cta == 0) && (tile == cta || next >= ntiles);
+            for (int n = 0; n < G::KR; ++n, ++period) {
+                std::vector<Access> lut_log, word_log;
+                Recorder rec{trace ? &lut_log : nullptr, trace ? &word_log : nullptr};
+                for (int tid = 0; tid < G::NTHR; ++tid) {
+                    const uint32_t wnew = w0[tid] + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
+                    ring_head<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, rec);
+                    if (have_prev) check(prev[tid], lanes[tid].p, tid);
+                }
+                if (n == 0) {
+                    // the kernel's mid-tile barrier: from here on the other buffer is refilled
+                    if (next < ntiles) { if (stage(next, buf ^ 1)) return 2; }
+                    else for (int k = 0; k < G::TILE_BYTES; ++k) smem[(size_t)G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES + k] = (unsigned char)(rand() & 0xff);
+                }
+                for (int tid = 0; tid < G::NTHR; ++tid) {
+                    const int l = tid & 31, w = tid >> 5, h = l >> 4;
+                    const uint32_t wnew = w0[tid] + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
+                    ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, rec);
+                    prev[tid] = {tl.f0[h] + 4LL * ((long long)n * G::BLK_PER_ROUND + 16 * w + (l & 15)), tl.c[h]};
+                }
+                have_prev = true;
+                if (trace) {
+                    std::map<long long, std::vector<uint32_t>> groups;
+                    for (auto& a : lut_log) groups[((((long long)(a.tid / 16)) * 128 + a.tag) * 4 + a.k)].push_back(a.addr);
+                    for (auto& kv : groups) { ++lut_instr; lut_wavefronts += wavefronts(kv.second, 8); }
+                    std::map<long long, std::vector<uint32_t>> wg;
+                    for (auto& a : word_log) wg[((long long)(a.tid / 32)) * 128 + a.tag].push_back(a.addr);
+                    for (auto& kv : wg) { ++word_instr; word_wavefronts += wavefronts(kv.second, 4); }
+                }
             }
-            for (auto& kv : groups) { ++lut_instr; lut_wavefronts += wavefronts(kv.second, 8); }
-            std::map<long long, std::vector<uint32_t>> wg;
-            for (auto& a : word_log) {
-                long long key = (((long long)(a.tid / 32) * 64 + a.period) * 128 + a.tag);
-                wg[key].push_back(a.addr);
-            }
-            for (auto& kv : wg) { ++word_instr; word_wavefronts += wavefronts(kv.second, 4); }
+            tile = next;
+            buf ^= 1;
         }
+        if (have_prev)
+            for (int tid = 0; tid < G::NTHR; ++tid) {
+                ring_head<G>(lanes[tid], smem.data(), lanes[tid].wlast, loff[tid], tid, period, Recorder{nullptr, nullptr});
+                check(prev[tid], lanes[tid].p, tid);
+            }
     }
     long long missing = 0;
     for (auto& ch : seen)
         for (auto v : ch) missing += (v == 0);
-    printf("{\"nwarp\": %d, \"kr\": %d, \"frames\": %lld, \"nch\": %d, \"tiles\": %lld, \"checked\": %lld, \"mismatches\": %lld, "
+    printf("{\"nwarp\": %d, \"kr\": %d, \"frames\": %lld, \"nch\": %d, \"tiles\": %lld, \"grid\": %d, \"checked\": %lld, \"mismatches\": %lld, "
            "\"missing\": %lld, \"duplicates\": %lld, \"oob\": %lld, \"lut_halfwarp_loads\": %lld, \"lut_wavefronts\": %lld, "
            "\"word_loads\": %lld, \"word_wavefronts\": %lld}\n",
-           G::NWARP, G::KR, nframes, nch, ntiles, checked, mismatches, missing, dup, g_oob, lut_instr, lut_wavefronts,
+           G::NWARP, G::KR, nframes, nch, ntiles, grid, checked, mismatches, missing, dup, g_oob, lut_instr, lut_wavefronts,
            word_instr, word_wavefronts);
     if (missing || dup || checked != nframes * nch) return 3;
     if (mismatches) return 1;
@@ -149,15 +183,18 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
 }
 
 int main(int argc, char** argv) {
-    if (argc < 9) { fprintf(stderr, "usage: emu_ring nwarp kr nframes nch p0 in_first in_count seed\n"); return 64; }
+    if (argc < 10) { fprintf(stderr, "usage: emu_ring nwarp kr nframes nch p0 in_first in_count seed grid\n"); return 64; }
     const int nwarp = atoi(argv[1]), kr = atoi(argv[2]);
     const long long nframes = atoll(argv[3]);
     const int nch = atoi(argv[4]);
     const long long p0 = atoll(argv[5]), in_first = atoll(argv[6]), in_count = atoll(argv[7]);
     const unsigned seed = (unsigned)atoi(argv[8]);
-    if (nwarp == 16 && kr == 3) return run<RingGeom<16, 3>>(nframes, nch, p0, in_first, in_count, seed);
-    if (nwarp == 16 && kr == 1) return run<RingGeom<16, 1>>(nframes, nch, p0, in_first, in_count, seed);
-    if (nwarp == 8 && kr == 6) return run<RingGeom<8, 6>>(nframes, nch, p0, in_first, in_count, seed);
+    const int grid = atoi(argv[9]);
+    if (grid < 1) return 64;
+    if (nwarp == 16 && kr == 3) return run<RingGeom<16, 3>>(nframes, nch, p0, in_first, in_count, seed, grid);
+    if (nwarp == 16 && kr == 2) return run<RingGeom<16, 2>>(nframes, nch, p0, in_first, in_count, seed, grid);
+    if (nwarp == 16 && kr == 1) return run<RingGeom<16, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);
+    if (nwarp == 8 && kr == 6) return run<RingGeom<8, 6>>(nframes, nch, p0, in_first, in_count, seed, grid);
     fprintf(stderr, "unsupported geometry\n");
     return 64;
 }

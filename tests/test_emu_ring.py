@@ -1,5 +1,6 @@
 """Lane-level emulation of the ring kernel on the CPU (tests/cpp/emu_ring.cpp runs the very
-ring_core.h the kernel compiles): every emitted fp64 sum equals the reference-order sum
+ring_core.h the kernel compiles, walking each CTA's tiles as the kernel does, buffers overwritten
+at the same points): every emitted fp64 sum equals the reference-order sum
 (dsd_decimator.cpp:194-198) bit for bit, every (channel, frame) is emitted exactly once, no
 shared-memory access leaves the CTA's allocation, every table load of every half-warp is
 bank-conflict free, and the window loads are conflict free whenever the frame grid is 4-byte
@@ -13,17 +14,18 @@ import pytest
 EMU = os.path.join(os.path.dirname(__file__), "cpp", "_build", "emu_ring")
 
 
-@pytest.mark.parametrize("nwarp,kr,nframes,nch,p0,in_first,in_count,seed", [
-    (16, 3, 3072, 2, 79, 0, 13000, 1),        # exactly one pair tile, aligned frame grid
-    (16, 3, 3072, 2, 72, 0, 13000, 1),        # the app's p0 = nLUT: unaligned by one byte
-    (16, 3, 7000, 1, 72, 0, 29000, 2),        # mono: halves hold consecutive frame ranges, ragged end
-    (16, 3, 5000, 3, -1, 0, 21000, 3),        # odd channel count; starts in the idle pre-fill
-    (16, 1, 4000, 2, 1000, 16, 17000, 4),     # one round per tile; source starts late, ends early
-    (8, 6, 9000, 6, 75, 3, 37000, 5),         # 5.1, unaligned in_first, 8-warp geometry
-    (16, 3, 1, 2, 72, 0, 100, 7),             # a single frame
+@pytest.mark.parametrize("nwarp,kr,nframes,nch,p0,in_first,in_count,seed,grid", [
+    (16, 3, 3072, 2, 79, 0, 13000, 1, 1),        # exactly one pair tile, aligned frame grid
+    (16, 3, 20000, 2, 72, 0, 81000, 1, 2),       # the app's p0 = nLUT (unaligned by one byte); 2 CTAs x 3-4 tiles
+    (16, 3, 7000, 1, 72, 0, 29000, 2, 1),        # mono: halves hold consecutive frame ranges, ragged end
+    (16, 3, 15000, 3, -1, 0, 61000, 3, 3),       # odd channel count; starts in the idle pre-fill
+    (16, 1, 9000, 2, 1000, 16, 17000, 4, 2),     # one round per tile; source starts late, ends early
+    (8, 6, 9000, 6, 75, 3, 37000, 5, 2),         # 5.1, unaligned in_first, 8-warp geometry
+    (16, 3, 1, 2, 72, 0, 100, 7, 4),             # a single frame
+    (16, 2, 30000, 2, 75, 0, 121000, 8, 3),      # two rounds per tile, 5 tiles per CTA, aligned
 ])
-def test_ring_lanes(nwarp, kr, nframes, nch, p0, in_first, in_count, seed):
-    r = subprocess.run([EMU, *map(str, (nwarp, kr, nframes, nch, p0, in_first, in_count, seed))],
+def test_ring_lanes(nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid):
+    r = subprocess.run([EMU, *map(str, (nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid))],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     rep = json.loads(r.stdout)
