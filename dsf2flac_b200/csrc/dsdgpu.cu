@@ -244,11 +244,6 @@ __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const Rin
     }
 }
 
-__device__ __forceinline__ int quantise_i32(const DecimateArgs& a, long long frame, int c, double sum) {
-    const double dith = (a.dither != nullptr) ? a.dither[frame * a.dither_stride + c] : 0.0;
-    return __double2int_rz(round(quantise_tail(sum, a.scale, a.dither_amp, dith, a.clip)));
-}
-
 // Where a lane's four frames of one period go: frames fb..fb+3 of channel c.  Its partner
 // (lane ^ 16) holds the same frames of channel c+1 (pair tile, c0 = the even channel) or frames
 // NTP further on of the same channel (single tile).
@@ -258,44 +253,75 @@ struct RingDest {
     bool pair;
 };
 
-template <class G>
-__device__ __forceinline__ void ring_emit(const DecimateArgs& a, const RingDest& d, int h, const double (&sums)[4],
-                                          bool out_aligned16) {
-    const long long fb = d.fb;
-    const int c = d.c;
-    if (a.out_kind != DSDGPU_OUT_INT32) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (fb + k < a.nframes) store_sample(a, fb + k, c, sums[k]);
-        return;
-    }
-    int v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (fb + k < a.nframes) ? quantise_i32(a, fb + k, c, sums[k]) : 0;
-    int32_t* out = reinterpret_cast<int32_t*>(a.out);
-    if (d.pair && (a.nch & 1) == 0) {
-        // trade halves: lane h=0 ends up with frames fb, fb+1 of both channels, lane h=1 with fb+2, fb+3
-        const int s0 = __shfl_xor_sync(0xffffffffu, h ? v[0] : v[2], 16);
-        const int s1 = __shfl_xor_sync(0xffffffffu, h ? v[1] : v[3], 16);
-        const long long f = fb + 2 * h;
-        const int2 lo2 = h ? make_int2(s0, v[2]) : make_int2(v[0], s0);
-        const int2 hi2 = h ? make_int2(s1, v[3]) : make_int2(v[1], s1);
-        if (a.nch == 2 && out_aligned16 && f + 1 < a.nframes) {
-            *reinterpret_cast<int4*>(out + f * 2) = make_int4(lo2.x, lo2.y, hi2.x, hi2.y);
-        } else {
-            if (f < a.nframes) *reinterpret_cast<int2*>(out + f * a.nch + d.c0) = lo2;
-            if (f + 1 < a.nframes) *reinterpret_cast<int2*>(out + (f + 1) * a.nch + d.c0) = hi2;
-        }
-    } else if (a.nch == 1 && out_aligned16 && fb + 3 < a.nframes) {
-        *reinterpret_cast<int4*>(out + fb) = make_int4(v[0], v[1], v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (fb + k < a.nframes) out[(fb + k) * a.nch + c] = v[k];
-    }
-}
+// The ring kernel's emitter (protocol: ring_core.h, RingNoEmit): dsd_decimator.cpp:199-216 as
+// straight-line code -- scale, dither, clip by selects, C round() as trunc + exact remainder test,
+// saturating double->int -- and frame-pair stores.  Called from inside the main steps.
+template <bool F64OUT, bool DITHER>
+struct RingEmitter {
+    const DecimateArgs& a;
+    RingDest d;
+    int h;
+    bool out_aligned16;
+    int vi[4];
+    double vd[4];
 
-template <class G>
+    __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, int h_, bool al)
+        : a(a_), d(d_), h(h_), out_aligned16(al) {}
+
+    __device__ __forceinline__ void quantise(int k, double sum) {
+        double x = __dmul_rn(sum, a.scale);
+        if (DITHER) {
+            const long long f = d.fb + k < a.nframes ? d.fb + k : 0;     // keep the load in bounds
+            x = __dadd_rn(x, __dmul_rn(a.dither[f * a.dither_stride + d.c], a.dither_amp));
+        }
+        const bool clipping = a.clip > 0.0;
+        x = (clipping && x > a.clip) ? a.clip : x;
+        x = (clipping && x < -a.clip) ? -a.clip : x;
+        if (F64OUT) {
+            vd[k] = x;
+        } else {
+            // round(): half away from zero.  x - trunc(x) is exact, so this is C's round() bit for bit.
+            const double r = trunc(x);
+            const double rem = __dsub_rn(x, r);
+            const double adj = (rem >= 0.5) ? 1.0 : ((rem <= -0.5) ? -1.0 : 0.0);
+            vi[k] = __double2int_rz(__dadd_rn(r, adj));
+        }
+    }
+
+    __device__ __forceinline__ void store() {
+        const long long fb = d.fb, nf = a.nframes;
+        if (F64OUT) {
+            double* out = reinterpret_cast<double*>(a.out);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (fb + k < nf) out[(fb + k) * a.nch + d.c] = vd[k];
+            return;
+        }
+        int32_t* out = reinterpret_cast<int32_t*>(a.out);
+        if (d.pair && (a.nch & 1) == 0) {
+            // trade halves: lane h=0 ends up with frames fb, fb+1 of both channels, lane h=1 with fb+2, fb+3
+            const int s0 = __shfl_xor_sync(0xffffffffu, h ? vi[0] : vi[2], 16);
+            const int s1 = __shfl_xor_sync(0xffffffffu, h ? vi[1] : vi[3], 16);
+            const long long f = fb + 2 * h;
+            const int2 lo2 = h ? make_int2(s0, vi[2]) : make_int2(vi[0], s0);
+            const int2 hi2 = h ? make_int2(s1, vi[3]) : make_int2(vi[1], s1);
+            if (a.nch == 2 && out_aligned16 && f + 1 < nf) {
+                *reinterpret_cast<int4*>(out + f * 2) = make_int4(lo2.x, lo2.y, hi2.x, hi2.y);
+            } else {
+                if (f < nf) *reinterpret_cast<int2*>(out + f * a.nch + d.c0) = lo2;
+                if (f + 1 < nf) *reinterpret_cast<int2*>(out + (f + 1) * a.nch + d.c0) = hi2;
+            }
+        } else if (a.nch == 1 && out_aligned16 && fb + 3 < nf) {
+            *reinterpret_cast<int4*>(out + fb) = make_int4(vi[0], vi[1], vi[2], vi[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (fb + k < nf) out[(fb + k) * a.nch + d.c] = vi[k];
+        }
+    }
+};
+
+template <class G, bool F64OUT, bool DITHER>
 __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     // [0, LUT_BYTES): table image; then two tiles of two byte buffers each.
@@ -318,18 +344,16 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     uint32_t loff = 0;
 
     long long tile = blockIdx.x;
+    if (tile >= ntiles) { cp_async_commit(); cp_async_wait<0>(); return; }
     int buf = 0;
-    RingTile tl;
-    if (tile < ntiles) {
-        tl = ring_tile_at<G>(tile, a.nframes, a.nch);
-        ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16);
-    }
+    RingTile tl = ring_tile_at<G>(tile, a.nframes, a.nch);
+    ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
 
-    RingDest prev;
-    bool have_prev = false;
+    RingDest prev;                   // nothing to emit in the very first period: every store is off
+    prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
     while (tile < ntiles) {
         const long long next = tile + gridDim.x;
         RingDest cur;
@@ -341,7 +365,6 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         for (int n = 0; n < G::KR; ++n) {
             const uint32_t wnew = w0 + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
             ring_head<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
-            if (have_prev) ring_emit<G>(a, prev, h, lane.p, out_aligned16);
             if (n == 0) {
                 __syncthreads();     // nobody reads the other buffer (the previous tile) any more
                 if (next < ntiles) {
@@ -350,9 +373,9 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
                 }
                 cp_async_commit();
             }
-            ring_tail<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
+            RingEmitter<F64OUT, DITHER> emit(a, prev, h, out_aligned16);
+            ring_tail<G>(lane, smem, wnew, loff, tid, n, emit, RingNoTrace());
             prev = cur;
-            have_prev = true;
             cur.fb += 4LL * G::BLK_PER_ROUND;
         }
         cp_async_wait<0>();
@@ -361,10 +384,12 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         buf ^= 1;
         if (tile < ntiles) tl = ring_tile_at<G>(tile, a.nframes, a.nch);
     }
-    if (have_prev) {                 // the one drain of this CTA: 16 more steps finish the last frames
-        ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
-        ring_emit<G>(a, prev, h, lane.p, out_aligned16);
-    }
+    // the one drain of this CTA: 16 more steps finish the last frames
+    ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
+    RingEmitter<F64OUT, DITHER> emit(a, prev, h, out_aligned16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit.quantise(k, lane.p[k]);
+    emit.store();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -493,7 +518,6 @@ using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x3 = RingGeom<16, 3>;
 using Ring16x2 = RingGeom<16, 2>;
-using Ring16x1 = RingGeom<16, 1>;
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -577,20 +601,28 @@ int launch_skew(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     return DSDGPU_OK;
 }
 
-template <class G>
-int launch_ring(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
+template <class G, bool F64OUT, bool DITHER>
+int launch_ring_variant(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     const int smem = G::LUT_BYTES + 2 * G::TILE_BYTES;
     static thread_local int configured_device = -1;
     if (configured_device != ctx->device) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_ring_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_ring_kernel<G, F64OUT, DITHER>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured_device = ctx->device;
     }
     const long long tiles = ring_tile_count<G>(a.nframes, a.nch);
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    decimate_ring_kernel<G><<<grid, G::NTHR, smem, st>>>(a);
+    decimate_ring_kernel<G, F64OUT, DITHER><<<grid, G::NTHR, smem, st>>>(a);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
+}
+
+template <class G>
+int launch_ring(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
+    const bool f64 = a.out_kind != DSDGPU_OUT_INT32, dith = a.dither != nullptr;
+    if (f64) return dith ? launch_ring_variant<G, true, true>(ctx, a, st) : launch_ring_variant<G, true, false>(ctx, a, st);
+    return dith ? launch_ring_variant<G, false, true>(ctx, a, st) : launch_ring_variant<G, false, false>(ctx, a, st);
 }
 
 int launch_direct(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
@@ -647,7 +679,6 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     if (kernel == DSDGPU_KERNEL_RING) {
         if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs nlut=72, nstep=4 and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
-        if (ctx->ring_rounds == 1) return launch_ring<Ring16x1>(ctx, a, st);
         if (ctx->ring_rounds == 2) return launch_ring<Ring16x2>(ctx, a, st);
         return launch_ring<Ring16x3>(ctx, a, st);
     }
@@ -770,7 +801,7 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
         if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
         ctx->threads = (int)value;
     } else if (!strcmp(key, "ring_rounds")) {
-        if (value < 1 || value > 3) return fail(ctx, DSDGPU_ERR_ARG, "ring_rounds must be 1, 2 or 3");
+        if (value < 2 || value > 3) return fail(ctx, DSDGPU_ERR_ARG, "ring_rounds must be 2 or 3");
         ctx->ring_rounds = (int)value;
     } else if (!strcmp(key, "dither_stride")) {
         if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");

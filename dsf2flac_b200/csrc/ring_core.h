@@ -123,6 +123,16 @@ struct RingNoTrace {
     RING_HD void word(int, int, int, uint32_t) const {}
 };
 
+// What happens to the finished sums r.p[0..3] of the previous period.  They are final after step
+// 15 and stay untouched until the period ends, so the kernel's emitter is called from INSIDE the
+// main steps -- quantise(k, sum) before groups 5..8, store() before group 9 -- as straight-line
+// code the compiler can schedule into the shadow of the table loads, instead of a block of
+// scale/clip/round/store work that every warp of the CTA would hit at the same time.
+struct RingNoEmit {
+    RING_HD void quantise(int, double) {}
+    RING_HD void store() {}
+};
+
 // Skew of lane l (0..31) of a warp.  Within each half-warp the 16 values are a permutation of
 // 0..15 (conflict-free table loads); across the warp the quarter (j >> 2) is arranged so that
 // the 32 window words of one LDS.32 -- lane stride 16 B plus j bytes -- fall in 32 distinct
@@ -179,11 +189,13 @@ RING_HD int ring_lane_init(RingLane& r, int tid, int a_tile) {
 
 // Steps 4*G0 .. 4*G1-1 of one period.  wnew / wold: smem byte offsets of word L(0) of this
 // period's window and of the previous period's window (whose groups 18.. continue here).
-template <class G, int G0, int G1, class Trace>
+template <class G, int G0, int G1, class Emit, class Trace>
 RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t wold, uint32_t& loff,
-                         int tid, int period, const Trace& tr) {
+                         int tid, int period, Emit& emit, const Trace& tr) {
 #pragma unroll
     for (int g = G0; g < G1; ++g) {
+        if (g >= 5 && g <= 8) emit.quantise(g - 5, r.p[g - 5]);
+        if (g == 9) emit.store();
         uint32_t x[4];
         {
             const uint32_t a = wnew - 4u * (uint32_t)g;
@@ -256,14 +268,16 @@ RING_HD void ring_head(RingLane& r, const unsigned char* smem, uint32_t wnew, ui
     r.qn[0] = ring_funnel_r(l1, l2, r.shift);
     r.ln = l1;
     loff = r.lwrap;
-    ring_groups<G, 0, 4>(r, smem, wnew, r.wlast, loff, tid, period, tr);
+    RingNoEmit none;
+    ring_groups<G, 0, 4>(r, smem, wnew, r.wlast, loff, tid, period, none, tr);
 }
 
-// Steps 16..71 of the period, then the hand-over to the next one.
-template <class G, class Trace>
+// Steps 16..71 of the period (with the previous period's sums handed to `emit` on the way), then
+// the hand-over to the next one.
+template <class G, class Emit, class Trace>
 RING_HD void ring_tail(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
-                       const Trace& tr) {
-    ring_groups<G, 4, 18>(r, smem, wnew, r.wlast, loff, tid, period, tr);
+                       Emit& emit, const Trace& tr) {
+    ring_groups<G, 4, 18>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = 0.0; }
     r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];   // this window's last words = next period's history

@@ -94,6 +94,11 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
     long long mismatches = 0, checked = 0, dup = 0;
     long long lut_instr = 0, lut_wavefronts = 0, word_instr = 0, word_wavefronts = 0;
     struct Dest { long long fb; int c; };
+    struct Collect {                      // the emulator's emitter: just keeps what the lane hands over
+        double sums[4]; int got = 0, stored = 0;
+        void quantise(int k, double v) { sums[k] = v; got |= 1 << k; }
+        void store() { ++stored; }
+    };
     auto check = [&](const Dest& d, const double (&sums)[4], int tid) {
         for (int k = 0; k < 4; ++k) {
             const long long f = d.fb + k;
@@ -135,7 +140,6 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                 for (int tid = 0; tid < G::NTHR; ++tid) {
                     const uint32_t wnew = w0[tid] + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
                     ring_head<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, rec);
-                    if (have_prev) check(prev[tid], lanes[tid].p, tid);
                 }
                 if (n == 0) {
                     // the kernel's mid-tile barrier: from here on the other buffer is refilled
@@ -145,7 +149,10 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                 for (int tid = 0; tid < G::NTHR; ++tid) {
                     const int l = tid & 31, w = tid >> 5, h = l >> 4;
                     const uint32_t wnew = w0[tid] + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
-                    ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, rec);
+                    Collect col;
+                    ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, col, rec);
+                    if (col.got != 15 || col.stored != 1) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
+                    if (have_prev) check(prev[tid], col.sums, tid);
                     prev[tid] = {tl.f0[h] + 4LL * ((long long)n * G::BLK_PER_ROUND + 16 * w + (l & 15)), tl.c[h]};
                 }
                 have_prev = true;
