@@ -395,11 +395,24 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
 // ---------------------------------------------------------------------------------------------
 // glibc rand() by position.  r[i] = r[i-31] + r[i-3] (mod 2^32) for i >= 34, draw k = r[344+k]>>1.
 // With x^31 = x^28 + 1:  r[3+m+i] = sum_k c_k r[3+i+k],  c = x^m mod (x^31 - x^28 - 1).
+//
+// The stream is cut into pieces of 248 values (124 output samples) per lane, 32 lanes per warp.
+// glibc_rand_anchor_kernel (one warp) jumps to the first value of the call: c = x^m as a product
+// of precomputed squarings, applied to the seed words -> 61 consecutive words ("segment").
+// glibc_rand_fill_kernel: every warp advances that segment to its own start by up to three
+// table polynomials (x^(7936*u), x^(7936*128*u), x^(7936*16384*u), u < 128; 31 MACs per lane
+// each), every lane then applies its x^(248*lane) and runs the recurrence in registers.  Results
+// go through shared memory so that the warp writes whole rows of 31 doubles.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRandDeg = 31;
 constexpr int kRandPowBits = 48;
-constexpr int kRandChunkValues = 62 * 32;               // values per chunk thread (2 per sample)
-constexpr int kRandChunkSamples = kRandChunkValues / 2;
+constexpr int kRandLaneValues = 248;                      // 4 blocks of 62 values = 124 samples
+constexpr int kRandLaneSamples = kRandLaneValues / 2;
+constexpr int kRandWarpValues = 32 * kRandLaneValues;     // 7936
+constexpr int kRandWarpSamples = kRandWarpValues / 2;     // 3968
+constexpr int kRandLevel = 128;                           // entries per jump table level
+constexpr int kRandBaseWords = 92;                        // seed words r[3..94]
+constexpr int kRandFillWarps = 4;                         // warps per CTA of the fill kernel
 
 __host__ __device__ inline void rand_poly_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
     uint32_t t[2 * kRandDeg - 1];
@@ -416,62 +429,129 @@ __host__ __device__ inline void rand_poly_mul(const uint32_t* a, const uint32_t*
     for (int i = 0; i < kRandDeg; ++i) out[i] = t[i];
 }
 
-// one thread per chunk: the 31 words preceding value index n = first_value + chunk*CH
-__global__ void glibc_rand_states_kernel(const uint32_t* __restrict__ pow2, const uint32_t* __restrict__ base,
-                                         unsigned long long first_value, int nchunks, uint32_t* __restrict__ states) {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= nchunks) return;
-    const unsigned long long n = first_value + (unsigned long long)chunk * kRandChunkValues;  // r index
-    unsigned long long m = n - 34ULL;         // r[n-31+i] = r[3 + m + i]
-    uint32_t c[kRandDeg];
-    for (int i = 0; i < kRandDeg; ++i) c[i] = 0;
-    c[0] = 1;
-    for (int b = 0; b < kRandPowBits && m != 0; ++b, m >>= 1)
-        if (m & 1ULL) {
-            uint32_t p[kRandDeg], o[kRandDeg];
-            for (int i = 0; i < kRandDeg; ++i) p[i] = pow2[b * kRandDeg + i];
-            rand_poly_mul(c, p, o);
-            for (int i = 0; i < kRandDeg; ++i) c[i] = o[i];
-        }
-    for (int i = 0; i < kRandDeg; ++i) {
-        uint32_t acc = 0;
-        for (int k = 0; k < kRandDeg; ++k) acc += c[k] * base[i + k];
-        states[(size_t)chunk * kRandDeg + i] = acc;
+// words [31, 61) of a segment from its first 31: w[i] = w[i-31] + w[i-3]; three lanes, ten rounds
+__device__ __forceinline__ void rand_extend_segment(uint32_t* seg, int lane) {
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        const int i = kRandDeg + 3 * r + lane;
+        if (lane < 3) seg[i] = seg[i - kRandDeg] + seg[i - 3];
+        __syncwarp();
     }
 }
 
-// one thread per chunk: run the recurrence from the chunk's state, emit (r1 - r2) per sample
-__global__ void __launch_bounds__(128)
-glibc_rand_fill_kernel(const uint32_t* __restrict__ states, int nchunks, long long count, double* __restrict__ out) {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= nchunks) return;
-    uint32_t ring[kRandDeg];                    // ring[i] = r[n - 31 + i]
+// seg_out[i] = sum_k poly[k] * seg_in[i + k], i < 31 (one lane per word), then extended to 61 words
+__device__ __forceinline__ void rand_apply_poly(const uint32_t* __restrict__ poly_g, const uint32_t* seg_in,
+                                                uint32_t* seg_out, uint32_t* poly_s, int lane) {
+    if (lane < kRandDeg) poly_s[lane] = poly_g[lane];
+    __syncwarp();
+    if (lane < kRandDeg) {
+        uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < kRandDeg; ++i) ring[i] = states[(size_t)chunk * kRandDeg + i];
-    const long long s0 = (long long)chunk * kRandChunkSamples;
-    const double rmax = 2147483647.0;
-    for (int blk = 0; blk < kRandChunkValues / 62; ++blk) {
-        const long long sb = s0 + blk * 31;
-        if (sb >= count) break;
-        uint32_t prev = 0;
+        for (int k = 0; k < kRandDeg; ++k) acc += poly_s[k] * seg_in[lane + k];
+        seg_out[lane] = acc;
+    }
+    __syncwarp();
+    rand_extend_segment(seg_out, lane);
+}
+
+// one warp: the 61-word segment r[n-31 .. n+29], n = first_value
+__global__ void __launch_bounds__(32)
+glibc_rand_anchor_kernel(const uint32_t* __restrict__ pow2, const uint32_t* __restrict__ base,
+                         unsigned long long first_value, uint32_t* __restrict__ segment) {
+    __shared__ uint32_t c[kRandDeg], p[kRandDeg], t[2 * kRandDeg];
+    const int lane = threadIdx.x;
+    unsigned long long m = first_value - 34ULL;            // r[n-31+i] = r[3 + m + i]
+    if (lane < kRandDeg) c[lane] = (lane == 0) ? 1u : 0u;
+    __syncwarp();
+#pragma unroll 1
+    for (int b = 0; b < kRandPowBits && (m >> b) != 0; ++b) {
+        if (!((m >> b) & 1ULL)) continue;
+        if (lane < kRandDeg) p[lane] = pow2[b * kRandDeg + lane];
+        __syncwarp();
+        for (int d = lane; d < 2 * kRandDeg - 1; d += 32) {       // product coefficient d
+            uint32_t acc = 0;
+            const int lo = d > kRandDeg - 1 ? d - (kRandDeg - 1) : 0, hi = d < kRandDeg - 1 ? d : kRandDeg - 1;
+            for (int i = lo; i <= hi; ++i) acc += c[i] * p[d - i];
+            t[d] = acc;
+        }
+        __syncwarp();
+        if (lane == 0)
+            for (int d = 2 * kRandDeg - 2; d >= kRandDeg; --d) { t[d - 3] += t[d]; t[d - kRandDeg] += t[d]; }
+        __syncwarp();
+        if (lane < kRandDeg) c[lane] = t[lane];
+        __syncwarp();
+    }
+    for (int i = lane; i < 2 * kRandDeg - 1; i += 32) {
+        uint32_t acc = 0;
+        for (int k = 0; k < kRandDeg; ++k) acc += c[k] * base[i + k];
+        segment[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kRandFillWarps)
+glibc_rand_fill_kernel(const uint32_t* __restrict__ segment, const uint32_t* __restrict__ lane_polys,
+                       const uint32_t* __restrict__ jump_polys, long long count, double* __restrict__ out) {
+    __shared__ uint32_t seg_s[kRandFillWarps][2][64];
+    __shared__ uint32_t poly_s[kRandFillWarps][32];
+    __shared__ double stage_s[kRandFillWarps][32][33];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const long long wi = (long long)blockIdx.x * kRandFillWarps + wl;
+    const long long s_warp = wi * kRandWarpSamples;
+    if (s_warp >= count) return;                                   // whole warp
+    uint32_t* cur = seg_s[wl][0];
+    uint32_t* oth = seg_s[wl][1];
+    for (int i = lane; i < 2 * kRandDeg - 1; i += 32) cur[i] = segment[i];
+    __syncwarp();
+    // the call's first value -> this warp's first value
+#pragma unroll 1
+    for (int level = 2; level >= 0; --level) {
+        const int u = (int)((wi >> (7 * level)) & (kRandLevel - 1));
+        if (u == 0) continue;
+        rand_apply_poly(jump_polys + ((size_t)level * kRandLevel + u) * kRandDeg, cur, oth, poly_s[wl], lane);
+        uint32_t* tmp = cur; cur = oth; oth = tmp;
+    }
+    // this lane's state: x^(248*lane) applied to the warp's segment
+    uint32_t ring[kRandDeg];                                        // ring[i] = r[n - 31 + i]
+    {
+        uint32_t c[kRandDeg];
+#pragma unroll
+        for (int k = 0; k < kRandDeg; ++k) { c[k] = lane_polys[k * 32 + lane]; ring[k] = 0; }
+#pragma unroll
+        for (int d = 0; d < 2 * kRandDeg - 1; ++d) {
+            const uint32_t v = cur[d];
+#pragma unroll
+            for (int i = 0; i < kRandDeg; ++i)
+                if (d - i >= 0 && d - i < kRandDeg) ring[i] += c[d - i] * v;
+        }
+    }
+    const double rmax = 2147483647.0, rcp = 1.0 / 2147483647.0;
+    const long long s_lane = s_warp + (long long)lane * kRandLaneSamples;
+#pragma unroll 1
+    for (int blk = 0; blk < kRandLaneValues / 62; ++blk) {
+        double r1 = 0.0;
 #pragma unroll
         for (int k = 0; k < 62; ++k) {
             const int slot = k % kRandDeg;
             const uint32_t v = ring[slot] + ring[(slot + 28) % kRandDeg];   // r[i-31] + r[i-3]
             ring[slot] = v;
-            const uint32_t draw = v >> 1;
-            if (k & 1) {
-                const long long s = sb + (k >> 1);
-                if (s < count) {
-                    const double r1 = __ddiv_rn((double)(int)prev, rmax);
-                    const double r2 = __ddiv_rn((double)(int)draw, rmax);
-                    out[s] = __dsub_rn(r1, r2);
-                }
-            } else {
-                prev = draw;
-            }
+            // draw / RAND_MAX, correctly rounded: q0 = a*rcp, q0 + (a - q0*d)*rcp (checked against
+            // a/d for all 2^31 possible draws)
+            const double a = (double)(int)(v >> 1);
+            const double q0 = __dmul_rn(a, rcp);
+            const double q = __fma_rn(__fma_rn(-q0, rmax, a), rcp, q0);
+            if (k & 1) stage_s[wl][lane][k >> 1] = __dsub_rn(r1, q);
+            else r1 = q;
         }
+        __syncwarp();
+        // row r of the stage = 31 consecutive samples of lane r
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const long long s = s_warp + (long long)r * kRandLaneSamples + blk * 31 + lane;
+            if (lane < 31 && s < count) out[s] = stage_s[wl][r][lane];
+        }
+        __syncwarp();
     }
+    (void)s_lane;
 }
 
 }  // namespace
@@ -487,8 +567,7 @@ struct dsdgpu_slot {
     size_t out_cap = 0;
     double* d_dither = nullptr;
     size_t dither_cap = 0;
-    uint32_t* d_states = nullptr;
-    size_t states_cap = 0;
+    uint32_t* d_segment = nullptr;           // 61 words: the dither stream at the call's first sample
     bool busy = false;
 };
 
@@ -497,14 +576,16 @@ struct dsdgpu_ctx {
     int sm_count = 0;
     int kernel = DSDGPU_KERNEL_AUTO;
     int threads = 512;
-    int ring_rounds = 3;                     // periods per tile of the ring kernel (1..3)
+    int ring_rounds = 2;                     // periods per tile of the ring kernel (2 or 3)
     int dither_stride = 0;                   // 0 = nch
     long long chunk_frames = 1LL << 21;
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
     unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only)
-    uint32_t* d_rand_pow2 = nullptr;
-    uint32_t* d_rand_base = nullptr;
+    uint32_t* d_rand_pow2 = nullptr;         // x^(2^b), b < 48
+    uint32_t* d_rand_base = nullptr;         // seed words r[3..94]
+    uint32_t* d_rand_lane = nullptr;         // x^(248*l), l < 32, stored [k][l]
+    uint32_t* d_rand_jump = nullptr;         // x^(7936 * 128^level * u), [level][u][k]
     cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
     dsdgpu_slot slots[2];
     dsdgpu_slot own;                         // scratch for the device entry point
@@ -539,7 +620,7 @@ void free_slot(dsdgpu_slot& s) {
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_dither) cudaFree(s.d_dither);
-    if (s.d_states) cudaFree(s.d_states);
+    if (s.d_segment) cudaFree(s.d_segment);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = dsdgpu_slot();
 }
@@ -573,14 +654,17 @@ void glibc_initial_words(uint32_t* r, int n) {
 int launch_dither(dsdgpu_ctx* ctx, dsdgpu_slot& s, unsigned long long first_sample, long long count,
                   double* d_out, cudaStream_t st) {
     if (count <= 0) return DSDGPU_OK;
-    const int nchunks = (int)((count + kRandChunkSamples - 1) / kRandChunkSamples);
-    int rc = ensure(ctx, &s.d_states, &s.states_cap, (size_t)nchunks * kRandDeg * sizeof(uint32_t));
-    if (rc) return rc;
-    const unsigned long long first_value = 344ULL + 2ULL * first_sample;
-    glibc_rand_states_kernel<<<(nchunks + 127) / 128, 128, 0, st>>>(ctx->d_rand_pow2, ctx->d_rand_base,
-                                                                    first_value, nchunks, s.d_states);
-    glibc_rand_fill_kernel<<<(nchunks + 127) / 128, 128, 0, st>>>(s.d_states, nchunks, count, d_out);
-    ctx->launches += 2;
+    if (!s.d_segment) CUDA_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&s.d_segment), 64 * sizeof(uint32_t)));
+    const long long max_samples = (long long)kRandLevel * kRandLevel * kRandLevel * kRandWarpSamples;
+    for (long long done = 0; done < count; done += max_samples) {      // one pass unless count > 8.3e9
+        const long long n = count - done < max_samples ? count - done : max_samples;
+        const unsigned long long first_value = 344ULL + 2ULL * (first_sample + (unsigned long long)done);
+        const long long warps = (n + kRandWarpSamples - 1) / kRandWarpSamples;
+        glibc_rand_anchor_kernel<<<1, 32, 0, st>>>(ctx->d_rand_pow2, ctx->d_rand_base, first_value, s.d_segment);
+        glibc_rand_fill_kernel<<<(unsigned)((warps + kRandFillWarps - 1) / kRandFillWarps), 32 * kRandFillWarps, 0, st>>>(
+            s.d_segment, ctx->d_rand_lane, ctx->d_rand_jump, n, d_out + done);
+        ctx->launches += 2;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
 }
@@ -755,10 +839,10 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     }
     // dither generator constants
     {
-        uint32_t words[3 + 62];
-        glibc_initial_words(words, 3 + 62);
-        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_base), 62 * sizeof(uint32_t)));
-        CREATE_TRY(cudaMemcpy(ctx->d_rand_base, words + 3, 62 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        uint32_t words[3 + kRandBaseWords];
+        glibc_initial_words(words, 3 + kRandBaseWords);
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_base), kRandBaseWords * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(ctx->d_rand_base, words + 3, kRandBaseWords * sizeof(uint32_t), cudaMemcpyHostToDevice));
         std::vector<uint32_t> pow2((size_t)kRandPowBits * kRandDeg, 0);
         uint32_t cur[kRandDeg] = {0};
         cur[1] = 1;                               // x^(2^0)
@@ -770,6 +854,35 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
         }
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_pow2), pow2.size() * sizeof(uint32_t)));
         CREATE_TRY(cudaMemcpy(ctx->d_rand_pow2, pow2.data(), pow2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // x^e from the squarings
+        auto power = [&](unsigned long long e, uint32_t* out) {
+            uint32_t acc[kRandDeg] = {0}, tmp[kRandDeg];
+            acc[0] = 1;
+            for (int b = 0; b < kRandPowBits && (e >> b) != 0; ++b)
+                if ((e >> b) & 1ULL) { rand_poly_mul(acc, &pow2[(size_t)b * kRandDeg], tmp); memcpy(acc, tmp, sizeof(acc)); }
+            memcpy(out, acc, sizeof(acc));
+        };
+        std::vector<uint32_t> lane_polys((size_t)kRandDeg * 32), jump((size_t)3 * kRandLevel * kRandDeg);
+        uint32_t step[kRandDeg], acc[kRandDeg], tmp[kRandDeg];
+        power(kRandLaneValues, step);
+        memset(acc, 0, sizeof(acc)); acc[0] = 1;
+        for (int l = 0; l < 32; ++l) {
+            for (int k = 0; k < kRandDeg; ++k) lane_polys[(size_t)k * 32 + l] = acc[k];
+            rand_poly_mul(acc, step, tmp); memcpy(acc, tmp, sizeof(acc));
+        }
+        unsigned long long stride = kRandWarpValues;
+        for (int level = 0; level < 3; ++level, stride *= kRandLevel) {
+            power(stride, step);
+            memset(acc, 0, sizeof(acc)); acc[0] = 1;
+            for (int u = 0; u < kRandLevel; ++u) {
+                memcpy(&jump[((size_t)level * kRandLevel + u) * kRandDeg], acc, sizeof(acc));
+                rand_poly_mul(acc, step, tmp); memcpy(acc, tmp, sizeof(acc));
+            }
+        }
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_lane), lane_polys.size() * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(ctx->d_rand_lane, lane_polys.data(), lane_polys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_jump), jump.size() * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(ctx->d_rand_jump, jump.data(), jump.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
 #undef CREATE_TRY
     *out = ctx;
@@ -786,6 +899,8 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     if (ctx->d_lut_ring) cudaFree(ctx->d_lut_ring);
     if (ctx->d_rand_pow2) cudaFree(ctx->d_rand_pow2);
     if (ctx->d_rand_base) cudaFree(ctx->d_rand_base);
+    if (ctx->d_rand_lane) cudaFree(ctx->d_rand_lane);
+    if (ctx->d_rand_jump) cudaFree(ctx->d_rand_jump);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

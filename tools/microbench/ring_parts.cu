@@ -13,6 +13,17 @@ using G = RingGeom<16, 3>;
 constexpr int SMEM = G::LUT_BYTES + 2 * G::TILE_BYTES;
 constexpr int ITER = 300;
 
+struct SinkEmit {                 // a cheap stand-in for the kernel's emitter
+    int sink = 0;
+    __device__ void quantise(int, double sum) {
+        double v = __dmul_rn(sum, 13295047.7);
+        if (v > 8388607.0) v = 8388607.0; else if (v < -8388607.0) v = -8388607.0;
+        const double r = trunc(v);
+        sink += __double2int_rz(r + ((v - r >= 0.5) ? 1.0 : ((v - r <= -0.5) ? -1.0 : 0.0)));
+    }
+    __device__ void store() { sink ^= __shfl_xor_sync(0xffffffffu, sink, 16); }
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(G::NTHR, 1) parts_kernel(unsigned long long* cycles, int* out, uint32_t seed) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -34,18 +45,8 @@ __global__ void __launch_bounds__(G::NTHR, 1) parts_kernel(unsigned long long* c
     for (int it = 0; it < ITER; ++it) {
         const uint32_t wnew = w0 + (uint32_t)((it % 3) * G::HOP);
         if (MODE != 0) ring_head<G>(lane, smem, wnew, loff, tid, 0, RingNoTrace());
-        if (MODE == 3) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double v = __dmul_rn(lane.p[k], 13295047.7);
-                if (v > 8388607.0) v = 8388607.0; else if (v < -8388607.0) v = -8388607.0;
-                const int q = __double2int_rz(round(v));
-                const int s = __shfl_xor_sync(0xffffffffu, q, 16);
-                sink += q ^ s;
-            }
-            if (sink == 0x7fffffff) out[tid] = sink;
-        }
-        if (MODE != 1) ring_tail<G>(lane, smem, wnew, loff, tid, 0, RingNoTrace());
+        if (MODE == 3) { SinkEmit e; ring_tail<G>(lane, smem, wnew, loff, tid, 0, e, RingNoTrace()); sink += e.sink; }
+        else if (MODE != 1) { RingNoEmit e; ring_tail<G>(lane, smem, wnew, loff, tid, 0, e, RingNoTrace()); sink += (int)lane.p[it & 3]; }
         else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) { lane.p[k] = lane.n[k]; lane.n[k] = 0.0; }
