@@ -214,8 +214,6 @@ def run_gpu_arm(args, wl):
         g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2, "ring": 3}[args.kernel])
     if args.threads:
         g.set_option("threads", args.threads)
-    if args.ring_rounds:
-        g.set_option("ring_rounds", args.ring_rounds)
 
     # device-resident ring of distinct input/output buffers, larger than L2 in total, so no step
     # finds its bytes in L2 from the step before
@@ -360,7 +358,6 @@ def main():
     ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring"])
     ap.add_argument("--align", type=int, default=1, help="0: device buffer starts at stream byte 0 (frame grid off by one byte)")
     ap.add_argument("--threads", type=int, default=0)
-    ap.add_argument("--ring-rounds", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="length of the CPU-baseline sample (stream seconds)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
     args = ap.parse_args()

@@ -117,6 +117,30 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// mbarrier (shared::cta) helpers for the ring kernel's split-phase tile pipeline
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives once every cp.async this thread has issued so far has landed (counts as one of the
+// barrier's expected arrivals)
+__device__ __forceinline__ void mbar_arrive_after_cp_async(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    for (unsigned spins = 0;; ++spins) {
+        unsigned done;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();       // a lost arrival must fail the launch, not hang the GPU
+    }
+}
+
 // Tiles are numbered channel-fastest: the CTAs that run side by side write the same frames of
 // neighbouring channels, so the 4-byte slots of one 32-byte output sector meet in L2 before the
 // sector goes to HBM (frame-major interleaved output, dsd_decimator.cpp:213).
@@ -321,11 +345,26 @@ struct RingEmitter {
     }
 };
 
+// Tile pipeline.  Three tile buffers and two mbarriers per buffer; nothing in the steady state
+// makes one warp wait for another:
+//   full[b]   expects one arrival per thread; a thread arrives when the cp.async chunks it staged
+//             for the tile have landed.  Staging of tile i+1 is issued at the top of tile i, the
+//             wait comes a whole tile later.
+//   empty[b]  a thread arrives when it has read buffer b for the last time (after the first 16
+//             steps of the NEXT tile, which still finish frames of this one); the buffer is
+//             refilled another tile later, so that wait does not block either.
 template <class G, bool F64OUT, bool DITHER>
 __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // [0, LUT_BYTES): table image; then two tiles of two byte buffers each.
+    // [0, LUT_BYTES): table image; three tiles of two byte buffers each; six mbarriers.
+    constexpr int NBUF = G::NBUF;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::LUT_BYTES + NBUF * G::TILE_BYTES);
+    uint64_t* empty = full + NBUF;
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], G::NTHR); mbar_init(&empty[b], G::NTHR); }
+    }
+    __syncthreads();                 // barriers initialised before anybody arrives on them
     {
         const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
         for (int k = tid; k < G::LUT_BYTES / 16; k += G::NTHR) cp_async16(smem + 16 * k, img + 16 * k);
@@ -343,19 +382,27 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     const uint32_t w0 = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lane, tid, a_tile));
     uint32_t loff = 0;
 
-    long long tile = blockIdx.x;
-    if (tile >= ntiles) { cp_async_commit(); cp_async_wait<0>(); return; }
-    int buf = 0;
+    long long tile = blockIdx.x;     // grid <= ntiles
     RingTile tl = ring_tile_at<G>(tile, a.nframes, a.nch);
     ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
+    __threadfence_block();           // plain stores of edge chunks are ordered before the arrival
+    mbar_arrive_after_cp_async(&full[0]);                       // covers the table image too
 
     RingDest prev;                   // nothing to emit in the very first period: every store is off
     prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
-    while (tile < ntiles) {
+    int b = 0, use = 0;              // buffer of the current tile, how often it has been used before
+    for (long long i = 0; tile < ntiles; ++i) {
         const long long next = tile + gridDim.x;
+        const int bn = b + 1 == NBUF ? 0 : b + 1;
+        if (next < ntiles) {
+            // buffer bn last held tile i-2; its use count is `use` when bn > b, else use + 1, minus one
+            if (i + 1 >= NBUF) mbar_wait(&empty[bn], (unsigned)(((i + 1) / NBUF - 1) & 1));
+            const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
+            ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16);
+            __threadfence_block();
+            mbar_arrive_after_cp_async(&full[bn]);
+        }
+        mbar_wait(&full[b], (unsigned)(use & 1));
         RingDest cur;
         cur.c = h ? tl.c[1] : tl.c[0];
         cur.c0 = tl.c[0];
@@ -363,25 +410,17 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         cur.fb = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
 #pragma unroll 1
         for (int n = 0; n < G::KR; ++n) {
-            const uint32_t wnew = w0 + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
+            const uint32_t wnew = w0 + (uint32_t)(b * G::TILE_BYTES + n * G::HOP);
             ring_head<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
-            if (n == 0) {
-                __syncthreads();     // nobody reads the other buffer (the previous tile) any more
-                if (next < ntiles) {
-                    const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
-                    ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES, aligned16);
-                }
-                cp_async_commit();
-            }
+            if (n == 0 && i > 0) mbar_arrive(&empty[b == 0 ? NBUF - 1 : b - 1]);   // done with the previous tile's bytes
             RingEmitter<F64OUT, DITHER> emit(a, prev, h, out_aligned16);
             ring_tail<G>(lane, smem, wnew, loff, tid, n, emit, RingNoTrace());
             prev = cur;
             cur.fb += 4LL * G::BLK_PER_ROUND;
         }
-        cp_async_wait<0>();
-        __syncthreads();             // the next tile has landed and is visible to every lane
         tile = next;
-        buf ^= 1;
+        if (bn == 0) ++use;
+        b = bn;
         if (tile < ntiles) tl = ring_tile_at<G>(tile, a.nframes, a.nch);
     }
     // the one drain of this CTA: 16 more steps finish the last frames
@@ -576,7 +615,6 @@ struct dsdgpu_ctx {
     int sm_count = 0;
     int kernel = DSDGPU_KERNEL_AUTO;
     int threads = 512;
-    int ring_rounds = 2;                     // periods per tile of the ring kernel (2 or 3)
     int dither_stride = 0;                   // 0 = nch
     long long chunk_frames = 1LL << 21;
     double* d_lut_direct = nullptr;          // [nlut][256]
@@ -597,7 +635,6 @@ namespace {
 
 using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
-using Ring16x3 = RingGeom<16, 3>;
 using Ring16x2 = RingGeom<16, 2>;
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
@@ -687,7 +724,7 @@ int launch_skew(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
 
 template <class G, bool F64OUT, bool DITHER>
 int launch_ring_variant(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
-    const int smem = G::LUT_BYTES + 2 * G::TILE_BYTES;
+    const int smem = G::SMEM_BYTES;
     static thread_local int configured_device = -1;
     if (configured_device != ctx->device) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_ring_kernel<G, F64OUT, DITHER>,
@@ -763,8 +800,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     if (kernel == DSDGPU_KERNEL_RING) {
         if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs nlut=72, nstep=4 and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
-        if (ctx->ring_rounds == 2) return launch_ring<Ring16x2>(ctx, a, st);
-        return launch_ring<Ring16x3>(ctx, a, st);
+        return launch_ring<Ring16x2>(ctx, a, st);
     }
     if (kernel == DSDGPU_KERNEL_SKEW) {
         if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
@@ -831,8 +867,8 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
         bool plain = true;
         for (double v : tab) plain = plain && std::isfinite(v) && !(v == 0.0 && std::signbit(v));
         if (plain) {
-            std::vector<unsigned char> rimg(Ring16x3::LUT_BYTES);
-            ring_build_lut_image<Ring16x3>(tab.data(), rimg.data());
+            std::vector<unsigned char> rimg(Ring16x2::LUT_BYTES);
+            ring_build_lut_image<Ring16x2>(tab.data(), rimg.data());
             CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
             CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
         }
@@ -915,9 +951,6 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "threads")) {
         if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
         ctx->threads = (int)value;
-    } else if (!strcmp(key, "ring_rounds")) {
-        if (value < 2 || value > 3) return fail(ctx, DSDGPU_ERR_ARG, "ring_rounds must be 2 or 3");
-        ctx->ring_rounds = (int)value;
     } else if (!strcmp(key, "dither_stride")) {
         if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");
         ctx->dither_stride = (int)value;

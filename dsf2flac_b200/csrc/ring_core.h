@@ -65,6 +65,8 @@ struct RingGeom {
     static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
     static constexpr int HALF_BYTES = NSTEP * NTP + 256;
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
+    static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
+    static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
     static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == 0, "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0 && BACK % 4 == 0, "windows of successive rounds share their byte phase");
 };

@@ -77,8 +77,7 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx);
 const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
 
 /* Knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk), "threads"
- * (skew kernel CTA size, 512 or 1024), "ring_rounds" (ring kernel: 72-step periods per tile, 2 or 3;
- * tile = ring_rounds * 1024 frames of two channels), "dither_stride" (output samples per frame of the WHOLE
+ * (skew kernel CTA size, 512 or 1024), "dither_stride" (output samples per frame of the WHOLE
  * stream when this context only holds a channel subset of it: sample m of frame i, local channel
  * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default). Unknown keys are an
  * error. */

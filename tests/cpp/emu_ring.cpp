@@ -1,8 +1,9 @@
 // Host-side lane emulator for the ring kernel (dsf2flac_b200/csrc/ring_core.h).
 //
 // Walks the tiles of every CTA of a small launch exactly like decimate_ring_kernel does -- same
-// double-buffered shared-memory image, the next tile staged over the previous one at the kernel's
-// mid-tile barrier, per-lane state carried across periods and tiles, one drain at the end -- running
+// shared-memory image with three tile buffers, the next tile staged at the top of each tile over
+// the buffer that held the tile before the previous one, per-lane state carried across periods
+// and tiles, one drain at the end -- running
 // ring_head()/ring_tail() once per thread id, for a small multi-channel stream, and
 //   1. compares every emitted fp64 sum, bit for bit, with the straightforward
 //      sum_{t=0..71} lut[t][B_c(p - t)] in reference order (dsd_decimator.cpp:194-198), and
@@ -72,8 +73,8 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         return (o >= 0 && o < in_count) ? src[c][(size_t)o] : fill;
     };
 
-    // smem image exactly as the kernel lays it out: tables, then two tile buffers
-    std::vector<unsigned char> smem((size_t)G::LUT_BYTES + 2 * G::TILE_BYTES);
+    // smem image exactly as the kernel lays it out: tables, then NBUF tile buffers (+ barriers)
+    std::vector<unsigned char> smem((size_t)G::SMEM_BYTES);
     g_smem_size = smem.size();
     const long long ntiles = ring_tile_count<G>(nframes, nch);
     int a_tile;
@@ -119,6 +120,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
     for (int cta = 0; cta < grid && cta < ntiles; ++cta) {
         ring_build_lut_image<G>(lut.data(), smem.data());
         for (size_t k = G::LUT_BYTES; k < smem.size(); ++k) smem[k] = (unsigned char)(rand() & 0xff);
+        g_smem_size = (size_t)G::LUT_BYTES + G::NBUF * G::TILE_BYTES;   // the barriers behind the tiles are never data
         std::vector<RingLane> lanes(G::NTHR);
         std::vector<uint32_t> w0(G::NTHR), loff(G::NTHR, 0);
         std::vector<Dest> prev(G::NTHR);
@@ -133,6 +135,10 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         while (tile < ntiles) {
             const long long next = tile + grid;
             const RingTile tl = ring_tile_at<G>(tile, nframes, nch);
+            // top of the tile: the kernel refills the buffer that held the tile before the previous one
+            const int bn = (buf + 1) % G::NBUF;
+            if (next < ntiles) { if (stage(next, bn)) return 2; }
+            else for (int k = 0; k < G::TILE_BYTES; ++k) smem[(size_t)G::LUT_BYTES + bn * G::TILE_BYTES + k] = (unsigned char)(rand() & 0xff);
             const bool trace = (cta == 0) && (tile == cta || next >= ntiles);
             for (int n = 0; n < G::KR; ++n, ++period) {
                 std::vector<Access> lut_log, word_log;
@@ -140,11 +146,6 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                 for (int tid = 0; tid < G::NTHR; ++tid) {
                     const uint32_t wnew = w0[tid] + (uint32_t)(buf * G::TILE_BYTES + n * G::HOP);
                     ring_head<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, rec);
-                }
-                if (n == 0) {
-                    // the kernel's mid-tile barrier: from here on the other buffer is refilled
-                    if (next < ntiles) { if (stage(next, buf ^ 1)) return 2; }
-                    else for (int k = 0; k < G::TILE_BYTES; ++k) smem[(size_t)G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES + k] = (unsigned char)(rand() & 0xff);
                 }
                 for (int tid = 0; tid < G::NTHR; ++tid) {
                     const int l = tid & 31, w = tid >> 5, h = l >> 4;
@@ -166,7 +167,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                 }
             }
             tile = next;
-            buf ^= 1;
+            buf = bn;
         }
         if (have_prev)
             for (int tid = 0; tid < G::NTHR; ++tid) {
