@@ -214,6 +214,10 @@ def run_gpu_arm(args, wl):
         g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2, "ring": 3}[args.kernel])
     if args.threads:
         g.set_option("threads", args.threads)
+    if args.slots:
+        g.set_option("slots", args.slots)
+    if args.chunk_frames:
+        g.set_option("chunk_frames", args.chunk_frames)
 
     # device-resident ring of distinct input/output buffers, larger than L2 in total, so no step
     # finds its bytes in L2 from the step before
@@ -279,6 +283,37 @@ def run_gpu_arm(args, wl):
     barrier()
     checksum = int(pin_out.array[:: max(1, nframes // 65536)].astype(np.int64).sum())
 
+    # ---- what the link allows: pinned copies of the same sizes, one way and both ways at once --
+    link = None
+    if rank == 0:
+        h_in = torch.from_numpy(pin_in.array.reshape(-1))          # views of the pinned buffers
+        h_out = torch.from_numpy(pin_out.array.reshape(-1))
+        dv_in = torch.empty_like(h_in, device="cuda")
+        dv_out = torch.empty_like(h_out, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def timed(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        def up():
+            with torch.cuda.stream(s1):
+                dv_in.copy_(h_in, non_blocking=True)
+
+        def down():
+            with torch.cuda.stream(s2):
+                h_out.copy_(dv_out, non_blocking=True)
+
+        t_up, t_down = timed(up), timed(down)
+        t_both = timed(lambda: (up(), down()))
+        link = {"h2d_gbs": in_bytes / t_up / 1e9, "d2h_gbs": out_bytes / t_down / 1e9,
+                "duplex_ms": t_both * 1e3, "note": "pinned cudaMemcpyAsync of one step's input / output; duplex = both at once"}
+        del dv_in, dv_out
+
     # ---- the drop-in class itself (reader drained byte by byte, as dsf2flac would run it) -----
     plugin = None
     if rank == 0 and args.plugin_seconds > 0:
@@ -336,7 +371,8 @@ def run_gpu_arm(args, wl):
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": e2e_s / args.steps * 1e3, "x_realtime": e2e_value * 1e6 / (dsd_fs * nch),
-                    "api": "dsdgpu_decimate_host (pinned host buffers, double-buffered chunks)", "checksum": checksum},
+                    "api": "dsdgpu_decimate_host (pinned host buffers, chunks pipelined over the context's slots)",
+                    "checksum": checksum, "link": link},
             "plugin": plugin, "gpu_launches": launches, "clocks": clocks,
         }), flush=True)
     pin_in.free()
@@ -358,6 +394,8 @@ def main():
     ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring"])
     ap.add_argument("--align", type=int, default=1, help="0: device buffer starts at stream byte 0 (frame grid off by one byte)")
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=0, help="pipelined slots of the host entry point (1..4)")
+    ap.add_argument("--chunk-frames", type=int, default=0, help="frames per pipelined host chunk")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="length of the CPU-baseline sample (stream seconds)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
     args = ap.parse_args()

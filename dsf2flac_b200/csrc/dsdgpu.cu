@@ -616,7 +616,7 @@ struct dsdgpu_ctx {
     int kernel = DSDGPU_KERNEL_AUTO;
     int threads = 512;
     int dither_stride = 0;                   // 0 = nch
-    long long chunk_frames = 1LL << 21;
+    long long chunk_frames = 1LL << 20;
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
     unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only)
@@ -625,7 +625,8 @@ struct dsdgpu_ctx {
     uint32_t* d_rand_lane = nullptr;         // x^(248*l), l < 32, stored [k][l]
     uint32_t* d_rand_jump = nullptr;         // x^(7936 * 128^level * u), [level][u][k]
     cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
-    dsdgpu_slot slots[2];
+    dsdgpu_slot slots[DSDGPU_SLOTS];
+    int pipeline_slots = DSDGPU_SLOTS;       // slots dsdgpu_decimate_host cycles through
     dsdgpu_slot own;                         // scratch for the device entry point
     unsigned long long launches = 0;
     char err[256] = "";
@@ -849,7 +850,7 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     CREATE_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (int s = 0; s < 2; ++s) CREATE_TRY(cudaStreamCreateWithFlags(&ctx->slots[s].stream, cudaStreamNonBlocking));
+    for (int s = 0; s < DSDGPU_SLOTS; ++s) CREATE_TRY(cudaStreamCreateWithFlags(&ctx->slots[s].stream, cudaStreamNonBlocking));
 
     // tables: fp32 variant = every entry rounded to fp32, then widened (accumulation stays fp64)
     std::vector<double> tab((size_t)nlut * 256);
@@ -928,7 +929,7 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
 void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (int s = 0; s < 2; ++s) free_slot(ctx->slots[s]);
+    for (int s = 0; s < DSDGPU_SLOTS; ++s) free_slot(ctx->slots[s]);
     free_slot(ctx->own);
     if (ctx->d_lut_direct) cudaFree(ctx->d_lut_direct);
     if (ctx->d_lut_skew) cudaFree(ctx->d_lut_skew);
@@ -954,6 +955,9 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "dither_stride")) {
         if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");
         ctx->dither_stride = (int)value;
+    } else if (!strcmp(key, "slots")) {
+        if (value < 1 || value > DSDGPU_SLOTS) return fail(ctx, DSDGPU_ERR_ARG, "slots must be 1..%d", DSDGPU_SLOTS);
+        ctx->pipeline_slots = (int)value;
     } else if (!strcmp(key, "chunk_frames")) {
         if (value < 1) return fail(ctx, DSDGPU_ERR_ARG, "chunk_frames must be >= 1");
         ctx->chunk_frames = value;
@@ -994,7 +998,7 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
                   double dither_amp, double clip, uint64_t dither_first_sample, int out_kind, void* out) {
     int rc = check_call(ctx, in, in_count, nframes, out_kind, out);
     if (rc) return rc;
-    if (slot < 0 || slot > 1) return fail(ctx, DSDGPU_ERR_ARG, "slot must be 0 or 1");
+    if (slot < 0 || slot >= DSDGPU_SLOTS) return fail(ctx, DSDGPU_ERR_ARG, "slot must be 0..%d", DSDGPU_SLOTS - 1);
     dsdgpu_slot& s = ctx->slots[slot];
     if (s.busy) return fail(ctx, DSDGPU_ERR_STATE, "slot %d is still in flight", slot);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1033,7 +1037,7 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
 
 int dsdgpu_wait(dsdgpu_ctx* ctx, int slot) {
     if (!ctx) return DSDGPU_ERR_ARG;
-    if (slot < 0 || slot > 1) return fail(ctx, DSDGPU_ERR_ARG, "slot must be 0 or 1");
+    if (slot < 0 || slot >= DSDGPU_SLOTS) return fail(ctx, DSDGPU_ERR_ARG, "slot must be 0..%d", DSDGPU_SLOTS - 1);
     dsdgpu_slot& s = ctx->slots[slot];
     if (!s.busy) return fail(ctx, DSDGPU_ERR_STATE, "slot %d has nothing in flight", slot);
     s.busy = false;
@@ -1051,9 +1055,10 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
     const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
     const long long chunk = ctx->chunk_frames;
     long long k = 0;
-    bool inflight[2] = {false, false};
+    const int nslots = ctx->pipeline_slots;
+    bool inflight[DSDGPU_SLOTS] = {false};
     for (int64_t f = 0; f < nframes; f += chunk, ++k) {
-        const int slot = (int)(k & 1);
+        const int slot = (int)(k % nslots);
         if (inflight[slot]) { rc = dsdgpu_wait(ctx, slot); inflight[slot] = false; if (rc) break; }
         const int64_t n = nframes - f < chunk ? nframes - f : chunk;
         rc = dsdgpu_submit(ctx, slot, in, in_stride, in_first, in_count, fill, p0 + f * ctx->nstep, n, scale,
@@ -1062,7 +1067,7 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
         if (rc) break;
         inflight[slot] = true;
     }
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < DSDGPU_SLOTS; ++s)
         if (inflight[s]) { int r2 = dsdgpu_wait(ctx, s); if (!rc) rc = r2; }
     return rc;
 }

@@ -47,6 +47,9 @@ enum {
 
 enum { DSDGPU_OUT_INT32 = 0, DSDGPU_OUT_FLOAT64 = 1 };
 
+/* Independent upload/kernel/download pipelines ("slots") a context owns. */
+#define DSDGPU_SLOTS 4
+
 /* Kernel selection, for tests and benchmarking (dsdgpu_set_option "kernel"). */
 enum {
     DSDGPU_KERNEL_AUTO = 0,   /* ring kernel when the geometry supports it, else direct */
@@ -76,7 +79,8 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx);
  * Maps to DsdDecimator::getErrorMsg (dsd_decimator.cpp:113-115). */
 const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
 
-/* Knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk), "threads"
+/* Knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk, default 2^20),
+ * "slots" (how many of the DSDGPU_SLOTS pipelines dsdgpu_decimate_host cycles through), "threads"
  * (skew kernel CTA size, 512 or 1024), "dither_stride" (output samples per frame of the WHOLE
  * stream when this context only holds a channel subset of it: sample m of frame i, local channel
  * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default). Unknown keys are an
@@ -110,8 +114,8 @@ int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_strid
 
 /*
  * Same operator with HOST buffers: uploads the bytes, runs the kernel, downloads the PCM,
- * internally cut into chunks that are double-buffered over two slots so that the upload of
- * chunk k+1, the kernel of chunk k and the download of chunk k-1 overlap.  Synchronous.
+ * internally cut into chunks that cycle through the context's slots so that uploads, kernels and
+ * downloads of neighbouring chunks overlap (PCIe runs in both directions at once).  Synchronous.
  * This is what DsdDecimator::getSamples calls (dsd_decimator.cpp:157-159).
  */
 int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first,
@@ -122,7 +126,7 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
 /*
  * The two halves of the above for callers that want to overlap their own work (reader drain,
  * FLAC encode) with the GPU: submit() enqueues upload + kernel + download of one chunk on slot
- * 0 or 1 and returns at once; wait() blocks until that slot's output is in `out`.
+ * 0..DSDGPU_SLOTS-1 and returns at once; wait() blocks until that slot's output is in `out`.
  * Host buffers must stay untouched between submit and wait.
  */
 int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride,
