@@ -347,6 +347,14 @@ def run_gpu_arm(args, wl):
                 "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                         "algorithmic_bytes_per_sample": fir.nstep + 4, "peak_source": peak_src}}
+        try:                                               # measured DRAM traffic of the same kernel on the same workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.kernel or "ring"]
+            if tr["workload"] == args.workload and fir.ratio == 32 and not args.dither:
+                roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roof["traffic_source"] = tr["source"]
+                roof["algorithmic_hbm_bytes"] = hbm_bytes
+        except Exception:
+            pass
         if clocks and clocks.get("sm_mhz"):
             roof["frac_at_sampled_clock"] = achieved / (n_sm * SMEM_BYTES_PER_CLK_PER_SM * clocks["sm_mhz"] * 1e6 / 1e9)
         # CPU baseline: bounded sample on the host cores
