@@ -38,8 +38,9 @@ thread_local char g_create_error[256] = "";
 // kernel arguments
 // ---------------------------------------------------------------------------------------------
 struct DecimateArgs {
-    const uint8_t* in;       // planar [nch][in_stride]
+    const uint8_t* in;       // planar [nch][in_stride], or blocks of 2^block_shift bytes per channel
     long long in_stride;
+    int block_shift;         // -1: planar rows; >= 4: DSF-style block-planar source (in_stride unused)
     long long in_first;      // stream index of in[c][0]
     long long in_count;      // valid bytes per channel
     long long p0;            // stream index of the newest byte of frame 0
@@ -53,6 +54,20 @@ struct DecimateArgs {
     void* out;
     int out_kind;
 };
+
+// Byte offset from a.in of source byte o (0 <= o < in_count) of channel c.  Planar rows, or the
+// DSF data-chunk layout [block 0: ch0 ch1 ..][block 1: ch0 ch1 ..] (dsf_file_reader.cpp:122-149),
+// consumed in place instead of being re-packed by a reader.
+__device__ __forceinline__ long long src_offset(const DecimateArgs& a, int c, long long o) {
+    if (a.block_shift < 0) return (long long)c * a.in_stride + o;
+    const long long blk = o >> a.block_shift;
+    return (((blk * a.nch + c) << a.block_shift) | (o & ((1LL << a.block_shift) - 1)));
+}
+__device__ __forceinline__ bool src_aligned16(const DecimateArgs& a) {
+    const unsigned long long bits = reinterpret_cast<unsigned long long>(a.in) |
+                                    (a.block_shift < 0 ? (unsigned long long)a.in_stride : 0ULL);
+    return (bits & 15ULL) == 0;
+}
 
 // dsd_decimator.cpp:199-216: scale, dither, clip.  No FMA contraction: the reference is x86-64
 // -O3 without FMA, so sum*scale and (r1-r2)*amp are each rounded before the add.
@@ -95,11 +110,10 @@ decimate_direct_kernel(DecimateArgs a, int nlut, int nstep) {
         const long long f = idx / a.nch;               // idx is the output index: stores coalesce
         const int c = (int)(idx - f * a.nch);
         const long long p = a.p0 + f * nstep;
-        const uint8_t* src = a.in + (long long)c * a.in_stride;
         double sum = 0.0;
         for (int t = 0; t < nlut; ++t) {
             const long long o = p - t - a.in_first;
-            const unsigned b = (o >= 0 && o < a.in_count) ? (unsigned)src[o] : a.fill;
+            const unsigned b = (o >= 0 && o < a.in_count) ? (unsigned)a.in[src_offset(a, c, o)] : a.fill;
             sum = __dadd_rn(sum, lut_s[t * 256 + b]);
         }
         store_sample(a, f, c, sum);
@@ -160,13 +174,12 @@ __device__ __forceinline__ void skew_tile_geometry(const DecimateArgs& a, long l
 template <class G>
 __device__ __forceinline__ void skew_stage_tile(const DecimateArgs& a, int c, long long t0,
                                                 unsigned char* dst, bool aligned16) {
-    const uint8_t* src = a.in + (long long)c * a.in_stride;
     const long long o0 = t0 - a.in_first;
     for (int k = threadIdx.x; k < G::TILE_BYTES / 16; k += G::NTHR) {
         const long long o = o0 + 16LL * k;
         unsigned char* d = dst + 16 * k;
         if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
-            cp_async16(d, src + o);
+            cp_async16(d, a.in + src_offset(a, c, o));
         } else {
             uint32_t w[4];
 #pragma unroll
@@ -175,7 +188,7 @@ __device__ __forceinline__ void skew_stage_tile(const DecimateArgs& a, int c, lo
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const long long ob = o + 4 * q + b;
-                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)src[ob] : a.fill;
+                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
                     v |= byte << (8 * b);
                 }
                 w[q] = v;
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_skew_kernel(DecimateArgs 
     }
     const long long tiles_per_ch = (a.nframes + G::NT - 1) / G::NT;
     const long long ntiles = tiles_per_ch * a.nch;
-    const bool aligned16 = ((reinterpret_cast<unsigned long long>(a.in) | (unsigned long long)a.in_stride) & 15ULL) == 0;
+    const bool aligned16 = src_aligned16(a);
 
     long long tile = blockIdx.x;
     int buf = 0;
@@ -245,11 +258,11 @@ __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const Rin
         const int kk = k - h * CHUNKS;
         long long t0; int a_tile;
         ring_half_origin<G>(a.p0, a.in_first, h ? tl.f0[1] : tl.f0[0], t0, a_tile);
-        const uint8_t* src = a.in + (long long)(h ? tl.c[1] : tl.c[0]) * a.in_stride;
+        const int c = h ? tl.c[1] : tl.c[0];
         const long long o = t0 - a.in_first + 16LL * kk;
         unsigned char* d = dst + h * G::HALF_BYTES + 16 * kk;
         if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
-            cp_async16(d, src + o);
+            cp_async16(d, a.in + src_offset(a, c, o));
         } else {
             uint32_t w[4];
 #pragma unroll
@@ -258,7 +271,7 @@ __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const Rin
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const long long ob = o + 4 * q + b;
-                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)src[ob] : a.fill;
+                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
                     v |= byte << (8 * b);
                 }
                 w[q] = v;
@@ -370,7 +383,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         for (int k = tid; k < G::LUT_BYTES / 16; k += G::NTHR) cp_async16(smem + 16 * k, img + 16 * k);
     }
     const long long ntiles = ring_tile_count<G>(a.nframes, a.nch);
-    const bool aligned16 = ((reinterpret_cast<unsigned long long>(a.in) | (unsigned long long)a.in_stride) & 15ULL) == 0;
+    const bool aligned16 = src_aligned16(a);
     const bool out_aligned16 = (reinterpret_cast<unsigned long long>(a.out) & 15ULL) == 0;
     int a_tile;
     {
@@ -429,6 +442,34 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
 #pragma unroll
     for (int k = 0; k < 4; ++k) emit.quantise(k, lane.p[k]);
     emit.store();
+}
+
+// ---------------------------------------------------------------------------------------------
+// DSDIFF sources: the "DSD " chunk is byte-interleaved, in[o*nch + c] (dsdiff_file_reader.cpp:234).
+// One pass turns the bytes a run needs into planar rows (out[c*stride + pad + o]) for the kernels
+// above; a thread owns one aligned 4-byte word of every row.  Pure HBM traffic: 2 bytes moved per
+// source byte, against the 144 bytes of table reads each of them causes later.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+deinterleave_kernel(const uint8_t* __restrict__ in, long long count, int nch, uint8_t* __restrict__ out,
+                    long long stride, int pad) {
+    const long long words = (count + (pad & 3) + 3) / 4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < words;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long o0 = 4 * t - (pad & 3);                  // first source index of this word
+        for (int c = 0; c < nch; ++c) {
+            uint8_t* dst = out + (long long)c * stride + pad + o0;   // 4-byte aligned by construction
+            if (o0 >= 0 && o0 + 4 <= count) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) v |= (uint32_t)in[(o0 + b) * nch + c] << (8 * b);
+                *reinterpret_cast<uint32_t*>(dst) = v;
+            } else {
+                for (int b = 0; b < 4; ++b)
+                    if (o0 + b >= 0 && o0 + b < count) dst[b] = in[(o0 + b) * nch + c];
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,6 +643,8 @@ struct dsdgpu_slot {
     cudaStream_t stream = nullptr;
     uint8_t* d_in = nullptr;
     size_t in_cap = 0;
+    uint8_t* d_raw = nullptr;                // interleaved bytes as uploaded (DSDIFF sources)
+    size_t raw_cap = 0;
     void* d_out = nullptr;
     size_t out_cap = 0;
     double* d_dither = nullptr;
@@ -616,6 +659,7 @@ struct dsdgpu_ctx {
     int kernel = DSDGPU_KERNEL_AUTO;
     int threads = 512;
     int dither_stride = 0;                   // 0 = nch
+    long long source_block = 0;              // 0: planar rows; 1: byte-interleaved; 2^k >= 16: block-planar
     long long chunk_frames = 1LL << 20;
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
@@ -656,6 +700,7 @@ int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
 
 void free_slot(dsdgpu_slot& s) {
     if (s.d_in) cudaFree(s.d_in);
+    if (s.d_raw) cudaFree(s.d_raw);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_dither) cudaFree(s.d_dither);
     if (s.d_segment) cudaFree(s.d_segment);
@@ -773,14 +818,34 @@ int check_call(dsdgpu_ctx* ctx, const void* in, int64_t in_count, int64_t nframe
     return DSDGPU_OK;
 }
 
-// enqueue dither fill (if any) + the decimation kernel on `st`
-int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in, size_t in_stride,
+int block_shift_of(long long block) {
+    int sh = -1;
+    if (block >= 16) for (sh = 0; (1LL << sh) < block; ++sh) {}
+    return sh;
+}
+
+// planar rows for a run out of an interleaved device source: out row c = in[o*nch + c], o in [lo, hi)
+int launch_deinterleave(dsdgpu_ctx* ctx, const uint8_t* d_raw, long long count, uint8_t* d_planar, long long stride,
+                        int pad, cudaStream_t st) {
+    if (count <= 0) return DSDGPU_OK;
+    const long long words = (count + 3 + 3) / 4;
+    long long blocks = (words + 255) / 256;
+    if (blocks > 8LL * ctx->sm_count) blocks = 8LL * ctx->sm_count;
+    deinterleave_kernel<<<(int)blocks, 256, 0, st>>>(d_raw, count, ctx->nch, d_planar, stride, pad);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+// enqueue dither fill (if any) + the decimation kernel on `st`; block_shift as in DecimateArgs
+int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in, size_t in_stride, int block_shift,
                      int64_t in_first, int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes,
                      double scale, double dither_amp, double clip, uint64_t dither_first_sample,
                      int out_kind, void* d_out, cudaStream_t st) {
     if (nframes == 0) return DSDGPU_OK;
     DecimateArgs a;
-    a.in = d_in; a.in_stride = (long long)in_stride; a.in_first = in_first; a.in_count = in_count;
+    a.in = d_in; a.in_stride = (long long)in_stride; a.block_shift = block_shift;
+    a.in_first = in_first; a.in_count = in_count;
     a.p0 = p0; a.nframes = nframes; a.nch = ctx->nch; a.fill = fill;
     a.dither = nullptr; a.dither_stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
     a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
@@ -805,6 +870,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     }
     if (kernel == DSDGPU_KERNEL_SKEW) {
         if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
+        if (block_shift >= 0) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel reads planar sources only");
         a.lut = ctx->d_lut_skew;
         return ctx->threads == 1024 ? launch_skew<Skew1024>(ctx, a, st) : launch_skew<Skew512>(ctx, a, st);
     }
@@ -955,6 +1021,11 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "dither_stride")) {
         if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");
         ctx->dither_stride = (int)value;
+    } else if (!strcmp(key, "source_block_bytes")) {
+        const bool pow2 = value > 0 && (value & (value - 1)) == 0;
+        if (!(value == 0 || value == 1 || (pow2 && value >= 16 && value <= (1LL << 30))))
+            return fail(ctx, DSDGPU_ERR_ARG, "source_block_bytes must be 0 (planar), 1 (interleaved) or a power of two >= 16");
+        ctx->source_block = value;
     } else if (!strcmp(key, "slots")) {
         if (value < 1 || value > DSDGPU_SLOTS) return fail(ctx, DSDGPU_ERR_ARG, "slots must be 1..%d", DSDGPU_SLOTS);
         ctx->pipeline_slots = (int)value;
@@ -978,6 +1049,35 @@ void dsdgpu_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+// the window of stream bytes a run of frames can touch, clipped to what the caller has: [lo, hi)
+static void run_window(const dsdgpu_ctx* ctx, int64_t in_first, int64_t in_count, int64_t p0, int64_t nframes,
+                       int64_t& lo, int64_t& hi) {
+    lo = p0 - (ctx->nlut - 1);
+    hi = p0 + (nframes - 1) * ctx->nstep + 1;
+    if (lo < in_first) lo = in_first;
+    if (hi > in_first + in_count) hi = in_first + in_count;
+    if (hi < lo) hi = lo;
+}
+
+// Interleaved device bytes d_raw[(j - raw_first)*nch + c] for j in [lo, hi) -> planar rows in
+// scratch.d_in, placed like dsdgpu_submit places host bytes (frame grid 16-byte aligned; pad bytes
+// that stand for positions before the source are set to `fill`).  Returns the planar view.
+static int planar_from_interleaved(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_raw, int64_t raw_first,
+                                   int64_t lo, int64_t hi, int64_t p0, uint8_t fill, cudaStream_t st,
+                                   size_t& dstride, int64_t& first, int64_t& count) {
+    const int64_t n = hi - lo;
+    const int64_t pad = ((lo - p0 - 1) % 16 + 16) % 16;
+    dstride = ((size_t)(n + pad) + 255) & ~(size_t)255;
+    int rc = ensure(ctx, &scratch.d_in, &scratch.in_cap, dstride * ctx->nch + 256);
+    if (rc) return rc;
+    if (pad > 0 && p0 - (ctx->nlut - 1) < lo)
+        CUDA_TRY(ctx, cudaMemset2DAsync(scratch.d_in, dstride, fill, (size_t)pad, (size_t)ctx->nch, st));
+    rc = launch_deinterleave(ctx, d_raw + (size_t)(lo - raw_first) * ctx->nch, n, scratch.d_in, (long long)dstride, (int)pad, st);
+    first = lo - pad;
+    count = n + pad;
+    return rc;
+}
+
 int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_stride, int64_t in_first,
                            int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
                            double dither_amp, double clip, uint64_t dither_first_sample, int out_kind,
@@ -986,8 +1086,18 @@ int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_strid
     if (rc) return rc;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    rc = enqueue_decimate(ctx, ctx->own, d_in, in_stride, in_first, in_count, fill, p0, nframes, scale,
-                          dither_amp, clip, dither_first_sample, out_kind, d_out, st);
+    if (ctx->source_block == 1 && nframes > 0) {
+        int64_t lo, hi, first, count;
+        size_t dstride;
+        run_window(ctx, in_first, in_count, p0, nframes, lo, hi);
+        rc = planar_from_interleaved(ctx, ctx->own, d_in, in_first, lo, hi, p0, fill, st, dstride, first, count);
+        if (rc) return rc;
+        rc = enqueue_decimate(ctx, ctx->own, ctx->own.d_in, dstride, -1, first, count, fill, p0, nframes, scale,
+                              dither_amp, clip, dither_first_sample, out_kind, d_out, st);
+    } else {
+        rc = enqueue_decimate(ctx, ctx->own, d_in, in_stride, block_shift_of(ctx->source_block), in_first, in_count, fill,
+                              p0, nframes, scale, dither_amp, clip, dither_first_sample, out_kind, d_out, st);
+    }
     if (rc) return rc;
     if (!cuda_stream) CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return DSDGPU_OK;
@@ -1003,32 +1113,58 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
     if (s.busy) return fail(ctx, DSDGPU_ERR_STATE, "slot %d is still in flight", slot);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (nframes == 0) { s.busy = true; return DSDGPU_OK; }
-    // bytes this run of frames can touch, clipped to what the caller has
-    int64_t lo = p0 - (ctx->nlut - 1), hi = p0 + (nframes - 1) * ctx->nstep + 1;   // [lo, hi)
-    if (lo < in_first) lo = in_first;
-    if (hi > in_first + in_count) hi = in_first + in_count;
-    int64_t n = hi > lo ? hi - lo : 0;
-    // Place the bytes so that (p0 - first + 1) is a multiple of 16, `first` being the stream index
-    // of the first byte of the device buffer: the ring kernel's window loads are then bank-conflict
-    // free (ring_core.h).  The pad bytes in front count as part of the source (d_in stays 16-byte
-    // aligned): either they are older than anything a frame of this run reads, or -- when the run
-    // starts before the caller's first byte -- they are set to the fill byte they stand for.
-    const int64_t pad = ((lo - p0 - 1) % 16 + 16) % 16;
-    const bool reads_before_source = p0 - (ctx->nlut - 1) < lo;
-    const size_t dstride = ((size_t)(n + pad) + 255) & ~(size_t)255;
-    rc = ensure(ctx, &s.d_in, &s.in_cap, dstride * ctx->nch + 256);
-    if (rc) return rc;
     const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
     const size_t out_bytes = (size_t)nframes * ctx->nch * elem;
     rc = ensure(ctx, reinterpret_cast<unsigned char**>(&s.d_out), &s.out_cap, out_bytes);
     if (rc) return rc;
-    if (pad > 0 && reads_before_source)
-        CUDA_TRY(ctx, cudaMemset2DAsync(s.d_in, dstride, fill, (size_t)pad, (size_t)ctx->nch, s.stream));
-    if (n > 0)
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in + pad, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
-                                        (size_t)ctx->nch, cudaMemcpyHostToDevice, s.stream));
-    rc = enqueue_decimate(ctx, s, s.d_in, dstride, lo - pad, n + pad, fill, p0, nframes, scale, dither_amp, clip,
-                          dither_first_sample, out_kind, s.d_out, s.stream);
+    // bytes this run of frames can touch, clipped to what the caller has
+    int64_t lo, hi;
+    run_window(ctx, in_first, in_count, p0, nframes, lo, hi);
+    const int64_t n = hi - lo;
+    if (ctx->source_block >= 16) {
+        // DSF-style source: whole blocks of every channel are one contiguous range of the host buffer
+        const int64_t B = ctx->source_block;
+        if (in_first % B != 0) return fail(ctx, DSDGPU_ERR_ARG, "block sources must start on a block boundary");
+        const int64_t b0 = (lo - in_first) / B, b1 = n > 0 ? (hi - in_first + B - 1) / B : b0;
+        const size_t bytes = (size_t)(b1 - b0) * (size_t)B * ctx->nch;
+        rc = ensure(ctx, &s.d_in, &s.in_cap, bytes + 256);
+        if (rc) return rc;
+        if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, in + (size_t)b0 * B * ctx->nch, bytes, cudaMemcpyHostToDevice, s.stream));
+        int64_t cnt = in_first + in_count - (in_first + b0 * B);
+        if (cnt > (b1 - b0) * B) cnt = (b1 - b0) * B;
+        rc = enqueue_decimate(ctx, s, s.d_in, 0, block_shift_of(B), in_first + b0 * B, cnt, fill, p0, nframes, scale,
+                              dither_amp, clip, dither_first_sample, out_kind, s.d_out, s.stream);
+    } else if (ctx->source_block == 1) {
+        // DSDIFF-style source: upload the interleaved range as it is, split it on the device
+        const size_t bytes = (size_t)n * ctx->nch;
+        rc = ensure(ctx, &s.d_raw, &s.raw_cap, bytes + 256);
+        if (rc) return rc;
+        if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_raw, in + (size_t)(lo - in_first) * ctx->nch, bytes, cudaMemcpyHostToDevice, s.stream));
+        int64_t first, count;
+        size_t dstride;
+        rc = planar_from_interleaved(ctx, s, s.d_raw, lo, lo, hi, p0, fill, s.stream, dstride, first, count);
+        if (rc) return rc;
+        rc = enqueue_decimate(ctx, s, s.d_in, dstride, -1, first, count, fill, p0, nframes, scale, dither_amp, clip,
+                              dither_first_sample, out_kind, s.d_out, s.stream);
+    } else {
+        // Place the bytes so that (p0 - first + 1) is a multiple of 16, `first` being the stream index
+        // of the first byte of the device buffer: the ring kernel's window loads are then bank-conflict
+        // free (ring_core.h).  The pad bytes in front count as part of the source (d_in stays 16-byte
+        // aligned): either they are older than anything a frame of this run reads, or -- when the run
+        // starts before the caller's first byte -- they are set to the fill byte they stand for.
+        const int64_t pad = ((lo - p0 - 1) % 16 + 16) % 16;
+        const bool reads_before_source = p0 - (ctx->nlut - 1) < lo;
+        const size_t dstride = ((size_t)(n + pad) + 255) & ~(size_t)255;
+        rc = ensure(ctx, &s.d_in, &s.in_cap, dstride * ctx->nch + 256);
+        if (rc) return rc;
+        if (pad > 0 && reads_before_source)
+            CUDA_TRY(ctx, cudaMemset2DAsync(s.d_in, dstride, fill, (size_t)pad, (size_t)ctx->nch, s.stream));
+        if (n > 0)
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in + pad, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
+                                            (size_t)ctx->nch, cudaMemcpyHostToDevice, s.stream));
+        rc = enqueue_decimate(ctx, s, s.d_in, dstride, -1, lo - pad, n + pad, fill, p0, nframes, scale, dither_amp, clip,
+                              dither_first_sample, out_kind, s.d_out, s.stream);
+    }
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     s.busy = true;

@@ -14,7 +14,8 @@
  *   v    = sum*scale;  if dither_amp>0: v += (r1-r2)*dither_amp;  if clip>0: clamp to +-clip
  *   out[i*nch + c] = (int32) round(v)        (half away from zero)   |  = v   (f64 output)
  *
- * B_c(j) is byte j of channel c of the packed DSD stream: in[c*in_stride + (j - in_first)] for
+ * B_c(j) is byte j of channel c of the packed DSD stream: in[c*in_stride + (j - in_first)] (planar
+ * rows, the default; see "source_block_bytes" below for the containers' own layouts) for
  * in_first <= j < in_first+in_count and `fill` everywhere else (the reference reader's idle
  * byte 0x69 before the start and after the end of data, dsd_sample_reader.h:122,
  * dsf_file_reader.cpp:94-97).  r1, r2 are the glibc rand() draws number 2m and 2m+1
@@ -80,7 +81,14 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx);
 const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
 
 /* Knobs: "kernel" (enum above), "chunk_frames" (frames per pipelined host chunk, default 2^20),
- * "slots" (how many of the DSDGPU_SLOTS pipelines dsdgpu_decimate_host cycles through), "threads"
+ * "slots" (how many of the DSDGPU_SLOTS pipelines dsdgpu_decimate_host cycles through),
+ * "source_block_bytes" (layout of `in` / `d_in` for all decimate / submit calls that follow:
+ *   0  planar rows, in[c*in_stride + o]                                   o = j - in_first
+ *   B  power of two >= 16: DSF data chunk, blocks of B bytes per channel, channel after channel
+ *      (dsf_file_reader.cpp:122-149): in[((o / B)*nch + c)*B + o % B]; in_first % B must be 0
+ *   1  DSDIFF "DSD " chunk, byte-interleaved (dsdiff_file_reader.cpp:234): in[o*nch + c]
+ *   in_stride is ignored for B != 0; the bytes are consumed where they lie, no host re-packing),
+ * "threads"
  * (skew kernel CTA size, 512 or 1024), "dither_stride" (output samples per frame of the WHOLE
  * stream when this context only holds a channel subset of it: sample m of frame i, local channel
  * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default). Unknown keys are an

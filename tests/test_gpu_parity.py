@@ -228,3 +228,64 @@ def test_batch_runner_shards_on_gpu(oracle, world):
         want = oracle.run_app(j.planar, j.length_samples, j.msb_flag, j.dsd_fs, j.out_fs, scale, amp, clip)
         assert np.array_equal(got, want)
     runner.close()
+
+
+def to_blocks(planar, B):
+    """DSF data-chunk layout of a planar [nch, n] stream (n padded with zeros to whole blocks)."""
+    nch, n = planar.shape
+    nb = -(-n // B)
+    padded = np.zeros((nch, nb * B), dtype=np.uint8)
+    padded[:, :n] = planar
+    return np.ascontiguousarray(padded.reshape(nch, nb, B).transpose(1, 0, 2)).reshape(-1)
+
+
+@pytest.mark.parametrize("kernel", ["ring", "direct"])
+@pytest.mark.parametrize("nch", [1, 2, 3, 6])
+def test_container_layouts_consumed_in_place(oracle, nch, kernel):
+    """DSF block-planar and DSDIFF byte-interleaved sources give the same PCM as
+    planar rows of the same stream: chunked pipeline, ragged last block, frames that start in
+    the idle pre-fill and run past the end of the data."""
+    fir, g = make(32, 1, nch, kernel)
+    g.set_option("chunk_frames", 5000)
+    n = 4096 * 7 + 1234
+    data = seeded_bytes(nch, n, 40 + nch)
+    scale, amp, clip = filters.app_params(24, dither=True)
+    nframes = (n + 400) // fir.nstep
+    want = oracle.run_raw(data, n * 8, 1, DSD64, 88200, 0, nframes, scale, amp, clip)
+    for block, src in ((4096, to_blocks(data, 4096)), (64, to_blocks(data, 64)), (1, np.ascontiguousarray(data.T).reshape(-1))):
+        g.set_option("source_block_bytes", block)
+        got = np.empty((nframes, nch), dtype=np.int32)
+        g.decimate_host_raw(src.ctypes.data, 0, 0, n, 0x69, -1, nframes, scale, amp, clip, 0, capi.OUT_INT32, got.ctypes.data)
+        assert np.array_equal(got, want), block
+    # a window of the stream that starts on a later block
+    g.set_option("source_block_bytes", 4096)
+    src = to_blocks(data, 4096)
+    first = 2 * 4096
+    masked = np.full_like(data, 0x69)
+    masked[:, first:] = data[:, first:]
+    want = oracle.run_raw(masked, n * 8, 1, DSD64, 88200, 0, nframes, scale, 0.0, clip)
+    got = np.empty((nframes, nch), dtype=np.int32)
+    g.decimate_host_raw(src.ctypes.data + first * nch, 0, first, n - first, 0x69, -1, nframes, scale, 0.0, clip, 0,
+                        capi.OUT_INT32, got.ctypes.data)
+    assert np.array_equal(got, want)
+    g.set_option("source_block_bytes", 0)
+    g.close()
+
+
+def test_container_layouts_device_pointers(oracle):
+    import torch
+    fir, g = make(32, 0, 2)
+    n = 50000
+    data = seeded_bytes(2, n, 77)
+    nframes = filters.app_frames(n * 8, fir)
+    scale, amp, clip = filters.app_params(24, dither=False)
+    want = oracle.run_app(data, n * 8, 0, DSD64, 88200, scale, amp, clip)
+    for block, src in ((4096, to_blocks(data, 4096)), (1, np.ascontiguousarray(data.T).reshape(-1))):
+        g.set_option("source_block_bytes", block)
+        d_in = torch.from_numpy(src).cuda()
+        d_out = torch.zeros((nframes, 2), dtype=torch.int32, device="cuda")
+        g.decimate_device(d_in, 0, 0, n, 0x69, fir.nlut, nframes, scale, amp, clip, 0, capi.OUT_INT32, d_out)
+        assert np.array_equal(d_out.cpu().numpy(), want), block
+    with pytest.raises(capi.DsdGpuError):
+        g.set_option("source_block_bytes", 48)
+    g.close()
