@@ -34,6 +34,8 @@ GPU_PROTOTYPES = {
     "dsdgpu_kernel_launches": (C.c_ulonglong, [_vp]),
     "dsdgpu_host_alloc": (_vp, [C.c_size_t]),
     "dsdgpu_host_free": (None, [_vp]),
+    "dsdgpu_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "dsdgpu_host_unregister": (C.c_int, [_vp]),
     "dsdgpu_decimate_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64,
                                          C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _vp, _vp]),
     "dsdgpu_decimate_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64,
@@ -89,6 +91,12 @@ def host_lib(path=None):
     lib.dsdhost_run_app.restype = i64
     lib.dsdhost_run_app.argtypes = [_vp, C.c_int, i64, i64, C.c_uint8, C.c_int, u32, u32, dbl, dbl, dbl, C.c_int, u32,
                                     _vp, i64]
+    lib.dsdhost_file_info.restype = C.c_int
+    lib.dsdhost_file_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(i64), C.POINTER(i64)]
+    lib.dsdhost_file_channel_bytes.restype = i64
+    lib.dsdhost_file_channel_bytes.argtypes = [C.c_char_p, C.c_int, C.c_int, _vp, i64]
+    lib.dsdhost_convert_file.restype = i64
+    lib.dsdhost_convert_file.argtypes = [C.c_char_p, C.c_int, u32, dbl, dbl, dbl, C.c_int, u32, _vp, i64]
     lib.dsdhost_synth_sdm.restype = None
     lib.dsdhost_synth_sdm.argtypes = [_vp, i64, dbl, dbl, dbl, C.c_int]
     if path is None:

@@ -1048,6 +1048,14 @@ void* dsdgpu_host_alloc(size_t bytes) {
 void dsdgpu_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+int dsdgpu_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return DSDGPU_ERR_ARG;
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? DSDGPU_OK : DSDGPU_ERR_CUDA;
+}
+int dsdgpu_host_unregister(void* p) {
+    if (!p) return DSDGPU_ERR_ARG;
+    return cudaHostUnregister(p) == cudaSuccess ? DSDGPU_OK : DSDGPU_ERR_CUDA;
+}
 
 // the window of stream bytes a run of frames can touch, clipped to what the caller has: [lo, hi)
 static void run_window(const dsdgpu_ctx* ctx, int64_t in_first, int64_t in_count, int64_t p0, int64_t nframes,

@@ -57,7 +57,7 @@ DsdDecimator::DsdDecimator(DsdSampleReader *r, dsf2flac_uint32 rate)
       gpu(nullptr), lutBits(64), pos(-1), harvested(0), samplesOut(0), bytes(nullptr), bytesStride(0),
       bytesCap(0), bytesFirst(0), bytesCount(0), block(nullptr), blockCap(0), blockKind(0), blockPos(0),
       blockFrames(0), blockSample0(0), blockScale(0), blockDither(0), blockClip(0),
-      readAhead(kDefaultReadAhead)
+      readAhead(kDefaultReadAhead), bulk(nullptr), bulkBlock(0), bulkCount(0), bulkStride(0)
 {
     ratio = rate ? r->getSamplingFreq() / rate : 0;
     nStep = ratio / 8;
@@ -163,6 +163,19 @@ bool DsdDecimator::setLutPrecision(int bits)
     return openGpu(bits);
 }
 
+bool DsdDecimator::setBulkSource(const dsf2flac_uint8* data, dsf2flac_int64 blockBytes, dsf2flac_int64 deliveredBytes,
+                                 dsf2flac_int64 planarStride)
+{
+    if (!gpu || !data || deliveredBytes < 0) return false;
+    if (dsdgpu_set_option(gpu, "source_block_bytes", blockBytes) != DSDGPU_OK) {
+        fail(std::string("DsdDecimator: ") + dsdgpu_last_error(gpu));
+        return false;
+    }
+    bulk = data; bulkBlock = blockBytes; bulkCount = deliveredBytes; bulkStride = planarStride;
+    blockFrames = 0;
+    return true;
+}
+
 // Pull bytes out of the reader until stream byte `hi` has been seen, keeping [lo, hi] (and
 // whatever later bytes were already drained) contiguous in `bytes`.  The reader can only move
 // forward one byte per step(), so anything before `lo` that was not drained yet is stepped over.
@@ -220,10 +233,12 @@ bool DsdDecimator::refill(dsf2flac_uint32 wantFrames, dsf2flac_float64 scale, ds
     if (frames > useful) frames = useful;
     if (frames < (dsf2flac_int64)wantFrames) frames = wantFrames;
 
-    const dsf2flac_int64 lo = pos - ((dsf2flac_int64)nLookupTable - 1);
-    const dsf2flac_int64 hi = pos + (frames - 1) * (dsf2flac_int64)nStep;
-    harvest(lo, hi);
-    if (!valid) return false;
+    if (!bulk) {
+        const dsf2flac_int64 lo = pos - ((dsf2flac_int64)nLookupTable - 1);
+        const dsf2flac_int64 hi = pos + (frames - 1) * (dsf2flac_int64)nStep;
+        harvest(lo, hi);
+        if (!valid) return false;
+    }
 
     const size_t elem = outKind == DSDGPU_OUT_INT32 ? sizeof(dsf2flac_int32) : sizeof(double);
     const size_t needOut = (size_t)frames * nch * elem;
@@ -233,8 +248,11 @@ bool DsdDecimator::refill(dsf2flac_uint32 wantFrames, dsf2flac_float64 scale, ds
         blockCap = block ? needOut : 0;
         if (!block) { fail("DsdDecimator: pinned host allocation failed"); return false; }
     }
-    const int rc = dsdgpu_decimate_host(gpu, bytes, bytesStride, bytesFirst, bytesCount, reader->getIdleSample(),
-                                        pos, frames, scale, dither, clip, samplesOut, outKind, block);
+    const int rc = bulk
+        ? dsdgpu_decimate_host(gpu, bulk, (size_t)bulkStride, 0, bulkCount, reader->getIdleSample(), pos, frames, scale,
+                               dither, clip, samplesOut, outKind, block)
+        : dsdgpu_decimate_host(gpu, bytes, bytesStride, bytesFirst, bytesCount, reader->getIdleSample(), pos, frames,
+                               scale, dither, clip, samplesOut, outKind, block);
     if (rc != DSDGPU_OK) {
         fail(std::string("DsdDecimator: GPU decimation failed: ") + dsdgpu_last_error(gpu));
         blockFrames = 0;

@@ -51,6 +51,14 @@ public:
     void setReadAheadFrames(dsf2flac_uint32 frames);
     // 64 (default, bit-exact) or 32 (fp32 tables, fp64 accumulate). Takes effect immediately.
     bool setLutPrecision(int bits);
+    // Bulk source: the stream bytes of all channels in the container's own layout, so that nothing
+    // is pulled through reader->step() any more.  `data` holds stream bytes 0 ..
+    // deliveredBytes-1 of every channel: blockBytes = 0 planar rows of `planarStride` bytes,
+    // blockBytes = 2^k >= 16 DSF block-planar, blockBytes = 1 DSDIFF byte-interleaved; every other
+    // stream index reads as the reader's idle byte.  Ideally pinned memory.  The reader still
+    // supplies the geometry (channels, rates, length, bit order).  Call before the first getSamples().
+    bool setBulkSource(const dsf2flac_uint8* data, dsf2flac_int64 blockBytes, dsf2flac_int64 deliveredBytes,
+                       dsf2flac_int64 planarStride = 0);
 
 private:
     void buildTables(int msbFlag);
@@ -95,6 +103,9 @@ private:
     dsf2flac_uint64 blockSample0;        // samplesOut at frame 0
     dsf2flac_float64 blockScale, blockDither, blockClip;
     dsf2flac_uint32 readAhead;
+
+    const dsf2flac_uint8* bulk;          // bulk source (nullptr: drain the reader)
+    dsf2flac_int64 bulkBlock, bulkCount, bulkStride;
 };
 
 #endif // DSDDECIMATOR_H

@@ -8,7 +8,10 @@
 #include <string>
 #include <vector>
 
+#include "container_sample_reader.h"
+#include "dsd_container.h"
 #include "dsd_decimator.h"
+#include "dsdgpu.h"
 #include "memory_sample_reader.h"
 
 namespace {
@@ -92,6 +95,76 @@ int64_t dsdhost_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t 
         done += 1;
     }
     if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    return done;
+}
+
+// Header facts of a DSF / DSDIFF file as the reference's readers report them, plus what the bulk
+// path derives: info = {channels, sampling frequency, msbIsPlayedFirst, kind (1 DSF, 2 DSDIFF),
+// source_block_bytes}; *length_samples = getLength(); *delivered_bytes = stream bytes per channel
+// the reference reader hands out before idle bytes.  Needs no GPU.  Returns 1, or 0 + error text.
+int dsdhost_file_info(const char* path, int kind, int32_t* info, int64_t* length_samples, int64_t* delivered_bytes) {
+    DsdContainer c;
+    if (!dsd_container_load(path, kind, c)) { g_error = c.error; return 0; }
+    info[0] = (int32_t)c.channels; info[1] = (int32_t)c.samplingFreq; info[2] = c.msbIsPlayedFirst ? 1 : 0;
+    info[3] = (int32_t)c.kind; info[4] = (int32_t)c.blockBytes;
+    *length_samples = c.lengthSamples;
+    *delivered_bytes = c.deliveredBytes;
+    return 1;
+}
+
+// The stream bytes of channel `ch` the container path will feed the GPU, [0, delivered) -> planar
+// (for CPU-side checks of the container model).  Returns bytes written or -1.
+int64_t dsdhost_file_channel_bytes(const char* path, int kind, int ch, uint8_t* out, int64_t cap) {
+    DsdContainer c;
+    if (!dsd_container_load(path, kind, c)) { g_error = c.error; return -1; }
+    if (ch < 0 || ch >= (int)c.channels) return -1;
+    const int64_t n = c.deliveredBytes < cap ? c.deliveredBytes : cap, nch = c.channels, B = c.blockBytes;
+    for (int64_t k = 0; k < n; ++k)
+        out[k] = B == 1 ? c.payload[(size_t)(k * nch + ch)] : c.payload[(size_t)(((k / B) * nch + ch) * B + k % B)];
+    return n;
+}
+
+// One whole file, what `dsf2flac -i file` computes before FLAC (reference main.cpp:232-258 with
+// onefile, :169-191), with the file's sample bytes handed to the GPU in their own layout instead of
+// being stepped through a reader.  Returns frames written, -1 on error, -2 if `out` is too small.
+int64_t dsdhost_convert_file(const char* path, int kind, uint32_t out_fs, double scale, double dither, double clip,
+                             int lut_bits, uint32_t read_ahead, int32_t* out, int64_t out_cap_frames) {
+    DsdContainer c;
+    if (!dsd_container_load(path, kind, c)) { g_error = c.error; return -1; }
+    const bool pinned = !c.payload.empty() && dsdgpu_host_register(c.payload.data(), c.payload.size()) == DSDGPU_OK;
+    int64_t done = -1;
+    {
+        ContainerSampleReader rd(c);
+        DsdDecimator dec(&rd, out_fs);
+        bool ok = dec.isValid();
+        if (ok && lut_bits != 64) ok = dec.setLutPrecision(lut_bits);
+        if (ok) ok = dec.setBulkSource(c.payload.data(), c.blockBytes, c.deliveredBytes);
+        if (!ok) {
+            g_error = dec.getErrorMsg();
+        } else {
+            if (read_ahead) dec.setReadAheadFrames(read_ahead);
+            double startPos = dec.getFirstValidSample();
+            double endPos = dec.getLastValidSample();
+            if (startPos > dec.getLength() - 1) startPos = dec.getLength() - 1;
+            if (endPos > dec.getLength()) endPos = dec.getLength();
+            const int block = 1024;
+            const int nch = (int)c.channels;
+            while (dec.getPosition() < startPos) dec.step();
+            done = 0;
+            while (dec.getPosition() <= endPos - block) {
+                if (done + block > out_cap_frames) { done = -2; break; }
+                dec.getSamples(out + done * nch, (dsf2flac_uint32)(nch * block), scale, dither, clip);
+                done += block;
+            }
+            while (done >= 0 && dec.getPosition() <= endPos) {
+                if (done + 1 > out_cap_frames) { done = -2; break; }
+                dec.getSamples(out + done * nch, (dsf2flac_uint32)nch, scale, dither, clip);
+                done += 1;
+            }
+            if (!dec.isValid()) { g_error = dec.getErrorMsg(); done = -1; }
+        }
+    }
+    if (pinned) dsdgpu_host_unregister(c.payload.data());
     return done;
 }
 

@@ -102,6 +102,9 @@ unsigned long long dsdgpu_kernel_launches(const dsdgpu_ctx* ctx);
  * works too, pinned memory is what lets the copies overlap the kernel). */
 void* dsdgpu_host_alloc(size_t bytes);
 void dsdgpu_host_free(void* p);
+/* Page-lock memory the caller already owns (a file payload, an mmap) for the duration of a run. */
+int dsdgpu_host_register(void* p, size_t bytes);
+int dsdgpu_host_unregister(void* p);
 
 /*
  * Replaces: the loop body of getSamplesInternal (dsd_decimator.cpp:191-221) for a whole run of

@@ -1,13 +1,15 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into the product path.
 //
-// C-ABI wrapper around the UNMODIFIED reference decimator.  oracle/Makefile compiles
-// /root/reference/src/dsd_decimator.cpp (+ filters.cpp through its #include) and
-// dsd_sample_reader.cpp where they lie, against oracle/ref_shim, together with this file,
-// into oracle/_ref/libdsdref.so.  This file adds only (1) an in-memory DsdSampleReader whose
+// C-ABI wrapper around the UNMODIFIED reference decimator and container readers.  oracle/Makefile
+// compiles /root/reference/src/dsd_decimator.cpp (+ filters.cpp through its #include),
+// dsd_sample_reader.cpp, dsf_file_reader.cpp, dsdiff_file_reader.cpp, fstream_plus.cpp and
+// libdstdec/*.c where they lie, against oracle/ref_shim, together with this file, into
+// oracle/_ref/libdsdref.so.  This file adds only (1) an in-memory DsdSampleReader whose
 // step() follows dsf_file_reader.cpp:83-103 and (2) drivers shaped like main.cpp:169-191.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
 
 // The lookup table is a private member (dsd_decimator.h:139); the unit tests want to compare
@@ -15,6 +17,8 @@
 #define private public
 #include "dsd_decimator.h"
 #undef private
+#include "dsdiff_file_reader.h"
+#include "dsf_file_reader.h"
 
 namespace {
 
@@ -157,6 +161,88 @@ int64_t dsdref_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t l
         std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch);
         done += 1;
     }
+    return done;
+}
+
+// ---- file level: the reference's own container readers in front of its decimator ------------
+// kind 1 = .dsf (DsfFileReader, dsf_file_reader.cpp), 2 = .dff (DsdiffFileReader,
+// dsdiff_file_reader.cpp).  info[0..3] = channels, sampling frequency, msbIsPlayedFirst, valid;
+// *length = getLength() (DSD samples per channel).  Returns 1 if the reader accepted the file.
+// The readers are constructed in zero-filled memory: DsdSampleReader's constructor leaves posMarker
+// unset (dsd_sample_reader.cpp:40-44) and DsdiffFileReader::rewind() reads it before assigning it
+// (dsdiff_file_reader.cpp:152-154 -> readNextBlock :167), so on recycled heap memory the first
+// 1024-byte block can come out as idle bytes.  Zeroed storage is what a fresh process's first
+// allocations look like and gives the behaviour the code intends (posMarker = 0 there).
+static DsdSampleReader* open_reader(const char* path, int kind) {
+    if (kind == 1) return new (calloc(1, sizeof(DsfFileReader))) DsfFileReader((char*)path);
+    if (kind == 2) return new (calloc(1, sizeof(DsdiffFileReader))) DsdiffFileReader((char*)path);
+    return nullptr;
+}
+static void close_reader(DsdSampleReader* rd) {
+    if (!rd) return;
+    rd->~DsdSampleReader();
+    free(rd);
+}
+
+int dsdref_file_info(const char* path, int kind, int32_t* info, int64_t* length) {
+    DsdSampleReader* rd = open_reader(path, kind);
+    if (!rd) return 0;
+    const int ok = rd->isValid() ? 1 : 0;
+    if (ok) {
+        info[0] = (int32_t)rd->getNumChannels();
+        info[1] = (int32_t)rd->getSamplingFreq();
+        info[2] = rd->msbIsPlayedFirst() ? 1 : 0;
+        info[3] = 1;
+        *length = rd->getLength();
+    }
+    close_reader(rd);
+    return ok;
+}
+
+// What `dsf2flac -i file` computes before FLAC (main.cpp:232-258 with onefile, :169-191).
+// Returns frames written, -1 reader invalid, -3 decimator invalid, -2 out too small.
+// NOTE: dsf_file_reader.cpp:40 keeps `blockBufferAllocated` in a file-scope static that is never
+// reset, so a process can open ONE .dsf file; callers run each conversion in a fresh process and get
+// the reader's geometry from the same call (info[0..2] = channels, sampling frequency,
+// msbIsPlayedFirst; *length = getLength(); either may be NULL).
+int64_t dsdref_file_run_app(const char* path, int kind, uint32_t out_fs, double scale, double dither,
+                            double clip, int reseed, int32_t* out, int64_t out_cap_frames,
+                            int32_t* info, int64_t* length) {
+    DsdSampleReader* rd = open_reader(path, kind);
+    if (!rd || !rd->isValid()) { close_reader(rd); return -1; }
+    if (info) {
+        info[0] = (int32_t)rd->getNumChannels();
+        info[1] = (int32_t)rd->getSamplingFreq();
+        info[2] = rd->msbIsPlayedFirst() ? 1 : 0;
+    }
+    if (length) *length = rd->getLength();
+    int64_t done = 0;
+    {
+        const int nch = (int)rd->getNumChannels();
+        DsdDecimator dec(rd, out_fs);
+        if (!dec.isValid()) { close_reader(rd); return -3; }
+        if (reseed) srand(1);
+        double startPos = dec.getFirstValidSample();
+        double endPos = dec.getLastValidSample();
+        if (startPos > dec.getLength() - 1) startPos = dec.getLength() - 1;
+        if (endPos > dec.getLength()) endPos = dec.getLength();
+        const int block = 1024;
+        while (dec.getPosition() < startPos) dec.step();
+        std::vector<int32_t> buf((size_t)nch * block);
+        while (dec.getPosition() <= endPos - block) {
+            dec.getSamples(buf.data(), (dsf2flac_uint32)(nch * block), scale, dither, clip);
+            if (done + block > out_cap_frames) { done = -2; break; }
+            std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch * block);
+            done += block;
+        }
+        while (done >= 0 && dec.getPosition() <= endPos) {
+            dec.getSamples(buf.data(), (dsf2flac_uint32)nch, scale, dither, clip);
+            if (done + 1 > out_cap_frames) { done = -2; break; }
+            std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch);
+            done += 1;
+        }
+    }
+    close_reader(rd);
     return done;
 }
 

@@ -19,6 +19,7 @@ struct dsdgpu_ctx {
     unsigned long long launches = 0;
     long long chunk_frames = 1 << 20;
     long long dither_stride = 0;
+    long long source_block = 0;        // include/dsdgpu.h "source_block_bytes"
     char err[128] = "";
 };
 
@@ -51,11 +52,14 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx) { return ctx ? ctx->err : "
 int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     if (!strcmp(key, "chunk_frames")) ctx->chunk_frames = value;
     if (!strcmp(key, "dither_stride")) ctx->dither_stride = value;
+    if (!strcmp(key, "source_block_bytes")) ctx->source_block = value;
     return DSDGPU_OK;
 }
 unsigned long long dsdgpu_kernel_launches(const dsdgpu_ctx* ctx) { return ctx->launches; }
 void* dsdgpu_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void dsdgpu_host_free(void* p) { free(p); }
+int dsdgpu_host_register(void*, size_t) { return DSDGPU_OK; }
+int dsdgpu_host_unregister(void*) { return DSDGPU_OK; }
 
 int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first,
                          int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
@@ -70,7 +74,11 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
             double sum = 0.0;
             for (int t = 0; t < ctx->nlut; ++t) {
                 const int64_t o = p - t - in_first;
-                const unsigned b = (o >= 0 && o < in_count) ? in[(size_t)c * in_stride + (size_t)o] : fill;
+                const long long B = ctx->source_block;
+                const size_t at = B == 0 ? (size_t)c * in_stride + (size_t)o
+                                : B == 1 ? (size_t)o * ctx->nch + c
+                                         : (size_t)(((o / B) * ctx->nch + c) * B + o % B);
+                const unsigned b = (o >= 0 && o < in_count) ? in[at] : fill;
                 sum += ctx->lut[(size_t)t * 256 + b];
             }
             sum = sum * scale;

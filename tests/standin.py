@@ -18,3 +18,8 @@ def lib():
 
 def make_ctx(lut, nch, nstep, device=0, lut_precision=64):
     return capi.DsdGpu(lut, nch, nstep, device=device, lut_precision=lut_precision, lib=lib())
+
+
+def cpu_host_lib():
+    """The drop-in host library linked against the CPU stand-in (dsdhost_* drivers)."""
+    return capi.host_lib(CPU_HOST)
