@@ -319,15 +319,25 @@ def run_gpu_arm(args, wl):
     if rank == 0 and args.plugin_seconds > 0:
         host = capi.host_lib()
         pb = min(nbytes, int(dsd_fs // 8 * args.plugin_seconds))
-        cap = pb + 2048
-        out = np.empty((cap, nch), dtype=np.int32)
-        t0 = time.perf_counter()
-        n = host.dsdhost_run_app(pin_in.ptr, nch, nbytes, pb * 8, 0x69, 1, dsd_fs, out_fs, scale, amp, clip, args.lut, 0,
-                                 out.ctypes.data, cap)
-        dt = time.perf_counter() - t0
-        if n > 0:
-            plugin = {"value": pb * 8 * nch / dt / 1e6, "unit": "Mbit/s", "sample": f"first {args.plugin_seconds:g} s",
-                      "note": "DsdDecimator::getSamples in 1024-frame calls over a byte-at-a-time DsdSampleReader"}
+        cap = nframes + 2048
+        out = capi.PinnedBuffer((cap, nch), np.int32)
+        plugin = {}
+        # (a) as dsf2flac runs it today: a reader stepped one byte per channel at a time
+        # (b) the same class with the file's bytes handed over in bulk (DsdDecimator::setBulkSource)
+        for name, fn, count in (("stepped_reader", host.dsdhost_run_app, pb), ("bulk_source", host.dsdhost_run_app_bulk, nbytes)):
+            best = None
+            for _ in range(2):                              # the first call pays context creation
+                t0 = time.perf_counter()
+                n = fn(pin_in.ptr, nch, nbytes, count * 8, 0x69, 1, dsd_fs, out_fs, scale, amp, clip, args.lut, 0, out.ptr, cap)
+                dt = time.perf_counter() - t0
+                if n > 0 and (best is None or dt < best):
+                    best = dt
+            if best:
+                plugin[name] = {"value": count * 8 * nch / best / 1e6, "unit": "Mbit/s", "stream_seconds": count * 8 / dsd_fs,
+                                "wall_ms": best * 1e3}
+        plugin["note"] = ("drop-in DsdDecimator::getSamples in main.cpp's 1024-frame calls, decimator construction "
+                          "(tables + GPU context) included")
+        out.free()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

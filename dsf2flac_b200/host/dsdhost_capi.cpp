@@ -65,14 +65,20 @@ int dsdhost_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t leng
 // One whole track, --onefile bounds (reference main.cpp:249-258) and the loop of
 // main.cpp:169-191: creep with step(), blocks of 1024 frames, then single frames.
 // Returns frames written, -1 on error, -2 if `out` is too small.
-int64_t dsdhost_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
-                        uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, double scale,
-                        double dither, double clip, int lut_bits, uint32_t read_ahead, int32_t* out,
-                        int64_t out_cap_frames) {
+static int64_t run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                       uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, double scale,
+                       double dither, double clip, int lut_bits, uint32_t read_ahead, int32_t* out,
+                       int64_t out_cap_frames, bool bulk) {
     MemorySampleReader rd(planar, (uint32_t)nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
     DsdDecimator dec(&rd, out_fs);
     if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
     if (lut_bits != 64 && !dec.setLutPrecision(lut_bits)) { g_error = dec.getErrorMsg(); return -1; }
+    if (bulk) {
+        // the reader would deliver bytes 0 .. ceil(L/8) (as far as they exist), idle bytes afterwards
+        int64_t delivered = (length_samples + 7) / 8 + 1;
+        if (delivered > nbytes) delivered = nbytes;
+        if (!dec.setBulkSource(planar, 0, delivered, nbytes)) { g_error = dec.getErrorMsg(); return -1; }
+    }
     if (read_ahead) dec.setReadAheadFrames(read_ahead);
     double startPos = dec.getFirstValidSample();
     double endPos = dec.getLastValidSample();
@@ -96,6 +102,24 @@ int64_t dsdhost_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t 
     }
     if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
     return done;
+}
+
+int64_t dsdhost_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                        uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, double scale,
+                        double dither, double clip, int lut_bits, uint32_t read_ahead, int32_t* out,
+                        int64_t out_cap_frames) {
+    return run_app(planar, nch, nbytes, length_samples, idle, msb_flag, dsd_fs, out_fs, scale, dither, clip, lut_bits,
+                   read_ahead, out, out_cap_frames, false);
+}
+
+// The same loop with the bytes handed over as a bulk source (DsdDecimator::setBulkSource) instead
+// of being stepped out of the reader one byte per channel at a time.
+int64_t dsdhost_run_app_bulk(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                             uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, double scale,
+                             double dither, double clip, int lut_bits, uint32_t read_ahead, int32_t* out,
+                             int64_t out_cap_frames) {
+    return run_app(planar, nch, nbytes, length_samples, idle, msb_flag, dsd_fs, out_fs, scale, dither, clip, lut_bits,
+                   read_ahead, out, out_cap_frames, true);
 }
 
 // Header facts of a DSF / DSDIFF file as the reference's readers report them, plus what the bulk

@@ -51,3 +51,17 @@ def test_dropin_fp32_tables(oracle):
     want = oracle.run_app(data, 50000 * 8, 1, DSD64, 88200, scale, 0.0, clip)
     got = run_app(data, 50000 * 8, 1, 88200, scale, 0.0, clip, lut_bits=32)
     assert np.abs(got.astype(np.int64) - want).max() <= 1
+
+
+def test_dropin_bulk_source_equals_stepped_reader(oracle):
+    """DsdDecimator::setBulkSource: same PCM as draining the reader byte by byte (and as the
+    oracle), with dither, for a length that is not a multiple of anything convenient."""
+    host = capi.host_lib()
+    nbytes, L = 300_000, 300_000 * 8 - 13
+    data = seeded_bytes(2, nbytes, 99)
+    scale, amp, clip = filters.app_params(24, dither=True)
+    want = oracle.run_app(data, L, 1, DSD64, 88200, scale, amp, clip)
+    for fn in (host.dsdhost_run_app, host.dsdhost_run_app_bulk):
+        out = np.zeros((len(want) + 16, 2), dtype=np.int32)
+        n = fn(data.ctypes.data, 2, nbytes, L, 0x69, 1, DSD64, 88200, scale, amp, clip, 64, 50_000, out.ctypes.data, len(out))
+        assert n == len(want) and np.array_equal(out[:n], want)

@@ -83,3 +83,14 @@ def test_fp32_tables_within_one_lsb(host, oracle):
     want = oracle.run_app(data, 5000 * 8, 1, DSD64, 88200, scale, 0.0, clip)
     got = run_app(host, data, 5000 * 8, 1, 88200, scale, 0.0, clip, lut_bits=32)
     assert np.abs(got.astype(np.int64) - want).max() <= 1
+
+
+def test_bulk_source_equals_stepped_reader(host, oracle):
+    nbytes, L = 40_000, 40_000 * 8 - 13
+    data = seeded_bytes(3, nbytes, 5)
+    scale, amp, clip = filters.app_params(16, dither=True)
+    want = oracle.run_app(data, L, 0, DSD64, 176400, scale, amp, clip)
+    for fn in (host.dsdhost_run_app, host.dsdhost_run_app_bulk):
+        out = np.zeros((len(want) + 16, 3), dtype=np.int32)
+        n = fn(data.ctypes.data, 3, nbytes, L, 0x69, 0, DSD64, 176400, scale, amp, clip, 64, 4000, out.ctypes.data, len(out))
+        assert n == len(want) and np.array_equal(out[:n], want)
