@@ -51,6 +51,7 @@ struct DecimateArgs {
     const double* dither;    // (r1 - r2) per output sample, [frame*dither_stride + c], or nullptr
     long long dither_stride; // samples per frame of the whole stream (>= nch)
     double scale, dither_amp, clip;
+    double unit;             // 32-bit tables: value of one table unit (2^-qbits); 1.0 otherwise
     void* out;
     int out_kind;
 };
@@ -391,8 +392,8 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         ring_half_origin<G>(a.p0, a.in_first, 0, t0, a_tile);   // the same for every half of the launch
     }
     const int l = tid & 31, w = tid >> 5, h = l >> 4;
-    RingLane lane;
-    const uint32_t w0 = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lane, tid, a_tile));
+    RingLane<G> lane;
+    const uint32_t w0 = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lane, tid, a_tile, a.unit));
     uint32_t loff = 0;
 
     long long tile = blockIdx.x;     // grid <= ntiles
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
     RingEmitter<F64OUT, DITHER> emit(a, prev, h, out_aligned16);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) emit.quantise(k, lane.p[k]);
+    for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));
     emit.store();
 }
 
@@ -663,7 +664,8 @@ struct dsdgpu_ctx {
     long long chunk_frames = 1LL << 20;
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
-    unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only)
+    unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only): fp64 or 32-bit entries
+    double lut_unit = 1.0;                   // 32-bit tables: 2^-qbits
     uint32_t* d_rand_pow2 = nullptr;         // x^(2^b), b < 48
     uint32_t* d_rand_base = nullptr;         // seed words r[3..94]
     uint32_t* d_rand_lane = nullptr;         // x^(248*l), l < 32, stored [k][l]
@@ -681,6 +683,7 @@ namespace {
 using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x2 = RingGeom<16, 2>;
+using Ring16x2Q = RingGeom<16, 2, true>;
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -849,6 +852,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     a.p0 = p0; a.nframes = nframes; a.nch = ctx->nch; a.fill = fill;
     a.dither = nullptr; a.dither_stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
     a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
+    a.unit = ctx->lut_unit;
     a.out = d_out; a.out_kind = out_kind;
     if (dither_amp > 0.0) {
         const long long count = (nframes - 1) * a.dither_stride + ctx->nch;
@@ -866,7 +870,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     if (kernel == DSDGPU_KERNEL_RING) {
         if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs nlut=72, nstep=4 and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
-        return launch_ring<Ring16x2>(ctx, a, st);
+        return ctx->lut_precision == 32 ? launch_ring<Ring16x2Q>(ctx, a, st) : launch_ring<Ring16x2>(ctx, a, st);
     }
     if (kernel == DSDGPU_KERNEL_SKEW) {
         if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
@@ -918,9 +922,30 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int s = 0; s < DSDGPU_SLOTS; ++s) CREATE_TRY(cudaStreamCreateWithFlags(&ctx->slots[s].stream, cudaStreamNonBlocking));
 
-    // tables: fp32 variant = every entry rounded to fp32, then widened (accumulation stays fp64)
+    // Tables.  lut_precision 32 = 32-bit tables: every entry rounded to a multiple of 2^-qbits, qbits
+    // the largest value <= 30 for which no sum of nlut entries can leave int32 (30 for the reference's
+    // filters, whose largest possible |sum| is 1.33).  Sums of such entries are exact in fp64 too, so
+    // every kernel -- integer or fp64 accumulation -- returns the same bits for this variant.
     std::vector<double> tab((size_t)nlut * 256);
-    for (size_t i = 0; i < tab.size(); ++i) tab[i] = (lut_precision == 32) ? (double)(float)lut[i] : lut[i];
+    if (lut_precision == 32) {
+        double worst = 0.0;
+        for (int t = 0; t < nlut; ++t) {
+            double m = 0.0;
+            for (int e = 0; e < 256; ++e) m = std::fmax(m, std::fabs(lut[(size_t)t * 256 + e]));
+            worst += m;
+        }
+        int qbits = 30;
+        while (qbits > 0 && !(worst * std::ldexp(1.0, qbits) + nlut < 2147483647.0)) --qbits;
+        if (!(worst * std::ldexp(1.0, qbits) + nlut < 2147483647.0)) {
+            fail(nullptr, DSDGPU_ERR_ARG, "table entries too large for the 32-bit variant");
+            dsdgpu_destroy(ctx);
+            return DSDGPU_ERR_ARG;
+        }
+        ctx->lut_unit = std::ldexp(1.0, -qbits);
+        for (size_t i = 0; i < tab.size(); ++i) tab[i] = std::nearbyint(lut[i] / ctx->lut_unit) * ctx->lut_unit;
+    } else {
+        for (size_t i = 0; i < tab.size(); ++i) tab[i] = lut[i];
+    }
     CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_direct), tab.size() * sizeof(double)));
     CREATE_TRY(cudaMemcpy(ctx->d_lut_direct, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (nlut == 72 && nstep == 4) {
@@ -928,12 +953,17 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
         skew_build_lut_image<Skew512>(tab.data(), img.data());
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_skew), img.size()));
         CREATE_TRY(cudaMemcpy(ctx->d_lut_skew, img.data(), img.size(), cudaMemcpyHostToDevice));
-        // The ring kernel restarts an accumulator as fma(acc, 0.0, x): that is 0.0 + x bit for bit
-        // unless x is -0.0 (or anything is non-finite).  No real filter has such a table entry;
-        // a table that does simply keeps the older kernels.
+        // The fp64 ring kernel routes a value into one of two sums as fma(x, 0 or 1, acc): bit-exact
+        // unless x is -0.0 (or anything is non-finite).  No real filter has such a table entry; a
+        // table that does simply keeps the older kernels.  (Integer tables have no such case.)
         bool plain = true;
         for (double v : tab) plain = plain && std::isfinite(v) && !(v == 0.0 && std::signbit(v));
-        if (plain) {
+        if (lut_precision == 32) {
+            std::vector<unsigned char> rimg(Ring16x2Q::LUT_BYTES);
+            ring_build_lut_image<Ring16x2Q>(tab.data(), rimg.data(), ctx->lut_unit);
+            CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
+            CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
+        } else if (plain) {
             std::vector<unsigned char> rimg(Ring16x2::LUT_BYTES);
             ring_build_lut_image<Ring16x2>(tab.data(), rimg.data());
             CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));

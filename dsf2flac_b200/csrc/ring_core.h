@@ -44,16 +44,32 @@
 
 namespace dsdgpu {
 
-template <int NWARP_, int KR_>
+// Q32 = false: fp64 tables, the bit-exact path described above.
+// Q32 = true : 32-bit tables.  Entries are the same sums rounded to multiples of 2^-qbits (qbits = 30
+//              for the reference's filters) and stored as int32; a frame's sum is then an EXACT
+//              integer sum -- order independent, so it does not depend on how frames are cut into
+//              tiles or shards -- converted to fp64 once per frame.  |error| <= 72 * 2^-31 before
+//              scaling (3e-8 of full scale; BASELINE's fp32 variant allows 1e-6).  A 4-byte entry
+//              halves the shared-memory traffic; all 32 lanes of a warp form one skew group (one
+//              LDS.32 = one 128-byte wavefront), rows are 96 slots = 384 B with THREE extra
+//              copies of taps 64..71: a wrapped lane whose lower neighbour in its residue class
+//              (j - 8) has already restarted reads slot tap + 8*(j >> 3), which puts it on the
+//              bank nobody else can be on.
+template <int NWARP_, int KR_, bool Q32_ = false>
 struct RingGeom {
+    static constexpr bool Q32 = Q32_;
     static constexpr int NLUT = 72;                   // tables = steps per period
     static constexpr int NSTEP = 4;                   // bytes between successive frames
     static constexpr int KF = 4;                      // consecutive frames per lane
     static constexpr int KR = KR_;                    // rounds (periods) per tile
     static constexpr int NWARP = NWARP_;
     static constexpr int NTHR = 32 * NWARP;
-    static constexpr int ROW = 80;                    // doubles per table row
-    static constexpr int ROW_BYTES = ROW * 8;
+    static constexpr int ELEM = Q32 ? 4 : 8;          // bytes per table entry
+    static constexpr int SKEW_LANES = Q32 ? 32 : 16;  // lanes of one conflict-free load = skew values
+    static constexpr int EARLY_GROUPS = SKEW_LANES / 4;   // 4-step groups in which some lane is still wrapped
+    static constexpr int EARLY_STEPS = SKEW_LANES;
+    static constexpr int ROW = Q32 ? 96 : 80;         // slots per table row
+    static constexpr int ROW_BYTES = ROW * ELEM;      // 384 / 640: a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
     static constexpr int LUT_BYTES = GUARD_BYTES + 256 * ROW_BYTES;
     // a tile has two halves (lanes 0-15 / 16-31 of every warp), each with its own byte buffer
@@ -61,14 +77,14 @@ struct RingGeom {
     static constexpr int FR_PER_ROUND = KF * BLK_PER_ROUND;
     static constexpr int NTP = KR * FR_PER_ROUND;     // frames per half per tile
     static constexpr int HOP = NSTEP * FR_PER_ROUND;  // bytes between a lane's rounds
-    static constexpr int BACK = HOP + NLUT;           // this round's window -> previous round's tail
     static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
     static constexpr int HALF_BYTES = NSTEP * NTP + 256;
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
     static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
     static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
-    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == 0, "staging chunks / bank pattern");
-    static_assert(HOP % 16 == 0 && BACK % 4 == 0, "windows of successive rounds share their byte phase");
+    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == 0 && ROW_BYTES % 128 == 0, "staging chunks / bank pattern");
+    static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
+    static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
 };
 
 RING_HD uint32_t ring_funnel_r(uint32_t lo, uint32_t hi, uint32_t shift) {
@@ -105,6 +121,9 @@ RING_HD uint32_t ring_lds_u32(const unsigned char* smem, uint32_t off) {
 RING_HD double ring_lds_f64(const unsigned char* smem, uint32_t off) {
     return *reinterpret_cast<const double*>(smem + off);
 }
+RING_HD int32_t ring_lds_i32(const unsigned char* smem, uint32_t off) {
+    return *reinterpret_cast<const int32_t*>(smem + off);
+}
 RING_HD double ring_add(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(a, b);
@@ -135,53 +154,74 @@ struct RingNoEmit {
     RING_HD void store() {}
 };
 
-// Skew of lane l (0..31) of a warp.  Within each half-warp the 16 values are a permutation of
-// 0..15 (conflict-free table loads); across the warp the quarter (j >> 2) is arranged so that
-// the 32 window words of one LDS.32 -- lane stride 16 B plus j bytes -- fall in 32 distinct
-// banks when the tile is 16-byte aligned to the frame grid.
+// Skew of lane l (0..31) of a warp.
+// fp64 tables: within each half-warp the 16 values are a permutation of 0..15 (conflict-free
+// LDS.64); across the warp the quarter (j >> 2) is arranged so that the 32 window words of one
+// LDS.32 -- lane stride 16 B plus j bytes -- fall in 32 distinct banks when the frame grid is 4-byte
+// aligned to the tile.
+// 32-bit tables: the 32 values are a permutation of 0..31.  Window word of lane l = 4*l + (j >> 2),
+// now with j >> 2 up to 7, i.e. possibly one 4-word group further on: in every group of four lanes
+// {g, g+8, g+16, g+24} two stay (j >> 2 in {0,1} or {2,3}) and two move on (j >> 2 in {4,5} or {6,7}),
+// alternating with g, so that each group of four banks receives exactly the columns the
+// neighbouring group vacates.
+template <class G>
 RING_HD int ring_lane_skew(int l) {
+    if (G::Q32) {
+        const int g = l & 7, r = (l >> 3) & 3;
+        const int q = ((g & 1) ? 2 : 0) + (r & 1) + ((r >> 1) ? 4 : 0);
+        return (g >> 1) + 4 * q;
+    }
     const int h = (l >> 4) & 1, i = l & 15;
     const int q = 2 * (((i >> 2) & 1) ^ h) + ((i >> 3) & 1);
     return (i & 3) + 4 * q;
 }
 
+template <bool Q32> struct RingAcc { typedef double type; };
+template <> struct RingAcc<true> { typedef int32_t type; };
+
 // Per-lane state.  It lives across periods AND across tiles: the pipeline never drains between
-// tiles, a lane finishes the last frames of one tile during the first 15 steps of the next.
+// tiles, a lane finishes the last frames of one tile during the first steps of the next.
+template <class G>
 struct RingLane {
-    double n[4];                // sums of the frames started in the current period
-    double p[4];                // sums of the frames started in the previous period (finished by step 15)
+    typedef typename RingAcc<G::Q32>::type acc_t;
+    acc_t n[4];                 // sums of the frames started in the current period
+    acc_t p[4];                 // sums of the frames started in the previous period (final after EARLY_STEPS)
     uint32_t qn[3], qo[3];      // previous window words of the current / the previous frame set
     uint32_t ln, lo;            // last aligned word loaded from either window
     uint32_t wlast;             // smem offset of word L(0) of the previous period's window
     // constants of the lane
     int j;                      // skew
     uint32_t shift;             // 8 * byte phase of the windows
-    uint32_t lnew, lwrap;       // table offset at static step 0: current frames / wrapped frames
-    uint32_t sel[4];            // byte selectors mixing the two windows in groups 0..3
+    uint32_t lnew, lwrap, lalt; // table offset at static step 0: current frames / wrapped frames; step to the tail copy
+    uint32_t sel[G::EARLY_GROUPS];   // byte selectors mixing the two windows in the early groups
+    double unit;                // value of one unit of acc_t (1.0, or 2^-qbits for 32-bit tables)
+    RING_HD double value(int k) const { return (double)p[k] * unit; }   // exact: |p| < 2^31
 };
 
 // a0 = a_tile + 16*(16*warp + (lane & 15)) + j: offset inside the half's buffer of the byte the
 // lane's frame 0 reads at its tap 0.  Returns the offset (inside the half's buffer) of L(0), the
 // aligned word holding that byte's predecessor window, for round 0.
 template <class G>
-RING_HD int ring_lane_init(RingLane& r, int tid, int a_tile) {
+RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.0) {
     const int l = tid & 31, w = tid >> 5;
-    const int j = ring_lane_skew(l);
+    const int j = ring_lane_skew<G>(l);
     const int a0 = a_tile + 16 * (16 * w + (l & 15)) + j;
     const int phi = (a0 + 1) & 3;
     r.j = j;
+    r.unit = unit;
     r.shift = 8u * (uint32_t)phi;
-    r.lnew = (uint32_t)(G::GUARD_BYTES - 8 * j);
-    r.lwrap = (uint32_t)(G::GUARD_BYTES + 8 * (G::NLUT - j));
+    r.lnew = (uint32_t)(G::GUARD_BYTES - G::ELEM * j);
+    r.lwrap = (uint32_t)(G::GUARD_BYTES + G::ELEM * (G::NLUT - j));
+    r.lalt = (uint32_t)(G::ELEM * 8 * (j >> 3));
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < G::EARLY_GROUPS; ++g) {
         uint32_t v = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) v |= (uint32_t)((4 * g + u >= j) ? 3 - u : 7 - u) << (4 * (3 - u));
         r.sel[g] = v;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { r.n[k] = 0.0; r.p[k] = 0.0; }
+    for (int k = 0; k < 4; ++k) { r.n[k] = 0; r.p[k] = 0; }
     r.qo[0] = r.qo[1] = r.qo[2] = 0u;
     r.qn[0] = r.qn[1] = r.qn[2] = 0u;
     r.lo = r.ln = 0u;
@@ -192,12 +232,12 @@ RING_HD int ring_lane_init(RingLane& r, int tid, int a_tile) {
 // Steps 4*G0 .. 4*G1-1 of one period.  wnew / wold: smem byte offsets of word L(0) of this
 // period's window and of the previous period's window (whose groups 18.. continue here).
 template <class G, int G0, int G1, class Emit, class Trace>
-RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t wold, uint32_t& loff,
+RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t wold, uint32_t& loff,
                          int tid, int period, Emit& emit, const Trace& tr) {
 #pragma unroll
     for (int g = G0; g < G1; ++g) {
-        if (g >= 5 && g <= 8) emit.quantise(g - 5, r.p[g - 5]);
-        if (g == 9) emit.store();
+        if (g > G::EARLY_GROUPS && g <= G::EARLY_GROUPS + 4) emit.quantise(g - G::EARLY_GROUPS - 1, r.value(g - G::EARLY_GROUPS - 1));
+        if (g == G::EARLY_GROUPS + 5) emit.store();
         uint32_t x[4];
         {
             const uint32_t a = wnew - 4u * (uint32_t)g;
@@ -208,7 +248,7 @@ RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, 
             x[0] = v; x[1] = r.qn[0]; x[2] = r.qn[1]; x[3] = r.qn[2];
             r.qn[2] = r.qn[1]; r.qn[1] = r.qn[0]; r.qn[0] = v;
         }
-        if (g < 4) {
+        if (g < G::EARLY_GROUPS) {
             const uint32_t a = wold - 4u * (uint32_t)(18 + g);
             const uint32_t w = ring_lds_u32(smem, a);
             tr.word(tid, period, 2 * g + 1, a);
@@ -223,16 +263,14 @@ RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
-            double to_n = 1.0, to_p = 0.0;
-            if (s < 16) {
-                // wrapped lanes (s < j) still add to their previous frames; the multipliers route
-                // each table value into exactly one of the two sums without a select:
-                // fma(x, 1, acc) == acc + x and fma(x, 0, acc) == acc, bit for bit
-                if (s < 8 && r.j == s + 8) loff += 64u;         // taps 64..71 from the duplicate slots
-                const bool cur = (s >= r.j);
+            bool cur = true;
+            if (s < G::EARLY_STEPS) {
+                // wrapped lanes (s < j) still add to their previous frames; multipliers route each
+                // table value into exactly one of the two sums without a select: fma(x, 1, acc) is
+                // acc + x and fma(x, 0, acc) is acc, bit for bit (integer tables: x*1 + acc, x*0 + acc)
+                if (s + 8 < G::EARLY_STEPS && r.j == s + 8) loff += r.lalt;   // taps 64..71 from this lane's tail copy
+                cur = (s >= r.j);
                 if (r.j == s) loff = r.lnew;                     // tap 0 of the next frame set
-                to_n = cur ? 1.0 : 0.0;
-                to_p = cur ? 0.0 : 1.0;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -241,24 +279,34 @@ RING_HD void ring_groups(RingLane& r, const unsigned char* smem, uint32_t wnew, 
                 else if (u == 1) e = ring_byte<2>(x[k]);
                 else if (u == 2) e = ring_byte<1>(x[k]);
                 else e = ring_byte<0>(x[k]);
-                const uint32_t addr = e * (uint32_t)G::ROW_BYTES + loff + 8u * (uint32_t)s;
+                const uint32_t addr = e * (uint32_t)G::ROW_BYTES + loff + (uint32_t)(G::ELEM * s);
                 tr.lut(tid, period, s, k, addr);
-                const double v = ring_lds_f64(smem, addr);
-                if (s < 16) {
-                    r.n[k] = ring_fma(v, to_n, r.n[k]);
-                    r.p[k] = ring_fma(v, to_p, r.p[k]);
+                if constexpr (G::Q32) {
+                    const int32_t v = ring_lds_i32(smem, addr);
+                    if (s < G::EARLY_STEPS) {
+                        r.n[k] = v * (cur ? 1 : 0) + r.n[k];
+                        r.p[k] = v * (cur ? 0 : 1) + r.p[k];
+                    } else {
+                        r.n[k] += v;
+                    }
                 } else {
-                    r.n[k] = ring_add(r.n[k], v);
+                    const double v = ring_lds_f64(smem, addr);
+                    if (s < G::EARLY_STEPS) {
+                        r.n[k] = ring_fma(v, cur ? 1.0 : 0.0, r.n[k]);
+                        r.p[k] = ring_fma(v, cur ? 0.0 : 1.0, r.p[k]);
+                    } else {
+                        r.n[k] = ring_add(r.n[k], v);
+                    }
                 }
             }
         }
     }
 }
 
-// First 16 steps of a period whose window word L(0) sits at smem offset wnew.  On return r.p[k]
-// holds the finished sums of the frames the lane started in the previous period.
+// The first EARLY_STEPS steps of a period whose window word L(0) sits at smem offset wnew.  On
+// return r.p[k] holds the finished sums of the frames the lane started in the previous period.
 template <class G, class Trace>
-RING_HD void ring_head(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
+RING_HD void ring_head(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        const Trace& tr) {
     // the three words ahead of group 0 (frames 1..3 start 4, 8, 12 bytes further on)
     const uint32_t l4 = ring_lds_u32(smem, wnew + 16u), l3 = ring_lds_u32(smem, wnew + 12u);
@@ -271,17 +319,17 @@ RING_HD void ring_head(RingLane& r, const unsigned char* smem, uint32_t wnew, ui
     r.ln = l1;
     loff = r.lwrap;
     RingNoEmit none;
-    ring_groups<G, 0, 4>(r, smem, wnew, r.wlast, loff, tid, period, none, tr);
+    ring_groups<G, 0, G::EARLY_GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, none, tr);
 }
 
-// Steps 16..71 of the period (with the previous period's sums handed to `emit` on the way), then
-// the hand-over to the next one.
+// The remaining steps of the period (with the previous period's sums handed to `emit` on the
+// way), then the hand-over to the next one.
 template <class G, class Emit, class Trace>
-RING_HD void ring_tail(RingLane& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
+RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        Emit& emit, const Trace& tr) {
-    ring_groups<G, 4, 18>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
+    ring_groups<G, G::EARLY_GROUPS, 18>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = 0.0; }
+    for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = 0; }
     r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];   // this window's last words = next period's history
     r.lo = r.ln;
     r.wlast = wnew;
@@ -331,15 +379,20 @@ RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
 }
 
 // Host side of the layout: writes the shared-memory image of the tables.
-//   lut   [72][256] doubles as the reference builds them (dsd_decimator.cpp:117-151)
+//   lut   [72][256] doubles as the reference builds them (dsd_decimator.cpp:117-151); for 32-bit
+//         tables every entry must already be a multiple of `unit` = 2^-qbits with |entry| / unit < 2^31
 template <class G>
-inline void ring_build_lut_image(const double* lut, unsigned char* image) {
-    double* d = reinterpret_cast<double*>(image);
-    for (int i = 0; i < G::LUT_BYTES / 8; ++i) d[i] = 0.0;
-    double* rows = reinterpret_cast<double*>(image + G::GUARD_BYTES);
+inline void ring_build_lut_image(const double* lut, unsigned char* image, double unit = 1.0) {
+    for (int i = 0; i < G::LUT_BYTES; ++i) image[i] = 0;
+    auto put = [&](int e, int slot, double v) {
+        unsigned char* at = image + G::GUARD_BYTES + e * G::ROW_BYTES + slot * G::ELEM;
+        if (G::Q32) *reinterpret_cast<int32_t*>(at) = (int32_t)(v / unit);
+        else *reinterpret_cast<double*>(at) = v;
+    };
     for (int e = 0; e < 256; ++e) {
-        for (int t = 0; t < G::NLUT; ++t) rows[e * G::ROW + t] = lut[t * 256 + e];
-        for (int m = 0; m < 8; ++m) rows[e * G::ROW + G::NLUT + m] = lut[(64 + m) * 256 + e];
+        for (int t = 0; t < G::NLUT; ++t) put(e, t, lut[t * 256 + e]);
+        for (int copy = 1; G::NLUT + 8 * copy <= G::ROW; ++copy)      // tail copies: slot = tap + 8*copy
+            for (int m = 0; m < 8; ++m) put(e, 64 + m + 8 * copy, lut[(64 + m) * 256 + e]);
     }
 }
 

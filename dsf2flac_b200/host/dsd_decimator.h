@@ -49,7 +49,8 @@ public:
     // --- additions (not in the reference) ---------------------------------------------------
     // Frames decimated per GPU round trip; larger = fewer, bigger transfers. Default 1<<20.
     void setReadAheadFrames(dsf2flac_uint32 frames);
-    // 64 (default, bit-exact) or 32 (fp32 tables, fp64 accumulate). Takes effect immediately.
+    // 64 (default, bit-exact) or 32 (32-bit fixed-point tables, exact integer sums: within +-1 LSB at
+    // 24 bit, about twice as fast). Takes effect immediately.
     bool setLutPrecision(int bits);
     // Bulk source: the stream bytes of all channels in the container's own layout, so that nothing
     // is pulled through reader->step() any more.  `data` holds stream bytes 0 ..

@@ -67,8 +67,13 @@ enum {
  *   nch           channels (>=1)
  *   nlut, nstep   nLookupTable and nStep of the reference (72/4, 30/2, 12/1; any nlut<=96 works)
  *   lut           [nlut][256] doubles, row t = table t
- *   lut_precision 64: tables kept in fp64 (bit-exact path); 32: tables rounded to fp32 and
- *                 accumulated in fp64 (within +-1 LSB at 24 bit)
+ *   lut_precision 64: tables kept in fp64 (bit-exact path).
+ *                 32: 32-bit tables -- every entry rounded to a multiple of 2^-30 (fixed point; a
+ *                 smaller exponent only if the table's entries could overflow int32 when summed),
+ *                 summed exactly and converted once per sample.  Error <= nlut * 2^-31 before
+ *                 scaling (3e-8 of full scale, within +-1 LSB at 24 bit); the sums are order
+ *                 independent, so every kernel and every sharding returns the same bits; half the
+ *                 shared-memory traffic of the fp64 tables
  */
 int dsdgpu_create(dsdgpu_ctx** ctx, int device, int nch, int nlut, int nstep, const double* lut,
                   int lut_precision);

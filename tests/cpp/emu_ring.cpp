@@ -15,7 +15,8 @@
 // Prints one JSON line; exit code 0 iff all sums match, coverage is exact and every table load
 // is conflict free.
 //
-// usage: emu_ring <nwarp:16|8> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed> <grid>
+// usage: emu_ring <nwarp:16|8, or 32 = 16 warps with 32-bit tables> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed> <grid>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,13 +30,14 @@ using namespace dsdgpu;
 struct Access { int tid, period, tag, k; uint32_t addr; };
 
 static size_t g_smem_size = 0;
+static int g_elem = 8;
 static long long g_oob = 0;
 
 struct Recorder {
     std::vector<Access>* lut_log;
     std::vector<Access>* word_log;
     void lut(int tid, int period, int s, int k, uint32_t a) const {
-        if ((size_t)a + 8 > g_smem_size || (a & 7)) ++g_oob;
+        if ((size_t)a + g_elem > g_smem_size || (a & (g_elem - 1))) ++g_oob;
         if (lut_log) lut_log->push_back({tid, period, s, k, a});
     }
     void word(int tid, int period, int tag, uint32_t a) const {
@@ -63,7 +65,13 @@ template <class G>
 static int run(long long nframes, int nch, long long p0, long long in_first, long long in_count, unsigned seed, int grid) {
     srand(seed);
     std::vector<double> lut((size_t)G::NLUT * 256);
-    for (auto& v : lut) v = (rand() / (double)RAND_MAX - 0.5) * 0.35;
+    g_elem = G::ELEM;
+    // random tables reach |sum| ~ 12, the reference's stay below 1.33: 2^-27 here, 2^-30 in the product
+    const double unit = G::Q32 ? 1.0 / (double)(1 << 27) : 1.0;
+    for (auto& v : lut) {
+        v = (rand() / (double)RAND_MAX - 0.5) * 0.35;
+        if (G::Q32) v = std::nearbyint(v / unit) * unit;         // 32-bit tables: multiples of 2^-30
+    }
     std::vector<std::vector<unsigned char>> src(nch, std::vector<unsigned char>((size_t)(in_count > 0 ? in_count : 1)));
     for (auto& ch : src)
         for (auto& b : ch) b = (unsigned char)(rand() & 0xff);
@@ -118,15 +126,15 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
 
     // one CTA after the other, each walking its tiles exactly like decimate_ring_kernel
     for (int cta = 0; cta < grid && cta < ntiles; ++cta) {
-        ring_build_lut_image<G>(lut.data(), smem.data());
+        ring_build_lut_image<G>(lut.data(), smem.data(), unit);
         for (size_t k = G::LUT_BYTES; k < smem.size(); ++k) smem[k] = (unsigned char)(rand() & 0xff);
         g_smem_size = (size_t)G::LUT_BYTES + G::NBUF * G::TILE_BYTES;   // the barriers behind the tiles are never data
-        std::vector<RingLane> lanes(G::NTHR);
+        std::vector<RingLane<G>> lanes(G::NTHR);
         std::vector<uint32_t> w0(G::NTHR), loff(G::NTHR, 0);
         std::vector<Dest> prev(G::NTHR);
         for (int tid = 0; tid < G::NTHR; ++tid) {
             const int h = (tid & 31) >> 4;
-            w0[tid] = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lanes[tid], tid, a_tile));
+            w0[tid] = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lanes[tid], tid, a_tile, unit));
         }
         bool have_prev = false;
         long long tile = cta;
@@ -159,8 +167,8 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                 have_prev = true;
                 if (trace) {
                     std::map<long long, std::vector<uint32_t>> groups;
-                    for (auto& a : lut_log) groups[((((long long)(a.tid / 16)) * 128 + a.tag) * 4 + a.k)].push_back(a.addr);
-                    for (auto& kv : groups) { ++lut_instr; lut_wavefronts += wavefronts(kv.second, 8); }
+                    for (auto& a : lut_log) groups[((((long long)(a.tid / G::SKEW_LANES)) * 128 + a.tag) * 4 + a.k)].push_back(a.addr);
+                    for (auto& kv : groups) { ++lut_instr; lut_wavefronts += wavefronts(kv.second, G::ELEM); }
                     std::map<long long, std::vector<uint32_t>> wg;
                     for (auto& a : word_log) wg[((long long)(a.tid / 32)) * 128 + a.tag].push_back(a.addr);
                     for (auto& kv : wg) { ++word_instr; word_wavefronts += wavefronts(kv.second, 4); }
@@ -172,16 +180,17 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         if (have_prev)
             for (int tid = 0; tid < G::NTHR; ++tid) {
                 ring_head<G>(lanes[tid], smem.data(), lanes[tid].wlast, loff[tid], tid, period, Recorder{nullptr, nullptr});
-                check(prev[tid], lanes[tid].p, tid);
+                const double last[4] = {lanes[tid].value(0), lanes[tid].value(1), lanes[tid].value(2), lanes[tid].value(3)};
+                check(prev[tid], last, tid);
             }
     }
     long long missing = 0;
     for (auto& ch : seen)
         for (auto v : ch) missing += (v == 0);
-    printf("{\"nwarp\": %d, \"kr\": %d, \"frames\": %lld, \"nch\": %d, \"tiles\": %lld, \"grid\": %d, \"checked\": %lld, \"mismatches\": %lld, "
+    printf("{\"nwarp\": %d, \"q32\": %d, \"kr\": %d, \"frames\": %lld, \"nch\": %d, \"tiles\": %lld, \"grid\": %d, \"checked\": %lld, \"mismatches\": %lld, "
            "\"missing\": %lld, \"duplicates\": %lld, \"oob\": %lld, \"lut_halfwarp_loads\": %lld, \"lut_wavefronts\": %lld, "
            "\"word_loads\": %lld, \"word_wavefronts\": %lld}\n",
-           G::NWARP, G::KR, nframes, nch, ntiles, grid, checked, mismatches, missing, dup, g_oob, lut_instr, lut_wavefronts,
+           G::NWARP, (int)G::Q32, G::KR, nframes, nch, ntiles, grid, checked, mismatches, missing, dup, g_oob, lut_instr, lut_wavefronts,
            word_instr, word_wavefronts);
     if (missing || dup || checked != nframes * nch) return 3;
     if (mismatches) return 1;
@@ -203,6 +212,8 @@ int main(int argc, char** argv) {
     if (nwarp == 16 && kr == 2) return run<RingGeom<16, 2>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 16 && kr == 1) return run<RingGeom<16, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 8 && kr == 6) return run<RingGeom<8, 6>>(nframes, nch, p0, in_first, in_count, seed, grid);
+    if (nwarp == 32 && kr == 2) return run<RingGeom<16, 2, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "32": 32-bit tables
+    if (nwarp == 32 && kr == 3) return run<RingGeom<16, 3, true>>(nframes, nch, p0, in_first, in_count, seed, grid);
     fprintf(stderr, "unsupported geometry\n");
     return 64;
 }

@@ -43,7 +43,10 @@ int dsdgpu_create(dsdgpu_ctx** ctx, int, int nch, int nlut, int nstep, const dou
     dsdgpu_ctx* c = new dsdgpu_ctx();
     c->nch = nch; c->nlut = nlut; c->nstep = nstep;
     c->lut.assign(lut, lut + (size_t)nlut * 256);
-    if (lut_precision == 32) for (auto& v : c->lut) v = (double)(float)v;
+    if (lut_precision == 32) {   // 32-bit tables: multiples of 2^-30 (include/dsdgpu.h; the reference's filters need no smaller exponent)
+        const double unit = std::ldexp(1.0, -30);
+        for (auto& v : c->lut) v = std::nearbyint(v / unit) * unit;
+    }
     *ctx = c;
     return DSDGPU_OK;
 }

@@ -289,3 +289,34 @@ def test_container_layouts_device_pointers(oracle):
     with pytest.raises(capi.DsdGpuError):
         g.set_option("source_block_bytes", 48)
     g.close()
+
+
+def test_32bit_tables_same_bits_from_every_kernel_and_sharding(oracle):
+    """lut_precision=32: fixed-point entries summed exactly -- the integer ring kernel, the fp64
+    skew and direct kernels and an 8-way sharded run all return the same bits, and those stay
+    within BASELINE's tolerance of the fp64 reference (checked tighter: 1e-7 relative)."""
+    fir = filters.FILTERS[32]
+    nbytes = 400_000
+    data = seeded_bytes(2, nbytes, 5)
+    n = filters.app_frames(nbytes * 8, fir)
+    scale, amp, clip = filters.app_params(24, dither=True)
+    outs = {}
+    for name in ("ring", "skew", "direct"):
+        g = capi.DsdGpu(filters.build_lut(fir, 1), 2, fir.nstep, lut_precision=32)
+        g.set_option("kernel", KERNELS[name])
+        outs[name] = g.decimate_host(data, fir.nlut, n, scale, amp, clip)
+        if name == "ring":
+            f64 = g.decimate_host(data, fir.nlut, n, 1.0, out_kind=capi.OUT_FLOAT64)
+        g.close()
+    assert np.array_equal(outs["ring"], outs["direct"]) and np.array_equal(outs["skew"], outs["direct"])
+    job = batch.Job(data, DSD64, 88200, msb_flag=True, bits=24, dither=True, lut_precision=32)
+    runner = batch.BatchRunner()
+    parts = []
+    for r in range(8):
+        parts += runner.run([job], r, 8)
+    assert np.array_equal(batch.stitch([job], parts)[0], outs["ring"])
+    runner.close()
+    want_i = oracle.run_app(data, nbytes * 8, 1, DSD64, 88200, scale, amp, clip)
+    assert np.abs(outs["ring"].astype(np.int64) - want_i).max() <= 1
+    want_f = oracle.run_raw(data, nbytes * 8, 1, DSD64, 88200, fir.nlut + 1, n, 1.0, want="f64")
+    assert np.abs(f64 - want_f).max() <= 1e-7 * np.abs(want_f).max()
