@@ -77,3 +77,49 @@ def test_config2_full_properties(oracle):
     # the signal is what went in: 1 kHz / 1.5 kHz sines at 0.5 * 4 dB
     x = outs["skew"][:176400].astype(np.float64) / 2 ** 23
     assert abs(np.abs(x).max() - 0.5 * 10 ** 0.2) < 0.01
+
+
+def test_config4_size_device_resident_periodicity(oracle):
+    """BASELINE config 4's size: DSD512 stereo, 600 s = 1 693 440 000 bytes per channel, divided
+    by 32 (423 359 983 frames x 2 channels, 3.4 GB in and 3.4 GB out, device resident).  The
+    stream is one second of modulator output tiled 600 times, so -- the filter being time
+    invariant -- frame f + k * (frames per second) must equal frame f bit for bit wherever the
+    72-byte window lies inside the data; the first second is checked against the oracle.  This
+    walks every index, offset and tile counter past 2^31 / 2^32."""
+    import torch
+    fs = 8 * DSD64
+    sec = fs // 8                                            # 2 822 400 bytes per channel per second
+    seconds = 600
+    nbytes = sec * seconds
+    fir = filters.pick(fs, fs // 32)
+    n = filters.app_frames(nbytes * 8, fir)
+    assert n == 423359983                                    # SURVEY.md 8a
+    one = sdm_stream(2, sec, fs)
+    scale, amp, clip = filters.app_params(24, dither=False)
+    front = 3                                                # frame grid 4-byte aligned to the buffer
+    stride = (nbytes + front + 255) // 256 * 256
+    d_in = torch.full((2, stride), 0x69, dtype=torch.uint8, device="cuda")
+    d_in[:, front:front + nbytes] = torch.from_numpy(one).cuda().repeat(1, seconds)
+    d_out = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    with capi.DsdGpu(filters.build_lut(fir, 1), 2, fir.nstep) as g:
+        g.decimate_device(d_in, stride, -front, nbytes + front, 0x69, fir.nlut, n, scale, amp, clip, 0, capi.OUT_INT32, d_out)
+        torch.cuda.synchronize()
+        fps = sec // fir.nstep                               # frames per tiled second
+        first = d_out[:fps].clone()
+        # the first second against the oracle (its own first frames see the start of the stream)
+        want = oracle.run_raw(np.ascontiguousarray(np.tile(one, (1, 2))[:, :sec + 400]), 1 << 40, 1, fs, fs // 32,
+                              fir.nlut + 1, fps, scale, amp, clip)
+        assert np.array_equal(first.cpu().numpy(), want)
+        # every later second repeats second 1 (second 0 starts with frames whose window is not periodic yet)
+        base = d_out[fps:2 * fps]
+        for k in (2, 77, 300, 598):
+            assert torch.equal(d_out[k * fps:(k + 1) * fps], base), k
+        tail = d_out[599 * fps:n]
+        assert torch.equal(tail[:len(tail) - 32], base[:len(tail) - 32])
+        # and the direct kernel agrees on the last 100 000 frames (stream end, past 2^32 bytes of output)
+        g.set_option("kernel", capi.KERNEL_DIRECT)
+        cnt = 100_000
+        d_chk = torch.empty((cnt, 2), dtype=torch.int32, device="cuda")
+        g.decimate_device(d_in, stride, -front, nbytes + front, 0x69, fir.nlut + (n - cnt) * fir.nstep, cnt, scale, amp, clip,
+                          0, capi.OUT_INT32, d_chk)
+        assert torch.equal(d_chk, d_out[n - cnt:])
