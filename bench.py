@@ -36,6 +36,20 @@ WORKLOADS = {
     "c1": (DSD64, 88200, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/88.2 kHz (BASELINE configs[0])"),
     "c2": (2 * DSD64, 176400, 2, 60, 24, "DSD128 stereo 60 s -> 24-bit/176.4 kHz, fp64 LUT (BASELINE configs[1])"),
 }
+# Sharded (strong-scaling) workloads, BASELINE configs[2..4]: (description, [(dsd_fs, out_fs, nch, seconds)...], lut, dither)
+def sharded_workloads(nfiles=256):
+    rng = np.random.default_rng(42)
+    c5 = [((DSD64, 88200) if k % 2 == 0 else (2 * DSD64, 176400)) + (2, int(rng.integers(30, 91))) for k in range(nfiles)]
+    return {
+        "c3": ("DSD256 5.1 60 s -> 24-bit/352.8 kHz, sharded by channel and time (BASELINE configs[2])",
+               [(4 * DSD64, 352800, 6, 60)], 64, 0),
+        "c4": ("DSD512 stereo 600 s, divide-by-32, time segments with a 71-byte halo (BASELINE configs[3]; the "
+               "reference has no divide-by-64 filter for 352.8 kHz)", [(8 * DSD64, 705600, 2, 600)], 64, 0),
+        "c5": (f"{nfiles} files, DSD64->88.2k / DSD128->176.4k alternating, 30-90 s, TPDF dither on, 32-bit tables "
+               "(BASELINE configs[4])", c5, 32, 1),
+    }
+
+
 SMEM_BYTES_PER_CLK_PER_SM = 128
 L2_BYTES = 126 * 1024 * 1024
 
@@ -402,24 +416,155 @@ def run_gpu_arm(args, wl):
         dist.destroy_process_group()
 
 
+def run_sharded_arm(args, spec):
+    """Strong scaling: one fixed job (a long stream, a multi-channel stream or a batch of files) cut
+    by dsdgpu_plan_shards into equal-cost shards, one process per GPU, no data-path collective.
+    value = device-resident throughput of the whole job; e2e = the same with pinned host buffers."""
+    import torch
+    import torch.distributed as dist
+    from dsf2flac_b200 import batch, capi, filters
+
+    desc, files, lut_bits, dither = spec
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    firs = [filters.pick(f[0], f[1]) for f in files]
+    frames = [filters.app_frames(f[0] * f[3], fir) for f, fir in zip(files, firs)]
+    shards = capi.plan_shards(frames, [f[2] for f in files], [fir.nlut for fir in firs], rank, world, 1024)
+    base = {}                                              # one second of modulator output per (rate, channel)
+
+    def second(fs, c):
+        if (fs, c) not in base:
+            base[(fs, c)] = synth_stream(fs, c + 1, 1)[c]
+        return base[(fs, c)]
+
+    runner = batch.BatchRunner(device=local)
+    work, total_bits = [], sum(f[0] * f[2] * f[3] for f in files)
+    for (j, c0, k, f0, nf) in shards:
+        fs, out_fs, nch, seconds = files[j]
+        fir = firs[j]
+        sec = fs // 8
+        lo = max(0, fir.nlut + f0 * fir.nstep - (fir.nlut - 1))
+        hi = min(sec * seconds, fir.nlut + (f0 + nf - 1) * fir.nstep + 1)
+        lo -= (lo - fir.nlut - f0 * fir.nstep - 1) % 16      # frame grid 16-byte aligned to the window
+        lo = max(lo, 0)
+        pin = capi.PinnedBuffer((k, hi - lo), np.uint8)
+        for c in range(k):                                   # the window [lo, hi) of the one-second pattern, tiled
+            one, phase = second(fs, c0 + c), lo % sec
+            pin.array[c] = np.tile(one, (hi - lo + phase) // sec + 2)[phase:phase + hi - lo]
+        job = batch.Job(pin.array, fs, out_fs, msb_flag=True, length_samples=fs * seconds, bits=24, dither=bool(dither),
+                        lut_precision=lut_bits, first_byte=lo)
+        job_nch = nch
+        out = capi.PinnedBuffer((nf, k), np.int32)
+        ctx = runner.ctx_for(job, k)
+        d_in = torch.from_numpy(pin.array).cuda()
+        d_out = torch.empty((nf, k), dtype=torch.int32, device="cuda")
+        work.append((job, (j, c0, k, f0, nf), pin, out, ctx, d_in, d_out, job_nch))
+    scale_of = lambda job: filters.app_params(job.bits, job.scale_db, job.dither)
+    stream = torch.cuda.Stream()
+
+    def device_step():
+        for job, (j, c0, k, f0, nf), pin, out, ctx, d_in, d_out, job_nch in work:
+            ctx.set_option("dither_stride", job_nch)
+            scale, amp, clip = scale_of(job)
+            ctx.decimate_device(d_in, d_in.shape[1], job.first_byte, job.in_count, job.idle, job.fir.nlut + f0 * job.fir.nstep,
+                                nf, scale, amp, clip, f0 * job_nch + c0, capi.OUT_INT32, d_out, stream=stream.cuda_stream)
+
+    def host_step():
+        for job, shard, pin, out, ctx, d_in, d_out, job_nch in work:
+            j, c0, k, f0, nf = shard
+            ctx.set_option("dither_stride", job_nch)
+            scale, amp, clip = scale_of(job)
+            ctx.decimate_host_raw(pin.ptr, pin.array.shape[1], job.first_byte, job.in_count, job.idle,
+                                  job.fir.nlut + f0 * job.fir.nstep, nf, scale, amp, clip, f0 * job_nch + c0, capi.OUT_INT32, out.ptr)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        device_step()
+    stream.synchronize()
+    barrier()
+    launches0 = runner.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    e1.record(stream)
+    stream.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = runner.launches - launches0
+    for _ in range(args.warmup):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop(0.0, time.perf_counter()) if sampler else None
+    h2d = sum(w[2].array.nbytes for w in work)
+    d2h = sum(w[3].array.nbytes for w in work)
+    if rank == 0:
+        value = total_bits * args.steps / (dev_ms * 1e-3) / 1e6
+        e2e_value = total_bits * args.steps / e2e_s / 1e6
+        audio_s = sum(f[3] for f in files)
+        print(json.dumps({
+            "metric": "dsd_mbit_per_s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if lut_bits == 64 else "i32", "data": "synthetic",
+            "per_gpu_mbit_per_s": value / world, "x_realtime": audio_s / (dev_ms * 1e-3 / args.steps),
+            "config": {"workload": desc, "files": len(files), "dither": bool(dither), "lut": f"{lut_bits}-bit",
+                       "shards_rank0": len(work), "l2": "per-step working set > L2" if h2d + d2h > L2_BYTES else "working set may fit L2",
+                       "parallelism": f"{world} ranks, dsdgpu_plan_shards (file / channel / time segment + halo), no collective"},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / args.steps * 1e3, "x_realtime": audio_s / (e2e_s / args.steps),
+                    "api": "dsdgpu_decimate_host per shard (pinned host buffers)", "note": "bytes are rank 0's"},
+            "gpu_launches": launches, "clocks": clocks,
+        }), flush=True)
+    runner.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c5"])
     ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
     ap.add_argument("--dither", type=int, default=0)
     ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring"])
     ap.add_argument("--align", type=int, default=1, help="0: device buffer starts at stream byte 0 (frame grid off by one byte)")
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--files", type=int, default=256, help="files in the c5 batch (about 120 MB of pinned host memory each)")
     ap.add_argument("--slots", type=int, default=0, help="pipelined slots of the host entry point (1..4)")
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per pipelined host chunk")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="length of the CPU-baseline sample (stream seconds)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload in ("c3", "c4", "c5"):
+        if args.impl == "reference":
+            raise SystemExit("the reference arm runs the unsharded workloads (c1, c2)")
+        return run_sharded_arm(args, sharded_workloads(args.files)[args.workload])
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)

@@ -31,11 +31,12 @@ class Job:
     scale_db: float = 4.0
     lut_precision: int = 64
     idle: int = 0x69
+    first_byte: int = 0           # stream index of planar[:, 0] when only a window of the stream is held
     fir: object = field(init=False)
 
     def __post_init__(self):
         if self.length_samples < 0:
-            self.length_samples = 8 * self.planar.shape[1]
+            self.length_samples = 8 * (self.first_byte + self.planar.shape[1])
         self.fir = filters.pick(self.dsd_fs, self.out_fs)
         if self.fir is None:
             raise ValueError("Sorry, incompatible sample rate combination")
@@ -52,7 +53,7 @@ class Job:
     def in_count(self):
         # the reader still delivers the byte at index ceil(L/8): availability is tested before
         # its marker moves (dsf_file_reader.cpp:87,101); clipped to what the buffer holds
-        return min(self.planar.shape[1], -(-self.length_samples // 8) + 1)
+        return max(0, min(self.first_byte + self.planar.shape[1], -(-self.length_samples // 8) + 1) - self.first_byte)
 
 
 def plan(jobs, rank, world, align_frames=1024):
@@ -85,7 +86,7 @@ class BatchRunner:
         if out is None:
             out = np.empty((nf, k), dtype=np.int32)
         nbytes = job.planar.shape[1]
-        ctx.decimate_host_raw(job.planar.ctypes.data + c0 * nbytes, nbytes, 0, job.in_count, job.idle,
+        ctx.decimate_host_raw(job.planar.ctypes.data + c0 * nbytes, nbytes, job.first_byte, job.in_count, job.idle,
                               job.fir.nlut + f0 * job.fir.nstep, nf, scale, amp, clip, f0 * job.nch + c0,
                               capi.OUT_INT32, out.ctypes.data)
         return out
