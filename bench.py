@@ -35,6 +35,9 @@ WORKLOADS = {
     # name: (dsd_fs, out_fs, nch, seconds, bits, description)
     "c1": (DSD64, 88200, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/88.2 kHz (BASELINE configs[0])"),
     "c2": (2 * DSD64, 176400, 2, 60, 24, "DSD128 stereo 60 s -> 24-bit/176.4 kHz, fp64 LUT (BASELINE configs[1])"),
+    # the other two filters of the reference (dsd_decimator.cpp:57-65): same input, higher output rates
+    "d16": (DSD64, 176400, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/176.4 kHz (divide-by-16 filter, 30 tables)"),
+    "d8": (DSD64, 352800, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/352.8 kHz (divide-by-8 filter, 12 tables)"),
 }
 # Sharded (strong-scaling) workloads, BASELINE configs[2..4]: (description, [(dsd_fs, out_fs, nch, seconds)...], lut, dither)
 def sharded_workloads(nfiles=256):

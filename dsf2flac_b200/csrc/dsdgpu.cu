@@ -478,8 +478,8 @@ deinterleave_kernel(const uint8_t* __restrict__ in, long long count, int nch, ui
 // With x^31 = x^28 + 1:  r[3+m+i] = sum_k c_k r[3+i+k],  c = x^m mod (x^31 - x^28 - 1).
 //
 // The stream is cut into pieces of 248 values (124 output samples) per lane, 32 lanes per warp.
-// glibc_rand_anchor_kernel (one warp) jumps to the first value of the call: c = x^m as a product
-// of precomputed squarings, applied to the seed words -> 61 consecutive words ("segment").
+// The host jumps to the first value of the call: c = x^m as a product of precomputed powers
+// (4 bits of m at a time), applied to the seed words -> 61 consecutive words ("segment").
 // glibc_rand_fill_kernel: every warp advances that segment to its own start by up to three
 // table polynomials (x^(7936*u), x^(7936*128*u), x^(7936*16384*u), u < 128; 31 MACs per lane
 // each), every lane then applies its x^(248*lane) and runs the recurrence in registers.  Results
@@ -535,42 +535,12 @@ __device__ __forceinline__ void rand_apply_poly(const uint32_t* __restrict__ pol
     rand_extend_segment(seg_out, lane);
 }
 
-// one warp: the 61-word segment r[n-31 .. n+29], n = first_value
-__global__ void __launch_bounds__(32)
-glibc_rand_anchor_kernel(const uint32_t* __restrict__ pow2, const uint32_t* __restrict__ base,
-                         unsigned long long first_value, uint32_t* __restrict__ segment) {
-    __shared__ uint32_t c[kRandDeg], p[kRandDeg], t[2 * kRandDeg];
-    const int lane = threadIdx.x;
-    unsigned long long m = first_value - 34ULL;            // r[n-31+i] = r[3 + m + i]
-    if (lane < kRandDeg) c[lane] = (lane == 0) ? 1u : 0u;
-    __syncwarp();
-#pragma unroll 1
-    for (int b = 0; b < kRandPowBits && (m >> b) != 0; ++b) {
-        if (!((m >> b) & 1ULL)) continue;
-        if (lane < kRandDeg) p[lane] = pow2[b * kRandDeg + lane];
-        __syncwarp();
-        for (int d = lane; d < 2 * kRandDeg - 1; d += 32) {       // product coefficient d
-            uint32_t acc = 0;
-            const int lo = d > kRandDeg - 1 ? d - (kRandDeg - 1) : 0, hi = d < kRandDeg - 1 ? d : kRandDeg - 1;
-            for (int i = lo; i <= hi; ++i) acc += c[i] * p[d - i];
-            t[d] = acc;
-        }
-        __syncwarp();
-        if (lane == 0)
-            for (int d = 2 * kRandDeg - 2; d >= kRandDeg; --d) { t[d - 3] += t[d]; t[d - kRandDeg] += t[d]; }
-        __syncwarp();
-        if (lane < kRandDeg) c[lane] = t[lane];
-        __syncwarp();
-    }
-    for (int i = lane; i < 2 * kRandDeg - 1; i += 32) {
-        uint32_t acc = 0;
-        for (int k = 0; k < kRandDeg; ++k) acc += c[k] * base[i + k];
-        segment[i] = acc;
-    }
-}
+// The 61-word segment r[n-31 .. n+29] at the call's first value n, computed on the host
+// (rand_anchor_segment below: a dozen 31x31 polynomial products) and passed by value.
+struct RandSegment { uint32_t w[64]; };
 
 __global__ void __launch_bounds__(32 * kRandFillWarps)
-glibc_rand_fill_kernel(const uint32_t* __restrict__ segment, const uint32_t* __restrict__ lane_polys,
+glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ lane_polys,
                        const uint32_t* __restrict__ jump_polys, long long count, double* __restrict__ out) {
     __shared__ uint32_t seg_s[kRandFillWarps][2][64];
     __shared__ uint32_t poly_s[kRandFillWarps][32];
@@ -581,7 +551,7 @@ glibc_rand_fill_kernel(const uint32_t* __restrict__ segment, const uint32_t* __r
     if (s_warp >= count) return;                                   // whole warp
     uint32_t* cur = seg_s[wl][0];
     uint32_t* oth = seg_s[wl][1];
-    for (int i = lane; i < 2 * kRandDeg - 1; i += 32) cur[i] = segment[i];
+    for (int i = lane; i < 2 * kRandDeg - 1; i += 32) cur[i] = segment.w[i];
     __syncwarp();
     // the call's first value -> this warp's first value
 #pragma unroll 1
@@ -650,7 +620,6 @@ struct dsdgpu_slot {
     size_t out_cap = 0;
     double* d_dither = nullptr;
     size_t dither_cap = 0;
-    uint32_t* d_segment = nullptr;           // 61 words: the dither stream at the call's first sample
     bool busy = false;
 };
 
@@ -666,8 +635,8 @@ struct dsdgpu_ctx {
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
     unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only): fp64 or 32-bit entries
     double lut_unit = 1.0;                   // 32-bit tables: 2^-qbits
-    uint32_t* d_rand_pow2 = nullptr;         // x^(2^b), b < 48
-    uint32_t* d_rand_base = nullptr;         // seed words r[3..94]
+    std::vector<uint32_t> rand_pow16;        // host: x^(d * 16^k), d < 16, k < 12, [k][d][31]
+    std::vector<uint32_t> rand_base;         // host: seed words r[3..94]
     uint32_t* d_rand_lane = nullptr;         // x^(248*l), l < 32, stored [k][l]
     uint32_t* d_rand_jump = nullptr;         // x^(7936 * 128^level * u), [level][u][k]
     cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
@@ -706,7 +675,6 @@ void free_slot(dsdgpu_slot& s) {
     if (s.d_raw) cudaFree(s.d_raw);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_dither) cudaFree(s.d_dither);
-    if (s.d_segment) cudaFree(s.d_segment);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = dsdgpu_slot();
 }
@@ -737,19 +705,39 @@ void glibc_initial_words(uint32_t* r, int n) {
     for (int i = 34; i < n; ++i) r[i] = r[i - 31] + r[i - 3];
 }
 
+// x^m mod (x^31 - x^28 - 1) applied to the seed words: the 61 words r[n-31 .. n+29], n = m + 34
+void rand_anchor_segment(const dsdgpu_ctx* ctx, unsigned long long first_value, RandSegment& seg) {
+    unsigned long long m = first_value - 34ULL;
+    uint32_t c[kRandDeg] = {0}, t[kRandDeg];
+    c[0] = 1;
+    for (int k = 0; k < 12 && m != 0; ++k, m >>= 4) {
+        const unsigned d = (unsigned)(m & 15ULL);
+        if (!d) continue;
+        rand_poly_mul(c, &ctx->rand_pow16[((size_t)k * 16 + d) * kRandDeg], t);
+        memcpy(c, t, sizeof(c));
+    }
+    for (int i = 0; i < 2 * kRandDeg - 1; ++i) {
+        uint32_t acc = 0;
+        for (int k = 0; k < kRandDeg; ++k) acc += c[k] * ctx->rand_base[i + k];
+        seg.w[i] = acc;
+    }
+}
+
 int launch_dither(dsdgpu_ctx* ctx, dsdgpu_slot& s, unsigned long long first_sample, long long count,
                   double* d_out, cudaStream_t st) {
+    (void)s;
     if (count <= 0) return DSDGPU_OK;
-    if (!s.d_segment) CUDA_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&s.d_segment), 64 * sizeof(uint32_t)));
     const long long max_samples = (long long)kRandLevel * kRandLevel * kRandLevel * kRandWarpSamples;
     for (long long done = 0; done < count; done += max_samples) {      // one pass unless count > 8.3e9
         const long long n = count - done < max_samples ? count - done : max_samples;
         const unsigned long long first_value = 344ULL + 2ULL * (first_sample + (unsigned long long)done);
+        if (first_value - 34ULL >= (1ULL << 48)) return fail(ctx, DSDGPU_ERR_ARG, "dither position beyond 2^47 samples");
         const long long warps = (n + kRandWarpSamples - 1) / kRandWarpSamples;
-        glibc_rand_anchor_kernel<<<1, 32, 0, st>>>(ctx->d_rand_pow2, ctx->d_rand_base, first_value, s.d_segment);
+        RandSegment seg;
+        rand_anchor_segment(ctx, first_value, seg);
         glibc_rand_fill_kernel<<<(unsigned)((warps + kRandFillWarps - 1) / kRandFillWarps), 32 * kRandFillWarps, 0, st>>>(
-            s.d_segment, ctx->d_rand_lane, ctx->d_rand_jump, n, d_out + done);
-        ctx->launches += 2;
+            seg, ctx->d_rand_lane, ctx->d_rand_jump, n, d_out + done);
+        ctx->launches += 1;
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
@@ -974,8 +962,7 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     {
         uint32_t words[3 + kRandBaseWords];
         glibc_initial_words(words, 3 + kRandBaseWords);
-        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_base), kRandBaseWords * sizeof(uint32_t)));
-        CREATE_TRY(cudaMemcpy(ctx->d_rand_base, words + 3, kRandBaseWords * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ctx->rand_base.assign(words + 3, words + 3 + kRandBaseWords);
         std::vector<uint32_t> pow2((size_t)kRandPowBits * kRandDeg, 0);
         uint32_t cur[kRandDeg] = {0};
         cur[1] = 1;                               // x^(2^0)
@@ -985,8 +972,6 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
             rand_poly_mul(cur, cur, sq);
             memcpy(cur, sq, sizeof(cur));
         }
-        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_rand_pow2), pow2.size() * sizeof(uint32_t)));
-        CREATE_TRY(cudaMemcpy(ctx->d_rand_pow2, pow2.data(), pow2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         // x^e from the squarings
         auto power = [&](unsigned long long e, uint32_t* out) {
             uint32_t acc[kRandDeg] = {0}, tmp[kRandDeg];
@@ -997,6 +982,14 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
         };
         std::vector<uint32_t> lane_polys((size_t)kRandDeg * 32), jump((size_t)3 * kRandLevel * kRandDeg);
         uint32_t step[kRandDeg], acc[kRandDeg], tmp[kRandDeg];
+        ctx->rand_pow16.assign((size_t)12 * 16 * kRandDeg, 0);          // x^(d * 16^k) for the host-side anchor
+        for (int k = 0; k < 12; ++k) {
+            memset(acc, 0, sizeof(acc)); acc[0] = 1;
+            for (int d = 0; d < 16; ++d) {
+                memcpy(&ctx->rand_pow16[((size_t)k * 16 + d) * kRandDeg], acc, sizeof(acc));
+                rand_poly_mul(acc, &pow2[(size_t)4 * k * kRandDeg], tmp); memcpy(acc, tmp, sizeof(acc));
+            }
+        }
         power(kRandLaneValues, step);
         memset(acc, 0, sizeof(acc)); acc[0] = 1;
         for (int l = 0; l < 32; ++l) {
@@ -1030,8 +1023,6 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     if (ctx->d_lut_direct) cudaFree(ctx->d_lut_direct);
     if (ctx->d_lut_skew) cudaFree(ctx->d_lut_skew);
     if (ctx->d_lut_ring) cudaFree(ctx->d_lut_ring);
-    if (ctx->d_rand_pow2) cudaFree(ctx->d_rand_pow2);
-    if (ctx->d_rand_base) cudaFree(ctx->d_rand_base);
     if (ctx->d_rand_lane) cudaFree(ctx->d_rand_lane);
     if (ctx->d_rand_jump) cudaFree(ctx->d_rand_jump);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
