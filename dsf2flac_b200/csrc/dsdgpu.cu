@@ -653,6 +653,8 @@ using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x2 = RingGeom<16, 2>;
 using Ring16x2Q = RingGeom<16, 2, true>;
+using Ring30 = RingGeom<16, 2, false, 30, 2>;   // divide-by-16 filter: 30 tables, 2 bytes per frame
+using Ring12 = RingGeom<16, 2, false, 12, 1>;   // divide-by-8 filter: 12 tables, 1 byte per frame
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -851,13 +853,15 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         a.dither = scratch.d_dither;
     }
     const bool skew_ok = (ctx->nlut == 72 && ctx->nstep == 4 && ctx->d_lut_skew != nullptr);
-    const bool ring_ok = (ctx->nlut == 72 && ctx->nstep == 4 && ctx->d_lut_ring != nullptr);
+    const bool ring_ok = ctx->d_lut_ring != nullptr;
     int kernel = ctx->kernel;
     if (kernel == DSDGPU_KERNEL_AUTO)
         kernel = ring_ok ? DSDGPU_KERNEL_RING : skew_ok ? DSDGPU_KERNEL_SKEW : DSDGPU_KERNEL_DIRECT;
     if (kernel == DSDGPU_KERNEL_RING) {
-        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs nlut=72, nstep=4 and tables without -0.0 entries");
+        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
+        if (ctx->nlut == 30) return launch_ring<Ring30>(ctx, a, st);
+        if (ctx->nlut == 12) return launch_ring<Ring12>(ctx, a, st);
         return ctx->lut_precision == 32 ? launch_ring<Ring16x2Q>(ctx, a, st) : launch_ring<Ring16x2>(ctx, a, st);
     }
     if (kernel == DSDGPU_KERNEL_SKEW) {
@@ -936,27 +940,34 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     }
     CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_direct), tab.size() * sizeof(double)));
     CREATE_TRY(cudaMemcpy(ctx->d_lut_direct, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // The fp64 ring kernels route a value into one of two sums as fma(x, 0 or 1, acc): bit-exact
+    // unless x is -0.0 (or anything is non-finite).  No real filter has such a table entry; a table
+    // that does simply keeps the older kernels.  (Integer tables have no such case.)
+    bool plain = true;
+    for (double v : tab) plain = plain && std::isfinite(v) && !(v == 0.0 && std::signbit(v));
+    std::vector<unsigned char> rimg;
     if (nlut == 72 && nstep == 4) {
         std::vector<unsigned char> img(Skew512::LUT_BYTES);
         skew_build_lut_image<Skew512>(tab.data(), img.data());
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_skew), img.size()));
         CREATE_TRY(cudaMemcpy(ctx->d_lut_skew, img.data(), img.size(), cudaMemcpyHostToDevice));
-        // The fp64 ring kernel routes a value into one of two sums as fma(x, 0 or 1, acc): bit-exact
-        // unless x is -0.0 (or anything is non-finite).  No real filter has such a table entry; a
-        // table that does simply keeps the older kernels.  (Integer tables have no such case.)
-        bool plain = true;
-        for (double v : tab) plain = plain && std::isfinite(v) && !(v == 0.0 && std::signbit(v));
         if (lut_precision == 32) {
-            std::vector<unsigned char> rimg(Ring16x2Q::LUT_BYTES);
+            rimg.resize(Ring16x2Q::LUT_BYTES);
             ring_build_lut_image<Ring16x2Q>(tab.data(), rimg.data(), ctx->lut_unit);
-            CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
-            CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
         } else if (plain) {
-            std::vector<unsigned char> rimg(Ring16x2::LUT_BYTES);
+            rimg.resize(Ring16x2::LUT_BYTES);
             ring_build_lut_image<Ring16x2>(tab.data(), rimg.data());
-            CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
-            CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
         }
+    } else if (nlut == 30 && nstep == 2 && plain) {
+        rimg.resize(Ring30::LUT_BYTES);
+        ring_build_lut_image<Ring30>(tab.data(), rimg.data());
+    } else if (nlut == 12 && nstep == 1 && plain) {
+        rimg.resize(Ring12::LUT_BYTES);
+        ring_build_lut_image<Ring12>(tab.data(), rimg.data());
+    }
+    if (!rimg.empty()) {
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
+        CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
     }
     // dither generator constants
     {

@@ -55,11 +55,18 @@ namespace dsdgpu {
 //              copies of taps 64..71: a wrapped lane whose lower neighbour in its residue class
 //              (j - 8) has already restarted reads slot tap + 8*(j >> 3), which puts it on the
 //              bank nobody else can be on.
-template <int NWARP_, int KR_, bool Q32_ = false>
+//
+// Other filters (NLUT = 30 tables, 2 bytes per frame; NLUT = 12, 1 byte per frame): the period is
+// NLUT rounded up to a multiple of 16 steps, the extra slots hold -0.0 (the identity of fp64
+// addition), so a wrapped lane needs no second copy: slot PERIOD + s - j is bank pair (s - j) mod 16.
+template <int NWARP_, int KR_, bool Q32_ = false, int NLUT_ = 72, int NSTEP_ = 4>
 struct RingGeom {
     static constexpr bool Q32 = Q32_;
-    static constexpr int NLUT = 72;                   // tables = steps per period
-    static constexpr int NSTEP = 4;                   // bytes between successive frames
+    static constexpr int NLUT = NLUT_;                // tables
+    static constexpr int NSTEP = NSTEP_;              // bytes between successive frames
+    static constexpr bool DUP = (NLUT == 72);         // 72-step periods with tail copies (see above)
+    static constexpr int PERIOD = DUP ? 72 : (NLUT + 15) / 16 * 16;   // steps per period
+    static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
     static constexpr int KF = 4;                      // consecutive frames per lane
     static constexpr int KR = KR_;                    // rounds (periods) per tile
     static constexpr int NWARP = NWARP_;
@@ -68,11 +75,12 @@ struct RingGeom {
     static constexpr int SKEW_LANES = Q32 ? 32 : 16;  // lanes of one conflict-free load = skew values
     static constexpr int EARLY_GROUPS = SKEW_LANES / 4;   // 4-step groups in which some lane is still wrapped
     static constexpr int EARLY_STEPS = SKEW_LANES;
-    static constexpr int ROW = Q32 ? 96 : 80;         // slots per table row
-    static constexpr int ROW_BYTES = ROW * ELEM;      // 384 / 640: a multiple of 128
+    static constexpr int ROW = Q32 ? 96 : (DUP ? 80 : PERIOD);   // slots per table row
+    static constexpr int ROW_BYTES = ROW * ELEM;      // a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
     static constexpr int LUT_BYTES = GUARD_BYTES + 256 * ROW_BYTES;
     // a tile has two halves (lanes 0-15 / 16-31 of every warp), each with its own byte buffer
+    static constexpr int LANE_BYTES = KF * NSTEP;     // bytes between the windows of neighbouring lanes
     static constexpr int BLK_PER_ROUND = 16 * NWARP;  // 4-frame blocks per half per round
     static constexpr int FR_PER_ROUND = KF * BLK_PER_ROUND;
     static constexpr int NTP = KR * FR_PER_ROUND;     // frames per half per tile
@@ -82,6 +90,11 @@ struct RingGeom {
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
     static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
     static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
+    // where the emitter is called from: spread over the groups after the early ones if there are enough
+    static constexpr bool EMIT_SPREAD = GROUPS >= EARLY_GROUPS + 6;
+    static_assert(!Q32 || DUP, "32-bit tables exist for the 72-table filter");
+    static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4, "frame hop of 8, 16 or 32 DSD samples");
+    static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
     static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == 0 && ROW_BYTES % 128 == 0, "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
     static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
@@ -172,6 +185,13 @@ RING_HD int ring_lane_skew(int l) {
         return (g >> 1) + 4 * q;
     }
     const int h = (l >> 4) & 1, i = l & 15;
+    if (G::LANE_BYTES == 8) {
+        // lane stride of two words: window word of lane i = 2*i + (j >> 2); found by search
+        // upper half: j >> 2 = {3,3,3,2,2,2,2,3,0,1,1,1,1,0,0,0}[i], j & 3 = {0,1,2,0,1,2,3,3,0,0,1,2,3,1,2,3}[i]
+        const uint32_t q1 = 0x0154eabfu, a1 = 0xe790f924u;              // two bits per lane
+        return h ? (int)(4 * ((q1 >> (2 * i)) & 3u) + ((a1 >> (2 * i)) & 3u)) : i;
+    }
+    // lane stride of four words (and, with two-way conflicts on the window loads, of one word)
     const int q = 2 * (((i >> 2) & 1) ^ h) + ((i >> 3) & 1);
     return (i & 3) + 4 * q;
 }
@@ -198,21 +218,21 @@ struct RingLane {
     RING_HD double value(int k) const { return (double)p[k] * unit; }   // exact: |p| < 2^31
 };
 
-// a0 = a_tile + 16*(16*warp + (lane & 15)) + j: offset inside the half's buffer of the byte the
+// a0 = a_tile + LANE_BYTES*(16*warp + (lane & 15)) + j: offset inside the half's buffer of the byte the
 // lane's frame 0 reads at its tap 0.  Returns the offset (inside the half's buffer) of L(0), the
 // aligned word holding that byte's predecessor window, for round 0.
 template <class G>
 RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.0) {
     const int l = tid & 31, w = tid >> 5;
     const int j = ring_lane_skew<G>(l);
-    const int a0 = a_tile + 16 * (16 * w + (l & 15)) + j;
+    const int a0 = a_tile + G::LANE_BYTES * (16 * w + (l & 15)) + j;
     const int phi = (a0 + 1) & 3;
     r.j = j;
     r.unit = unit;
     r.shift = 8u * (uint32_t)phi;
     r.lnew = (uint32_t)(G::GUARD_BYTES - G::ELEM * j);
-    r.lwrap = (uint32_t)(G::GUARD_BYTES + G::ELEM * (G::NLUT - j));
-    r.lalt = (uint32_t)(G::ELEM * 8 * (j >> 3));
+    r.lwrap = (uint32_t)(G::GUARD_BYTES + G::ELEM * (G::PERIOD - j));
+    r.lalt = (uint32_t)(G::DUP ? G::ELEM * 8 * (j >> 3) : 0);
 #pragma unroll
     for (int g = 0; g < G::EARLY_GROUPS; ++g) {
         uint32_t v = 0;
@@ -229,6 +249,19 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     return a0 - 3 - phi;
 }
 
+// The 4-byte windows of the lane's four frames for one group: frame k reads NSTEP*k bytes further
+// on than frame 0, i.e. the word stream v = V(g), q[0..2] = V(g-1..g-3) shifted by NSTEP*k bytes.
+template <class G>
+RING_HD void ring_slot_words(uint32_t v, const uint32_t (&q)[3], uint32_t (&x)[4]) {
+    if (G::NSTEP == 4) {
+        x[0] = v; x[1] = q[0]; x[2] = q[1]; x[3] = q[2];
+    } else if (G::NSTEP == 2) {
+        x[0] = v; x[1] = ring_funnel_r(v, q[0], 16u); x[2] = q[0]; x[3] = ring_funnel_r(q[0], q[1], 16u);
+    } else {
+        x[0] = v; x[1] = ring_funnel_r(v, q[0], 8u); x[2] = ring_funnel_r(v, q[0], 16u); x[3] = ring_funnel_r(v, q[0], 24u);
+    }
+}
+
 // Steps 4*G0 .. 4*G1-1 of one period.  wnew / wold: smem byte offsets of word L(0) of this
 // period's window and of the previous period's window (whose groups 18.. continue here).
 template <class G, int G0, int G1, class Emit, class Trace>
@@ -236,8 +269,11 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                          int tid, int period, Emit& emit, const Trace& tr) {
 #pragma unroll
     for (int g = G0; g < G1; ++g) {
-        if (g > G::EARLY_GROUPS && g <= G::EARLY_GROUPS + 4) emit.quantise(g - G::EARLY_GROUPS - 1, r.value(g - G::EARLY_GROUPS - 1));
-        if (g == G::EARLY_GROUPS + 5) emit.store();
+        if (G::EMIT_SPREAD) {
+            if (g > G::EARLY_GROUPS && g <= G::EARLY_GROUPS + 4) emit.quantise(g - G::EARLY_GROUPS - 1, r.value(g - G::EARLY_GROUPS - 1));
+            if (g == G::EARLY_GROUPS + 5) emit.store();
+        }
+        // window words: v[0] = V(g), v[1..3] = V(g-1..g-3); frame k reads the 4 bytes NSTEP*k further on
         uint32_t x[4];
         {
             const uint32_t a = wnew - 4u * (uint32_t)g;
@@ -245,19 +281,19 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             tr.word(tid, period, 2 * g, a);
             const uint32_t v = ring_funnel_r(w, r.ln, r.shift);
             r.ln = w;
-            x[0] = v; x[1] = r.qn[0]; x[2] = r.qn[1]; x[3] = r.qn[2];
+            ring_slot_words<G>(v, r.qn, x);
             r.qn[2] = r.qn[1]; r.qn[1] = r.qn[0]; r.qn[0] = v;
         }
         if (g < G::EARLY_GROUPS) {
-            const uint32_t a = wold - 4u * (uint32_t)(18 + g);
+            const uint32_t a = wold - 4u * (uint32_t)(G::GROUPS + g);
             const uint32_t w = ring_lds_u32(smem, a);
             tr.word(tid, period, 2 * g + 1, a);
             const uint32_t v = ring_funnel_r(w, r.lo, r.shift);
             r.lo = w;
-            x[0] = ring_prmt(x[0], v, r.sel[g]);
-            x[1] = ring_prmt(x[1], r.qo[0], r.sel[g]);
-            x[2] = ring_prmt(x[2], r.qo[1], r.sel[g]);
-            x[3] = ring_prmt(x[3], r.qo[2], r.sel[g]);
+            uint32_t y[4];
+            ring_slot_words<G>(v, r.qo, y);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = ring_prmt(x[k], y[k], r.sel[g]);
             r.qo[2] = r.qo[1]; r.qo[1] = r.qo[0]; r.qo[0] = v;
         }
 #pragma unroll
@@ -268,7 +304,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 // wrapped lanes (s < j) still add to their previous frames; multipliers route each
                 // table value into exactly one of the two sums without a select: fma(x, 1, acc) is
                 // acc + x and fma(x, 0, acc) is acc, bit for bit (integer tables: x*1 + acc, x*0 + acc)
-                if (s + 8 < G::EARLY_STEPS && r.j == s + 8) loff += r.lalt;   // taps 64..71 from this lane's tail copy
+                if (G::DUP && s + 8 < G::EARLY_STEPS && r.j == s + 8) loff += r.lalt;   // taps 64..71 from this lane's tail copy
                 cur = (s >= r.j);
                 if (r.j == s) loff = r.lnew;                     // tap 0 of the next frame set
             }
@@ -327,7 +363,12 @@ RING_HD void ring_head(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
 template <class G, class Emit, class Trace>
 RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        Emit& emit, const Trace& tr) {
-    ring_groups<G, G::EARLY_GROUPS, 18>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
+    if (!G::EMIT_SPREAD) {               // short periods: the whole emitter before the remaining steps
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit.quantise(k, r.value(k));
+        emit.store();
+    }
+    ring_groups<G, G::EARLY_GROUPS, G::GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = 0; }
     r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];   // this window's last words = next period's history
@@ -384,6 +425,8 @@ RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
 template <class G>
 inline void ring_build_lut_image(const double* lut, unsigned char* image, double unit = 1.0) {
     for (int i = 0; i < G::LUT_BYTES; ++i) image[i] = 0;
+    if (!G::Q32)                                        // pad slots: -0.0, the identity of fp64 addition
+        for (int i = 0; i < G::LUT_BYTES / 8; ++i) reinterpret_cast<double*>(image)[i] = -0.0;
     auto put = [&](int e, int slot, double v) {
         unsigned char* at = image + G::GUARD_BYTES + e * G::ROW_BYTES + slot * G::ELEM;
         if (G::Q32) *reinterpret_cast<int32_t*>(at) = (int32_t)(v / unit);
@@ -391,7 +434,7 @@ inline void ring_build_lut_image(const double* lut, unsigned char* image, double
     };
     for (int e = 0; e < 256; ++e) {
         for (int t = 0; t < G::NLUT; ++t) put(e, t, lut[t * 256 + e]);
-        for (int copy = 1; G::NLUT + 8 * copy <= G::ROW; ++copy)      // tail copies: slot = tap + 8*copy
+        for (int copy = 1; G::DUP && G::NLUT + 8 * copy <= G::ROW; ++copy)      // tail copies: slot = tap + 8*copy
             for (int m = 0; m < 8; ++m) put(e, 64 + m + 8 * copy, lut[(64 + m) * 256 + e]);
     }
 }

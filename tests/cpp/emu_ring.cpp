@@ -212,6 +212,8 @@ int main(int argc, char** argv) {
     if (nwarp == 16 && kr == 2) return run<RingGeom<16, 2>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 16 && kr == 1) return run<RingGeom<16, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 8 && kr == 6) return run<RingGeom<8, 6>>(nframes, nch, p0, in_first, in_count, seed, grid);
+    if (nwarp == 30 && kr == 2) return run<RingGeom<16, 2, false, 30, 2>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "30": /16 filter
+    if (nwarp == 12 && kr == 2) return run<RingGeom<16, 2, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "12": /8 filter
     if (nwarp == 32 && kr == 2) return run<RingGeom<16, 2, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "32": 32-bit tables
     if (nwarp == 32 && kr == 3) return run<RingGeom<16, 3, true>>(nframes, nch, p0, in_first, in_count, seed, grid);
     fprintf(stderr, "unsupported geometry\n");

@@ -23,6 +23,16 @@ EMU = os.path.join(os.path.dirname(__file__), "cpp", "_build", "emu_ring")
     (8, 6, 9000, 6, 75, 3, 37000, 5, 2),         # 5.1, unaligned in_first, 8-warp geometry
     (16, 3, 1, 2, 72, 0, 100, 7, 4),             # a single frame
     (16, 2, 30000, 2, 75, 0, 121000, 8, 3),      # two rounds per tile, 5 tiles per CTA, aligned
+    (32, 2, 30000, 2, 75, 0, 121000, 8, 3),      # nwarp "32" = 32-bit tables: 32-lane skew, three tail copies
+    (32, 2, 20000, 2, 72, 0, 81000, 1, 2),
+    (32, 3, 15000, 3, -1, 0, 61000, 3, 3),
+    (32, 2, 9000, 6, 75, 3, 37000, 5, 2),
+    (30, 2, 30000, 2, 31, 0, 61000, 8, 3),       # nwarp "30" = the divide-by-16 filter (30 tables, 32-step periods)
+    (30, 2, 9000, 3, -1, 0, 19000, 3, 2),
+    (30, 2, 9000, 1, 30, 2, 18000, 3, 2),
+    (12, 2, 30000, 2, 15, 0, 31000, 8, 3),       # nwarp "12" = the divide-by-8 filter (12 tables, 16-step periods)
+    (12, 2, 9000, 6, -1, 0, 9500, 3, 2),
+    (12, 2, 5000, 1, 12, 1, 5200, 4, 1),
 ])
 def test_ring_lanes(nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid):
     r = subprocess.run([EMU, *map(str, (nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid))],
@@ -32,7 +42,7 @@ def test_ring_lanes(nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid)
     assert rep["checked"] == nframes * nch and rep["mismatches"] == 0
     assert rep["missing"] == 0 and rep["duplicates"] == 0 and rep["oob"] == 0
     assert rep["lut_wavefronts"] == rep["lut_halfwarp_loads"]
-    if (p0 - in_first + 1) % 4 == 0:
+    if (p0 - in_first + 1) % 4 == 0 and nwarp != 12:     # one-word lane stride (divide-by-8): two-way by construction
         assert rep["word_wavefronts"] == rep["word_loads"]
     else:
         assert rep["word_wavefronts"] <= 2 * rep["word_loads"]

@@ -19,8 +19,8 @@ KERNELS = {"direct": capi.KERNEL_DIRECT, "skew": capi.KERNEL_SKEW, "ring": capi.
 
 def make(ratio, msb, nch, kernel="auto", precision=64):
     fir = filters.FILTERS[ratio]
-    if kernel in ("skew", "ring") and ratio != 32:
-        pytest.skip("the lane-skewed kernels exist for the divide-by-32 filter only")
+    if kernel == "skew" and ratio != 32:
+        pytest.skip("the 80-step skew kernel exists for the divide-by-32 filter only")
     g = capi.DsdGpu(filters.build_lut(fir, msb), nch, fir.nstep, lut_precision=precision)
     g.set_option("kernel", KERNELS[kernel])
     return fir, g
@@ -205,9 +205,13 @@ def test_option_errors():
     fir, g = make(16, 1, 2)
     with pytest.raises(capi.DsdGpuError):
         g.set_option("no_such_knob", 1)
-    g.set_option("kernel", capi.KERNEL_RING)
+    odd = capi.DsdGpu(np.ones((5, 256)), 1, 3)              # not one of the reference's filter geometries
+    odd.set_option("kernel", capi.KERNEL_RING)
     with pytest.raises(capi.DsdGpuError, match="ring kernel needs"):
-        g.decimate_host(seeded_bytes(2, 1000, 1), 30, 10, 1.0)
+        odd.decimate_host(seeded_bytes(1, 1000, 1), 30, 10, 1.0)
+    odd.set_option("kernel", capi.KERNEL_AUTO)                # ... the direct kernel takes any geometry
+    assert odd.decimate_host(seeded_bytes(1, 1000, 1), 30, 10, 1.0).shape == (10, 1)
+    odd.close()
     g.set_option("kernel", capi.KERNEL_SKEW)
     with pytest.raises(capi.DsdGpuError, match="skew kernel needs"):
         g.decimate_host(seeded_bytes(2, 1000, 1), 30, 10, 1.0)
