@@ -324,3 +324,27 @@ def test_32bit_tables_same_bits_from_every_kernel_and_sharding(oracle):
     assert np.abs(outs["ring"].astype(np.int64) - want_i).max() <= 1
     want_f = oracle.run_raw(data, nbytes * 8, 1, DSD64, 88200, fir.nlut + 1, n, 1.0, want="f64")
     assert np.abs(f64 - want_f).max() <= 1e-7 * np.abs(want_f).max()
+
+
+@pytest.mark.parametrize("ratio", [32, 16, 8])
+def test_device_pointers_unaligned_everything(oracle, ratio):
+    """Device entry point with nothing aligned: input base and row stride odd, output base only
+    4-byte aligned, frame grid off the 4-byte grid, odd channel count -- the staging falls back
+    to bytewise assembly and the emitter to scalar stores, the PCM does not change."""
+    import torch
+    fir, g = make(ratio, 1, 3, "ring")
+    n_bytes = 33_333
+    data = seeded_bytes(3, n_bytes, 17 + ratio)
+    scale, amp, clip = filters.app_params(20, dither=True)
+    n = filters.app_frames(n_bytes * 8, fir)
+    want = oracle.run_app(data, n_bytes * 8, 1, DSD64, RATES[ratio], scale, amp, clip)
+    stride = n_bytes + 7
+    raw = torch.zeros(3 * stride + 64, dtype=torch.uint8, device="cuda")
+    for c in range(3):
+        raw[1 + c * stride: 1 + c * stride + n_bytes] = torch.from_numpy(data[c]).cuda()
+    out = torch.zeros(n * 3 + 8, dtype=torch.int32, device="cuda")
+    g.decimate_device(raw.data_ptr() + 1, stride, 0, n_bytes, 0x69, fir.nlut, n, scale, amp, clip, 0, capi.OUT_INT32,
+                      out.data_ptr() + 4)
+    assert np.array_equal(out[1:1 + n * 3].cpu().numpy().reshape(n, 3), want)
+    assert int(out[0]) == 0 and int(out[1 + n * 3]) == 0          # nothing written outside
+    g.close()
