@@ -144,6 +144,16 @@ RING_HD double ring_add(double a, double b) {
     return a + b;
 #endif
 }
+// a * m + b on the integer multiply-add pipe (never rewritten into add / select by the compiler)
+RING_HD int32_t ring_imad(int32_t a, int32_t m, int32_t b) {
+#if defined(__CUDA_ARCH__)
+    int32_t r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(m), "r"(b));
+    return r;
+#else
+    return (int32_t)((uint32_t)a * (uint32_t)m + (uint32_t)b);
+#endif
+}
 RING_HD double ring_fma(double a, double m, double b) {
 #if defined(__CUDA_ARCH__)
     return __fma_rn(a, m, b);
@@ -215,6 +225,8 @@ struct RingLane {
     uint32_t lnew, lwrap, lalt; // table offset at static step 0: current frames / wrapped frames; step to the tail copy
     uint32_t sel[G::EARLY_GROUPS];   // byte selectors mixing the two windows in the early groups
     double unit;                // value of one unit of acc_t (1.0, or 2^-qbits for 32-bit tables)
+    int one;                    // 1, in a register the compiler cannot see through: x * one + acc issues on
+                                // the multiply-add pipe instead of the integer ALU the byte extraction keeps busy
     RING_HD double value(int k) const { return (double)p[k] * unit; }   // exact: |p| < 2^31
 };
 
@@ -229,6 +241,7 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     const int phi = (a0 + 1) & 3;
     r.j = j;
     r.unit = unit;
+    r.one = unit > 0.0 ? 1 : 0;
     r.shift = 8u * (uint32_t)phi;
     r.lnew = (uint32_t)(G::GUARD_BYTES - G::ELEM * j);
     r.lwrap = (uint32_t)(G::GUARD_BYTES + G::ELEM * (G::PERIOD - j));
@@ -300,6 +313,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
             bool cur = true;
+            int to_n = 1, to_p = 0;
             if (s < G::EARLY_STEPS) {
                 // wrapped lanes (s < j) still add to their previous frames; multipliers route each
                 // table value into exactly one of the two sums without a select: fma(x, 1, acc) is
@@ -307,6 +321,8 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 if (G::DUP && s + 8 < G::EARLY_STEPS && r.j == s + 8) loff += r.lalt;   // taps 64..71 from this lane's tail copy
                 cur = (s >= r.j);
                 if (r.j == s) loff = r.lnew;                     // tap 0 of the next frame set
+                to_n = cur ? 1 : 0;
+                to_p = 1 - to_n;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -320,10 +336,10 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 if constexpr (G::Q32) {
                     const int32_t v = ring_lds_i32(smem, addr);
                     if (s < G::EARLY_STEPS) {
-                        r.n[k] = v * (cur ? 1 : 0) + r.n[k];
-                        r.p[k] = v * (cur ? 0 : 1) + r.p[k];
+                        r.n[k] = ring_imad(v, to_n, r.n[k]);
+                        r.p[k] = ring_imad(v, to_p, r.p[k]);
                     } else {
-                        r.n[k] += v;
+                        r.n[k] = ring_imad(v, r.one, r.n[k]);
                     }
                 } else {
                     const double v = ring_lds_f64(smem, addr);
