@@ -545,13 +545,83 @@ def run_sharded_arm(args, spec):
         dist.destroy_process_group()
 
 
+def run_dop_arm(args):
+    """DoP packing: DSD64 stereo 60 s -> 176.4 kHz DoP frames.  An HBM-bound byte
+    shuffle: 2 bytes in + 4 bytes out per output sample."""
+    import torch
+    from dsf2flac_b200 import capi
+    from tests.oracle_lib import Oracle, REF_SO
+    dsd_fs, nch, seconds = DSD64, 2, 60
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local)
+    data = synth_stream(dsd_fs, nch, seconds)
+    nbytes = data.shape[1]
+    nframes = nbytes // 2
+    g = capi.DsdGpu(np.zeros((1, 256)), nch, 1, device=local)
+    ring = 4
+    d_in = [torch.from_numpy(np.roll(data, 4096 * k, axis=1)).cuda() for k in range(ring)]
+    d_out = [torch.empty((nframes, nch), dtype=torch.int32, device="cuda") for _ in range(ring)]
+    flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    times = []
+    sampler = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        for k in range(args.warmup + args.steps):
+            flush.fill_(k & 0xFF)                           # the working set (127 MB) is about L2-sized: evict it
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            g.dop_pack_device(d_in[k % ring], nbytes, 0, nbytes, 0x69, 0, nframes, 1, d_out[k % ring], stream=stream.cuda_stream)
+            e1.record(stream)
+            times.append((e0, e1))
+    stream.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in times[args.warmup:])
+    kernel_ms = ms[len(ms) // 2]
+    pin_in = capi.PinnedBuffer((nch, nbytes), np.uint8)
+    pin_in.array[:] = data
+    pin_out = capi.PinnedBuffer((nframes, nch), np.int32)
+    lib = g.lib
+    for _ in range(args.warmup):
+        lib.dsdgpu_dop_pack_host(g.h, pin_in.ptr, nbytes, 0, nbytes, 0x69, 0, nframes, 1, pin_out.ptr)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lib.dsdgpu_dop_pack_host(g.h, pin_in.ptr, nbytes, 0, nbytes, 0x69, 0, nframes, 1, pin_out.ptr)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(0.0, time.perf_counter())
+    orc = Oracle(reference=os.path.exists(REF_SO))
+    sub = np.ascontiguousarray(data[:, :dsd_fs // 8 * 5])
+    t0 = time.perf_counter()
+    want = orc.dop_run_raw(sub, 1 << 40, 1, 1, sub.shape[1] // 2 - 1)
+    cpu_s = time.perf_counter() - t0
+    assert np.array_equal(pin_out.array[:len(want)], want), "DoP frames differ from the CPU packer"
+    peaks, peak_src = measured_peaks()
+    bits = nbytes * 8 * nch
+    hbm_bytes = nframes * nch * 6
+    print(json.dumps({
+        "metric": "dsd_mbit_per_s", "value": bits / (kernel_ms * 1e-3) / 1e6, "unit": "Mbit/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "DSD64 stereo 60 s -> DoP frames at 176.4 kHz (reference dop_packer.cpp)", "l2": "L2 flushed between steps"},
+        "roofline": {"bound": "hbm", "achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                     "algorithmic_bytes_per_sample": 6, "samples_per_launch": nframes * nch, "peak_source": peak_src},
+        "cpu_baseline": {"value": sub.size * 8 / cpu_s / 1e6, "unit": "Mbit/s", "cores": 1, "kind": "reference" if orc.reference else "port",
+                         "sample": "first 5 s, DopPacker::pack_buffer over an in-memory reader"},
+        "e2e": {"value": bits * args.steps / e2e_s / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": nch * nbytes,
+                "d2h_bytes_per_step": nframes * nch * 4, "ms_per_step": e2e_s / args.steps * 1e3, "api": "dsdgpu_dop_pack_host"},
+        "gpu_launches": args.steps, "clocks": clocks,
+    }), flush=True)
+    g.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c5", "dop"])
     ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
     ap.add_argument("--dither", type=int, default=0)
     ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring"])
@@ -564,6 +634,8 @@ def main():
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "dop":
+        return run_dop_arm(args)
     if args.workload in ("c3", "c4", "c5"):
         if args.impl == "reference":
             raise SystemExit("the reference arm runs the unsharded workloads (c1, c2)")

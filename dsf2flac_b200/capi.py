@@ -44,6 +44,10 @@ GPU_PROTOTYPES = {
                                 C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _vp]),
     "dsdgpu_wait": (C.c_int, [_vp, C.c_int]),
     "dsdgpu_dither_fill_device": (C.c_int, [_vp, C.c_uint64, C.c_int64, _vp, _vp]),
+    "dsdgpu_dop_pack_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64, C.c_int,
+                                         _vp, _vp]),
+    "dsdgpu_dop_pack_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64, C.c_int,
+                                       _vp]),
     "dsdgpu_plan_shards": (C.c_int64, [C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                        C.c_int, C.c_int, C.c_int64, _vp, C.c_int64]),
 }
@@ -99,6 +103,10 @@ def host_lib(path=None):
     lib.dsdhost_file_channel_bytes.argtypes = [C.c_char_p, C.c_int, C.c_int, _vp, i64]
     lib.dsdhost_convert_file.restype = i64
     lib.dsdhost_convert_file.argtypes = [C.c_char_p, C.c_int, u32, dbl, dbl, dbl, C.c_int, u32, _vp, i64]
+    lib.dsdhost_dop_run_app.restype = i64
+    lib.dsdhost_dop_run_app.argtypes = [_vp, C.c_int, i64, i64, C.c_uint8, C.c_int, _vp, i64]
+    lib.dsdhost_dop_file.restype = i64
+    lib.dsdhost_dop_file.argtypes = [C.c_char_p, C.c_int, _vp, i64]
     lib.dsdhost_synth_sdm.restype = None
     lib.dsdhost_synth_sdm.argtypes = [_vp, i64, dbl, dbl, dbl, C.c_int]
     if path is None:
@@ -199,6 +207,21 @@ class DsdGpu:
 
     def wait(self, slot):
         self._check(self.lib.dsdgpu_wait(self.h, slot), "dsdgpu_wait")
+
+    def dop_pack_device(self, d_in, in_stride, in_first, in_count, fill, pm0, nframes, reverse_bits, d_out, stream=None):
+        self._check(self.lib.dsdgpu_dop_pack_device(self.h, _ptr(d_in), in_stride, in_first, in_count, fill, pm0, nframes,
+                                                    int(reverse_bits), _ptr(d_out), stream), "dsdgpu_dop_pack_device")
+
+    def dop_pack_host(self, planar, pm0, nframes, reverse_bits, fill=0x69, in_first=0, in_count=None):
+        """planar: uint8 [nch, nbytes] (or the source in the layout set with source_block_bytes)."""
+        planar = np.ascontiguousarray(planar, dtype=np.uint8)
+        stride = planar.shape[1] if planar.ndim == 2 else 0
+        if in_count is None:
+            in_count = planar.shape[1]
+        out = np.empty((nframes, self.nch), dtype=np.int32)
+        self._check(self.lib.dsdgpu_dop_pack_host(self.h, planar.ctypes.data, stride, in_first, in_count, fill, pm0, nframes,
+                                                  int(reverse_bits), out.ctypes.data), "dsdgpu_dop_pack_host")
+        return out
 
     def dither_fill_device(self, first_sample, count, d_out, stream=None):
         self._check(self.lib.dsdgpu_dither_fill_device(self.h, first_sample, count, _ptr(d_out), stream),

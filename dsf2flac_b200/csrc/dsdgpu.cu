@@ -474,6 +474,81 @@ deinterleave_kernel(const uint8_t* __restrict__ in, long long count, int nch, ui
 }
 
 // ---------------------------------------------------------------------------------------------
+// DoP packing (reference src/dop_packer.cpp:100-141): output sample (frame i, channel c) =
+// marker + (B_c(pm - 1) << 8) + B_c(pm), pm = pm0 + 2*i + 1 the reader's marker after the frame's
+// first step(); marker 0x00050000 when (8*pm - 8) % 32 == 0 (C remainder), else 0xFFFA0000; both
+// bytes bit-reversed when the reader says msbIsPlayedFirst().  Pure byte traffic: 2 B in, 4 B out.
+// One thread per output sample in output order (coalesced 4-byte stores).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dop_pack_kernel(DecimateArgs a, long long pm0, int reverse) {
+    const long long total = a.nframes * a.nch;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx / a.nch;
+        const int c = (int)(idx - i * a.nch);
+        const long long pm = pm0 + 2 * i + 1;
+        const long long o1 = pm - 1 - a.in_first, o2 = pm - a.in_first;
+        unsigned b1 = (o1 >= 0 && o1 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o1)] : a.fill;
+        unsigned b2 = (o2 >= 0 && o2 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o2)] : a.fill;
+        if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
+        const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
+        reinterpret_cast<int32_t*>(a.out)[idx] = marker + (int)(b1 << 8) + (int)b2;
+    }
+}
+
+// Four consecutive output samples per thread (mono: 4 frames = 8 source bytes; stereo: 2 frames of
+// both channels = 4 source bytes per channel), aligned word loads, one 16-byte store.  Requires
+// (pm0 - in_first) % 4 == 0 and 4-byte aligned rows; groups that touch the ends of the source fall
+// back to the byte-wise expression.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+dop_pack_wide_kernel(DecimateArgs a, long long pm0, int reverse) {
+    const long long total = a.nframes * NCH, groups = (total + 3) / 4;
+    constexpr int FR = 4 / NCH;                                   // frames per thread
+    constexpr int NB = 2 * FR;                                    // source bytes per channel per thread
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < groups;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long f0 = t * FR;
+        const long long o = pm0 + 2 * f0 - a.in_first;           // source index of the group's first byte
+        int v[4];
+        if (o >= 0 && o + NB <= a.in_count && 4 * t + 3 < total) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t w[NB / 4];
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(a.in + src_offset(a, c, o));
+#pragma unroll
+                for (int q = 0; q < NB / 4; ++q) w[q] = src[q];
+#pragma unroll
+                for (int k = 0; k < FR; ++k) {
+                    uint32_t pair = (w[(2 * k) / 4] >> (8 * ((2 * k) & 3))) & 0xffffu;   // bytes 2k (low), 2k+1 (high)
+                    uint32_t b1 = pair & 0xffu, b2 = pair >> 8;
+                    if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
+                    const long long pm = pm0 + 2 * (f0 + k) + 1;
+                    const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
+                    v[k * NCH + c] = marker + (int)(b1 << 8) + (int)b2;
+                }
+            }
+            reinterpret_cast<int4*>(a.out)[t] = make_int4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int e = 0; e < 4; ++e) {
+                const long long idx = 4 * t + e;
+                if (idx >= total) break;
+                const long long i = idx / NCH;
+                const int c = (int)(idx - i * NCH);
+                const long long pm = pm0 + 2 * i + 1;
+                const long long o1 = pm - 1 - a.in_first, o2 = pm - a.in_first;
+                unsigned b1 = (o1 >= 0 && o1 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o1)] : a.fill;
+                unsigned b2 = (o2 >= 0 && o2 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o2)] : a.fill;
+                if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
+                const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
+                reinterpret_cast<int32_t*>(a.out)[idx] = marker + (int)(b1 << 8) + (int)b2;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // glibc rand() by position.  r[i] = r[i-31] + r[i-3] (mod 2^32) for i >= 34, draw k = r[344+k]>>1.
 // With x^31 = x^28 + 1:  r[3+m+i] = sum_k c_k r[3+i+k],  c = x^m mod (x^31 - x^28 - 1).
 //
@@ -1144,6 +1219,63 @@ int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_strid
     return DSDGPU_OK;
 }
 
+// What a kernel reads after a host window has been brought to the device.
+struct SourceView {
+    const uint8_t* d = nullptr;
+    size_t stride = 0;
+    int block_shift = -1;
+    int64_t first = 0, count = 0;
+};
+
+// Upload stream bytes [lo, hi) (already clipped to the caller's window) of every channel in the
+// context's source layout on slot `s`.  `oldest` = the oldest stream index the run reads, `grid` =
+// a stream index the device buffer should be 16-byte aligned to (planar / interleaved sources).
+static int stage_source(dsdgpu_ctx* ctx, dsdgpu_slot& s, const uint8_t* in, size_t in_stride, int64_t in_first,
+                        int64_t in_count, uint8_t fill, int64_t lo, int64_t hi, int64_t oldest, int64_t grid,
+                        SourceView& v) {
+    const int64_t n = hi - lo;
+    int rc;
+    if (ctx->source_block >= 16) {
+        // DSF-style source: whole blocks of every channel are one contiguous range of the host buffer
+        const int64_t B = ctx->source_block;
+        if (in_first % B != 0) return fail(ctx, DSDGPU_ERR_ARG, "block sources must start on a block boundary");
+        const int64_t b0 = (lo - in_first) / B, b1 = n > 0 ? (hi - in_first + B - 1) / B : b0;
+        const size_t bytes = (size_t)(b1 - b0) * (size_t)B * ctx->nch;
+        rc = ensure(ctx, &s.d_in, &s.in_cap, bytes + 256);
+        if (rc) return rc;
+        if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, in + (size_t)b0 * B * ctx->nch, bytes, cudaMemcpyHostToDevice, s.stream));
+        int64_t cnt = in_count - b0 * B;
+        if (cnt > (b1 - b0) * B) cnt = (b1 - b0) * B;
+        v.d = s.d_in; v.stride = 0; v.block_shift = block_shift_of(B); v.first = in_first + b0 * B; v.count = cnt;
+        return DSDGPU_OK;
+    }
+    // Planar rows on the device, placed so that (grid - first) is a multiple of 16, `first` being the
+    // stream index of the first byte of the device buffer: with grid = p0 + 1 the ring kernel's window
+    // loads are bank-conflict free (ring_core.h).  The pad bytes in front count as part of the source
+    // (d_in stays 16-byte aligned): either they are older than anything the run reads, or -- when the
+    // run starts before the caller's first byte -- they are set to the fill byte they stand for.
+    const int64_t pad = ((lo - grid) % 16 + 16) % 16;
+    const size_t dstride = ((size_t)(n + pad) + 255) & ~(size_t)255;
+    rc = ensure(ctx, &s.d_in, &s.in_cap, dstride * ctx->nch + 256);
+    if (rc) return rc;
+    if (pad > 0 && oldest < lo)
+        CUDA_TRY(ctx, cudaMemset2DAsync(s.d_in, dstride, fill, (size_t)pad, (size_t)ctx->nch, s.stream));
+    if (ctx->source_block == 1) {
+        // DSDIFF-style source: upload the interleaved range as it is, split it on the device
+        const size_t bytes = (size_t)n * ctx->nch;
+        rc = ensure(ctx, &s.d_raw, &s.raw_cap, bytes + 256);
+        if (rc) return rc;
+        if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_raw, in + (size_t)(lo - in_first) * ctx->nch, bytes, cudaMemcpyHostToDevice, s.stream));
+        rc = launch_deinterleave(ctx, s.d_raw, n, s.d_in, (long long)dstride, (int)pad, s.stream);
+        if (rc) return rc;
+    } else if (n > 0) {
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in + pad, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
+                                        (size_t)ctx->nch, cudaMemcpyHostToDevice, s.stream));
+    }
+    v.d = s.d_in; v.stride = dstride; v.block_shift = -1; v.first = lo - pad; v.count = n + pad;
+    return DSDGPU_OK;
+}
+
 int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride, int64_t in_first,
                   int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
                   double dither_amp, double clip, uint64_t dither_first_sample, int out_kind, void* out) {
@@ -1161,55 +1293,110 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
     // bytes this run of frames can touch, clipped to what the caller has
     int64_t lo, hi;
     run_window(ctx, in_first, in_count, p0, nframes, lo, hi);
-    const int64_t n = hi - lo;
-    if (ctx->source_block >= 16) {
-        // DSF-style source: whole blocks of every channel are one contiguous range of the host buffer
-        const int64_t B = ctx->source_block;
-        if (in_first % B != 0) return fail(ctx, DSDGPU_ERR_ARG, "block sources must start on a block boundary");
-        const int64_t b0 = (lo - in_first) / B, b1 = n > 0 ? (hi - in_first + B - 1) / B : b0;
-        const size_t bytes = (size_t)(b1 - b0) * (size_t)B * ctx->nch;
-        rc = ensure(ctx, &s.d_in, &s.in_cap, bytes + 256);
-        if (rc) return rc;
-        if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, in + (size_t)b0 * B * ctx->nch, bytes, cudaMemcpyHostToDevice, s.stream));
-        int64_t cnt = in_first + in_count - (in_first + b0 * B);
-        if (cnt > (b1 - b0) * B) cnt = (b1 - b0) * B;
-        rc = enqueue_decimate(ctx, s, s.d_in, 0, block_shift_of(B), in_first + b0 * B, cnt, fill, p0, nframes, scale,
-                              dither_amp, clip, dither_first_sample, out_kind, s.d_out, s.stream);
-    } else if (ctx->source_block == 1) {
-        // DSDIFF-style source: upload the interleaved range as it is, split it on the device
-        const size_t bytes = (size_t)n * ctx->nch;
-        rc = ensure(ctx, &s.d_raw, &s.raw_cap, bytes + 256);
-        if (rc) return rc;
-        if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_raw, in + (size_t)(lo - in_first) * ctx->nch, bytes, cudaMemcpyHostToDevice, s.stream));
-        int64_t first, count;
-        size_t dstride;
-        rc = planar_from_interleaved(ctx, s, s.d_raw, lo, lo, hi, p0, fill, s.stream, dstride, first, count);
-        if (rc) return rc;
-        rc = enqueue_decimate(ctx, s, s.d_in, dstride, -1, first, count, fill, p0, nframes, scale, dither_amp, clip,
-                              dither_first_sample, out_kind, s.d_out, s.stream);
-    } else {
-        // Place the bytes so that (p0 - first + 1) is a multiple of 16, `first` being the stream index
-        // of the first byte of the device buffer: the ring kernel's window loads are then bank-conflict
-        // free (ring_core.h).  The pad bytes in front count as part of the source (d_in stays 16-byte
-        // aligned): either they are older than anything a frame of this run reads, or -- when the run
-        // starts before the caller's first byte -- they are set to the fill byte they stand for.
-        const int64_t pad = ((lo - p0 - 1) % 16 + 16) % 16;
-        const bool reads_before_source = p0 - (ctx->nlut - 1) < lo;
-        const size_t dstride = ((size_t)(n + pad) + 255) & ~(size_t)255;
-        rc = ensure(ctx, &s.d_in, &s.in_cap, dstride * ctx->nch + 256);
-        if (rc) return rc;
-        if (pad > 0 && reads_before_source)
-            CUDA_TRY(ctx, cudaMemset2DAsync(s.d_in, dstride, fill, (size_t)pad, (size_t)ctx->nch, s.stream));
-        if (n > 0)
-            CUDA_TRY(ctx, cudaMemcpy2DAsync(s.d_in + pad, dstride ? dstride : 256, in + (lo - in_first), in_stride, (size_t)n,
-                                            (size_t)ctx->nch, cudaMemcpyHostToDevice, s.stream));
-        rc = enqueue_decimate(ctx, s, s.d_in, dstride, -1, lo - pad, n + pad, fill, p0, nframes, scale, dither_amp, clip,
-                              dither_first_sample, out_kind, s.d_out, s.stream);
-    }
+    SourceView v;
+    rc = stage_source(ctx, s, in, in_stride, in_first, in_count, fill, lo, hi, p0 - (ctx->nlut - 1), p0 + 1, v);
+    if (rc) return rc;
+    rc = enqueue_decimate(ctx, s, v.d, v.stride, v.block_shift, v.first, v.count, fill, p0, nframes, scale, dither_amp,
+                          clip, dither_first_sample, out_kind, s.d_out, s.stream);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     s.busy = true;
     return DSDGPU_OK;
+}
+
+static int launch_dop(dsdgpu_ctx* ctx, const SourceView& v, uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits,
+                      int32_t* d_out, cudaStream_t st) {
+    if (nframes == 0) return DSDGPU_OK;
+    DecimateArgs a = {};
+    a.in = v.d; a.in_stride = (long long)v.stride; a.block_shift = v.block_shift;
+    a.in_first = v.first; a.in_count = v.count; a.nframes = nframes; a.nch = ctx->nch; a.fill = fill; a.out = d_out;
+    const long long total = nframes * ctx->nch;
+    // mono / stereo with everything 4-byte aligned: four output samples per thread, word loads, 16-byte stores
+    const bool wide = (ctx->nch == 1 || ctx->nch == 2) && ((pm0 - v.first) & 3) == 0 &&
+                      ((reinterpret_cast<unsigned long long>(v.d) | (v.block_shift < 0 ? (unsigned long long)v.stride : 0ULL)) & 3ULL) == 0 &&
+                      (reinterpret_cast<unsigned long long>(d_out) & 15ULL) == 0;
+    if (wide) {
+        const long long groups = (total + 3) / 4;
+        long long blocks = (groups + 255) / 256;
+        if (blocks > 64LL * ctx->sm_count) blocks = 64LL * ctx->sm_count;
+        if (ctx->nch == 1) dop_pack_wide_kernel<1><<<(int)blocks, 256, 0, st>>>(a, pm0, reverse_bits);
+        else dop_pack_wide_kernel<2><<<(int)blocks, 256, 0, st>>>(a, pm0, reverse_bits);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return DSDGPU_OK;
+    }
+    long long blocks = (total + 255) / 256;
+    if (blocks > 32LL * ctx->sm_count) blocks = 32LL * ctx->sm_count;
+    dop_pack_kernel<<<(int)blocks, 256, 0, st>>>(a, pm0, reverse_bits);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+int dsdgpu_dop_pack_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_stride, int64_t in_first, int64_t in_count,
+                           uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits, int32_t* d_out,
+                           void* cuda_stream) {
+    int rc = check_call(ctx, d_in, in_count, nframes, DSDGPU_OUT_INT32, d_out);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    SourceView v;
+    if (ctx->source_block == 1) {
+        int64_t lo = pm0, hi = pm0 + 2 * nframes + 1, first, count;
+        if (lo < in_first) lo = in_first;
+        if (hi > in_first + in_count) hi = in_first + in_count;
+        if (hi < lo) hi = lo;
+        size_t dstride;
+        rc = planar_from_interleaved(ctx, ctx->own, d_in, in_first, lo, hi, lo - 1, fill, st, dstride, first, count);
+        if (rc) return rc;
+        v.d = ctx->own.d_in; v.stride = dstride; v.first = first; v.count = count;
+    } else {
+        v.d = d_in; v.stride = in_stride; v.block_shift = block_shift_of(ctx->source_block); v.first = in_first; v.count = in_count;
+    }
+    rc = launch_dop(ctx, v, fill, pm0, nframes, reverse_bits, d_out, st);
+    if (rc) return rc;
+    if (!cuda_stream) CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return DSDGPU_OK;
+}
+
+int dsdgpu_dop_pack_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first, int64_t in_count,
+                         uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits, int32_t* out) {
+    int rc = check_call(ctx, in, in_count, nframes, DSDGPU_OUT_INT32, out);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const long long chunk = ctx->chunk_frames;
+    const int nslots = ctx->pipeline_slots;
+    bool inflight[DSDGPU_SLOTS] = {false};
+    long long k = 0;
+    for (int64_t f = 0; f < nframes && !rc; f += chunk, ++k) {
+        const int slot = (int)(k % nslots);
+        dsdgpu_slot& s = ctx->slots[slot];
+        if (inflight[slot]) { rc = dsdgpu_wait(ctx, slot); inflight[slot] = false; if (rc) break; }
+        if (s.busy) { rc = fail(ctx, DSDGPU_ERR_STATE, "slot %d is still in flight", slot); break; }
+        const int64_t n = nframes - f < chunk ? nframes - f : chunk;
+        const int64_t pm = pm0 + 2 * f;
+        int64_t lo = pm, hi = pm + 2 * n + 1;                       // frames f .. f+n-1 read bytes pm .. pm + 2n
+        if (lo < in_first) lo = in_first;
+        if (hi > in_first + in_count) hi = in_first + in_count;
+        if (hi < lo) hi = lo;
+        const size_t out_bytes = (size_t)n * ctx->nch * sizeof(int32_t);
+        rc = ensure(ctx, reinterpret_cast<unsigned char**>(&s.d_out), &s.out_cap, out_bytes);
+        if (rc) break;
+        SourceView v;
+        rc = stage_source(ctx, s, in, in_stride, in_first, in_count, fill, lo, hi, pm, lo, v);
+        if (rc) break;
+        rc = launch_dop(ctx, v, fill, pm, n, reverse_bits, static_cast<int32_t*>(s.d_out), s.stream);
+        if (rc) break;
+        if (cudaMemcpyAsync(out + (size_t)f * ctx->nch, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) {
+            rc = fail(ctx, DSDGPU_ERR_CUDA, "cudaMemcpyAsync failed");
+            break;
+        }
+        s.busy = true;
+        inflight[slot] = true;
+    }
+    for (int sidx = 0; sidx < DSDGPU_SLOTS; ++sidx)
+        if (inflight[sidx]) { int r2 = dsdgpu_wait(ctx, sidx); if (!rc) rc = r2; }
+    return rc;
 }
 
 int dsdgpu_wait(dsdgpu_ctx* ctx, int slot) {

@@ -4,6 +4,7 @@
 // the decimator byte by byte exactly as the DSF/DSDIFF readers do, the decimator drains it in
 // blocks and runs the FIR on the GPU through include/dsdgpu.h.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -190,6 +191,61 @@ int64_t dsdhost_convert_file(const char* path, int kind, uint32_t out_fs, double
     }
     if (pinned) dsdgpu_host_unregister(c.payload.data());
     return done;
+}
+
+// ---- DoP (reference dop_packer.cpp + dop_track_helper, main.cpp:294-403) -------------------------
+// The frames dop_track_helper emits for a whole file (--onefile: start 0, end getLength(),
+// main.cpp:423-424): creep with step() to position >= start, blocks of 1024 frames while position <=
+// end - 1024*16, single frames while position <= end; a frame advances the reader by two bytes.
+// Returns the number of frames; *pm0 = the reader's marker when the first frame is packed.
+static int64_t dop_app_frames(int64_t length_samples, int64_t* pm0) {
+    int64_t start = 0, end = length_samples;
+    if (start > length_samples - 1) start = length_samples - 1;
+    int64_t pm = -1, n = 0;
+    while (8 * pm < start) pm += 1;
+    *pm0 = pm;
+    if (8 * pm <= end - 1024 * 16) {
+        const int64_t blocks = (end - 1024 * 16 - 8 * pm) / (16 * 1024) + 1;
+        n += 1024 * blocks; pm += 2048 * blocks;
+    }
+    if (8 * pm <= end) n += (end - 8 * pm) / 16 + 1;
+    return n;
+}
+
+static int64_t dop_pack_all(const uint8_t* data, size_t stride, int64_t block_bytes, int64_t delivered, int nch,
+                            int64_t length_samples, uint8_t idle, int msb_flag, int32_t* out, int64_t out_cap_frames) {
+    int64_t pm0 = -1;
+    const int64_t n = dop_app_frames(length_samples, &pm0);
+    if (n > out_cap_frames) return -2;
+    const double dummy[256] = {0.0};                       // the packer uses no tables
+    dsdgpu_ctx* gpu = nullptr;
+    int device = 0;
+    if (const char* env = std::getenv("DSDGPU_DEVICE")) device = std::atoi(env);
+    if (dsdgpu_create(&gpu, device, nch, 1, 1, dummy, 64) != DSDGPU_OK) { g_error = dsdgpu_last_error(nullptr); return -1; }
+    int rc = dsdgpu_set_option(gpu, "source_block_bytes", block_bytes);
+    if (rc == DSDGPU_OK) rc = dsdgpu_dop_pack_host(gpu, data, stride, 0, delivered, idle, pm0, n, msb_flag, out);
+    if (rc != DSDGPU_OK) g_error = dsdgpu_last_error(gpu);
+    dsdgpu_destroy(gpu);
+    return rc == DSDGPU_OK ? n : -1;
+}
+
+// Planar bytes in memory -> DoP frames of a whole stream.
+int64_t dsdhost_dop_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples, uint8_t idle,
+                            int msb_flag, int32_t* out, int64_t out_cap_frames) {
+    int64_t delivered = (length_samples + 7) / 8 + 1;        // the reader hands out bytes 0 .. ceil(L/8), as far as they exist
+    if (delivered > nbytes) delivered = nbytes;
+    return dop_pack_all(planar, (size_t)nbytes, 0, delivered, nch, length_samples, idle, msb_flag, out, out_cap_frames);
+}
+
+// One DSF / DSDIFF file -> DoP frames, what `dsf2flac -d` computes before FLAC.
+int64_t dsdhost_dop_file(const char* path, int kind, int32_t* out, int64_t out_cap_frames) {
+    DsdContainer c;
+    if (!dsd_container_load(path, kind, c)) { g_error = c.error; return -1; }
+    const bool pinned = !c.payload.empty() && dsdgpu_host_register(c.payload.data(), c.payload.size()) == DSDGPU_OK;
+    const int64_t n = dop_pack_all(c.payload.data(), 0, c.blockBytes, c.deliveredBytes, (int)c.channels, c.lengthSamples,
+                                   c.idle, c.msbIsPlayedFirst ? 1 : 0, out, out_cap_frames);
+    if (pinned) dsdgpu_host_unregister(c.payload.data());
+    return n;
 }
 
 }  // extern "C"

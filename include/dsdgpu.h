@@ -160,6 +160,25 @@ int dsdgpu_dither_fill_device(dsdgpu_ctx* ctx, uint64_t first_sample, int64_t co
                               void* cuda_stream);
 
 /*
+ * DoP packing -- the other consumer of the same bytes.  Replaces: DopPacker::pack_buffer (reference
+ * src/dop_packer.cpp:100-141) for a run of frames:
+ *   pm_i = pm0 + 2*i + 1               (the reader's marker after the frame's first step())
+ *   out[i*nch + c] = marker(pm_i) + (B_c(pm_i - 1) << 8) + B_c(pm_i)
+ *   marker = 0x00050000 if (8*pm_i - 8) % 32 == 0 (C remainder) else 0xFFFA0000
+ * with both bytes bit-reversed when reverse_bits != 0 (reader->msbIsPlayedFirst(), :128-131).  pm0 is
+ * the reader's marker before the call: -1 right after rewind(), 0 after main.cpp's creep loop
+ * (main.cpp:362-364).  B_c, in_first/in_count/fill and the source layouts are those of the decimation
+ * calls; the context only supplies the channel count, streams and slots (its tables are not used).
+ * Bound: HBM / PCIe, 2 bytes in and 4 bytes out per output sample.
+ */
+int dsdgpu_dop_pack_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_stride, int64_t in_first,
+                           int64_t in_count, uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits,
+                           int32_t* d_out, void* cuda_stream);
+int dsdgpu_dop_pack_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first,
+                         int64_t in_count, uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits,
+                         int32_t* out);
+
+/*
  * Multi-GPU partitioning (no reference counterpart: the reference is one thread, its only batch
  * notion is the serial loop of scripts/batch_dsf2flac.sh:16-19).  Output sample (job, channel,
  * frame) depends only on nlut bytes of its own channel (dsd_decimator.cpp:193-198), so a batch

@@ -267,6 +267,58 @@ int64_t dsdoracle_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_
     return done;
 }
 
+/* ---- DoP packing (dop_packer.cpp:100-141) -------------------------------------------------
+ * pack_buffer, per frame: reader->step(); then for every channel the marker is 0x00050000 if
+ * (getPosition() - 8) % 32 == 0 else 0xFFFA0000 (C remainder), plus ring[1] << 8 (the byte before the
+ * newest) plus ring[0] (the newest), both bit-reversed when msbIsPlayedFirst(); reader->step() again.
+ * With pm = the reader's marker after the first step, getPosition() = 8*pm.  Starting right after
+ * rewind() (pre_steps = 0) every marker comes out 0xFFFA0000; main.cpp's creep loop (:362-364) takes
+ * one step() first, after which they alternate 0x05 / 0xFA as DoP requires.                       */
+static uint8_t reverse_bits(uint8_t b) {
+    b = (uint8_t)((b & 0xF0) >> 4 | (b & 0x0F) << 4);
+    b = (uint8_t)((b & 0xCC) >> 2 | (b & 0x33) << 2);
+    b = (uint8_t)((b & 0xAA) >> 1 | (b & 0x55) << 1);
+    return b;
+}
+
+int dsdoracle_dop_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                          uint8_t idle, int msb_flag, int64_t pre_steps, int64_t nframes, int32_t* out) {
+    byte_source src = {planar, nch, nbytes, length_samples, idle};
+    int64_t pm = -1 + pre_steps;
+    for (int64_t i = 0; i < nframes; ++i) {
+        pm += 1;
+        for (int c = 0; c < nch; ++c) {
+            int32_t v = ((8 * pm - 8) % 32 != 0) ? (int32_t)0xFFFA0000 : 0x00050000;
+            uint8_t b1 = source_byte(&src, c, pm - 1), b2 = source_byte(&src, c, pm);
+            if (msb_flag) { b1 = reverse_bits(b1); b2 = reverse_bits(b2); }
+            out[i * nch + c] = v + ((int32_t)b1 << 8) + (int32_t)b2;
+        }
+        pm += 1;
+    }
+    return 0;
+}
+
+/* dop_track_helper's loops for the --onefile case (main.cpp:300-306, 362-383): creep to position 0,
+ * blocks of 1024 frames while position <= end - 1024*16, then single frames while position <= end. */
+int64_t dsdoracle_dop_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
+                              uint8_t idle, int msb_flag, int32_t* out, int64_t out_cap_frames) {
+    int64_t start = 0, end = length_samples;
+    if (start > length_samples - 1) start = length_samples - 1;
+    int64_t pm = -1, done = 0;
+    while (8 * pm < start) pm += 1;
+    while (8 * pm <= end - 1024 * 16) {
+        if (done + 1024 > out_cap_frames) return -2;
+        dsdoracle_dop_run_raw(planar, nch, nbytes, length_samples, idle, msb_flag, pm + 1, 1024, out + done * nch);
+        done += 1024; pm += 2048;
+    }
+    while (8 * pm <= end) {
+        if (done + 1 > out_cap_frames) return -2;
+        dsdoracle_dop_run_raw(planar, nch, nbytes, length_samples, idle, msb_flag, pm + 1, 1, out + done * nch);
+        done += 1; pm += 2;
+    }
+    return done;
+}
+
 void dsdoracle_rand(int32_t* out, int64_t n, int64_t skip) {
     glibc_rand g;
     glibc_rand_seed(&g, 1);

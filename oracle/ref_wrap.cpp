@@ -17,6 +17,7 @@
 #define private public
 #include "dsd_decimator.h"
 #undef private
+#include "dop_packer.h"
 #include "dsdiff_file_reader.h"
 #include "dsf_file_reader.h"
 
@@ -243,6 +244,58 @@ int64_t dsdref_file_run_app(const char* path, int kind, uint32_t out_fs, double 
         }
     }
     close_reader(rd);
+    return done;
+}
+
+// ---- DoP: the reference's DopPacker (dop_packer.cpp) ------------------------------------------
+// rewind, `pre_steps` x reader step(), then pack_buffer in calls of `chunk_frames` frames (0 = one call).
+int dsdref_dop_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples, uint8_t idle,
+                       int msb_flag, int64_t pre_steps, int64_t nframes, int64_t chunk_frames, int32_t* out) {
+    MemoryReader rd(planar, nch, nbytes, length_samples, 2822400, msb_flag != 0, idle);
+    DopPacker dopp(&rd);
+    for (int64_t i = 0; i < pre_steps; ++i) rd.step();
+    if (chunk_frames <= 0) chunk_frames = nframes;
+    for (int64_t f = 0; f < nframes; f += chunk_frames) {
+        const int64_t n = nframes - f < chunk_frames ? nframes - f : chunk_frames;
+        dopp.pack_buffer(out + f * nch, (dsf2flac_uint32)(n * nch));
+    }
+    return 0;
+}
+
+// What `dsf2flac -d -i file` computes before FLAC: dop_track_helper's loops (main.cpp:300-306,
+// 362-383) with the --onefile bounds (:423-424), over the reference's own file reader.
+// Returns frames written, -1 reader invalid, -2 out too small.  One call per process (see above).
+int64_t dsdref_file_run_dop(const char* path, int kind, int32_t* out, int64_t out_cap_frames,
+                            int32_t* info, int64_t* length) {
+    DsdSampleReader* dsr = open_reader(path, kind);
+    if (!dsr || !dsr->isValid()) { close_reader(dsr); return -1; }
+    if (info) {
+        info[0] = (int32_t)dsr->getNumChannels();
+        info[1] = (int32_t)dsr->getSamplingFreq();
+        info[2] = dsr->msbIsPlayedFirst() ? 1 : 0;
+    }
+    if (length) *length = dsr->getLength();
+    int64_t done = 0;
+    {
+        const int nch = (int)dsr->getNumChannels();
+        dsf2flac_int64 startPos = 0, endPos = dsr->getLength();
+        if (startPos > dsr->getLength() - 1) startPos = dsr->getLength() - 1;
+        if (endPos > dsr->getLength()) endPos = dsr->getLength();
+        DopPacker dopp(dsr);
+        while (dsr->getPosition() < startPos) dsr->step();
+        const int block = 1024;
+        while (dsr->getPosition() <= endPos - block * 16) {
+            if (done + block > out_cap_frames) { done = -2; break; }
+            dopp.pack_buffer(out + done * nch, (dsf2flac_uint32)(nch * block));
+            done += block;
+        }
+        while (done >= 0 && dsr->getPosition() <= endPos) {
+            if (done + 1 > out_cap_frames) { done = -2; break; }
+            dopp.pack_buffer(out + done * nch, (dsf2flac_uint32)nch);
+            done += 1;
+        }
+    }
+    close_reader(dsr);
     return done;
 }
 

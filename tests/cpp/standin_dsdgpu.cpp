@@ -94,6 +94,33 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
     return DSDGPU_OK;
 }
 
+int dsdgpu_dop_pack_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, int64_t in_first, int64_t in_count,
+                         uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits, int32_t* out) {
+    auto rev = [](unsigned b) { unsigned r = 0; for (int k = 0; k < 8; ++k) r |= ((b >> k) & 1u) << (7 - k); return r; };
+    auto byte_at = [&](int c, int64_t j) -> unsigned {
+        const int64_t o = j - in_first;
+        if (o < 0 || o >= in_count) return fill;
+        const long long B = ctx->source_block;
+        const size_t at = B == 0 ? (size_t)c * in_stride + (size_t)o : B == 1 ? (size_t)o * ctx->nch + c
+                                 : (size_t)(((o / B) * ctx->nch + c) * B + o % B);
+        return in[at];
+    };
+    for (int64_t i = 0; i < nframes; ++i) {
+        const int64_t pm = pm0 + 2 * i + 1;
+        for (int c = 0; c < ctx->nch; ++c) {
+            unsigned b1 = byte_at(c, pm - 1), b2 = byte_at(c, pm);
+            if (reverse_bits) { b1 = rev(b1); b2 = rev(b2); }
+            out[i * ctx->nch + c] = (((8 * pm - 8) % 32 != 0) ? (int32_t)0xFFFA0000 : 0x00050000) + (int32_t)(b1 << 8) + (int32_t)b2;
+        }
+    }
+    ctx->launches += 1;
+    return DSDGPU_OK;
+}
+int dsdgpu_dop_pack_device(dsdgpu_ctx* ctx, const uint8_t*, size_t, int64_t, int64_t, uint8_t, int64_t, int64_t, int, int32_t*,
+                           void*) {
+    snprintf(ctx->err, sizeof ctx->err, "stand-in has no device");
+    return DSDGPU_ERR_NODEVICE;
+}
 int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t*, size_t, int64_t, int64_t, uint8_t, int64_t,
                            int64_t, double, double, double, uint64_t, int, void*, void*) {
     snprintf(ctx->err, sizeof ctx->err, "stand-in has no device");

@@ -99,6 +99,36 @@ class Oracle:
             raise RuntimeError(f"oracle run_app failed ({n})")
         return out[:n].copy()
 
+    def dop_run_raw(self, planar, length_samples, msb_flag, pre_steps, nframes, idle=0x69, chunk_frames=0):
+        """DopPacker::pack_buffer after rewind + pre_steps x reader step().  int32 [nframes, nch]."""
+        planar = np.ascontiguousarray(planar, dtype=np.uint8)
+        nch, nbytes = planar.shape
+        out = np.zeros((nframes, nch), dtype=np.int32)
+        f = self._fn("dop_run_raw")
+        f.restype = C.c_int
+        if self.reference:
+            f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _i64, _i64, _i64, _vp]
+            f(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), pre_steps, nframes, chunk_frames, out.ctypes.data)
+        else:
+            f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _i64, _i64, _vp]
+            f(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), pre_steps, nframes, out.ctypes.data)
+        return out
+
+    def dop_run_app(self, planar, length_samples, msb_flag, idle=0x69):
+        """dop_track_helper's loops for --onefile (oracle restatement only).  int32 [frames, nch]."""
+        assert not self.reference
+        planar = np.ascontiguousarray(planar, dtype=np.uint8)
+        nch, nbytes = planar.shape
+        cap = length_samples // 16 + 2048
+        out = np.zeros((cap, nch), dtype=np.int32)
+        f = self.lib.dsdoracle_dop_run_app
+        f.restype = _i64
+        f.argtypes = [_vp, C.c_int, _i64, _i64, C.c_uint8, C.c_int, _vp, _i64]
+        n = f(planar.ctypes.data, nch, nbytes, length_samples, idle, int(msb_flag), out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError(f"oracle dop_run_app failed ({n})")
+        return out[:n].copy()
+
     def rand(self, n, skip=0):
         out = np.zeros(n, dtype=np.int32)
         if self.reference:

@@ -4,6 +4,8 @@ the reference's readers keep "allocated" flags in file-scope statics (dsf_file_r
 dsdiff_file_reader.cpp:46-49), so a second reader in the same process would crash.
 
 usage: python -m tests.ref_file_runner <path> <kind:1=dsf|2=dff> <out_fs> <scale> <dither> <clip> <out.npz>
+       out_fs = 0 runs the DoP path instead (dsdref_file_run_dop: the reference's DopPacker in
+       dop_track_helper's loops); scale / dither / clip are then ignored.
 """
 import ctypes as C
 import sys
@@ -25,8 +27,13 @@ def main():
     length = C.c_int64(-1)
     out = np.zeros((cap, 8), dtype=np.int32)
     flat = np.zeros(cap * 8, dtype=np.int32)
-    n = lib.dsdref_file_run_app(path.encode(), int(kind), int(out_fs), float(scale), float(dither), float(clip), 1,
-                                flat.ctypes.data, cap, info, C.byref(length))
+    if int(out_fs) == 0:
+        lib.dsdref_file_run_dop.restype = C.c_int64
+        lib.dsdref_file_run_dop.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        n = lib.dsdref_file_run_dop(path.encode(), int(kind), flat.ctypes.data, cap, info, C.byref(length))
+    else:
+        n = lib.dsdref_file_run_app(path.encode(), int(kind), int(out_fs), float(scale), float(dither), float(clip), 1,
+                                    flat.ctypes.data, cap, info, C.byref(length))
     nch = max(1, info[0])
     pcm = flat[:max(n, 0) * nch].reshape(-1, nch)
     np.savez(dst, frames=n, channels=info[0], fs=info[1], msb=info[2], length=length.value, pcm=pcm)
