@@ -116,7 +116,7 @@ _CPU_DATA = None        # inherited by the forked workers (no pickling of the st
 
 
 def _cpu_worker(args):
-    seg_bytes, k, dsd_fs, out_fs, nlut, nstep, scale, clip = args
+    seg_bytes, k, dsd_fs, out_fs, nlut, nstep, scale, clip, reps = args
     data = _CPU_DATA
     from tests.oracle_lib import Oracle, REF_SO
     orc = Oracle(reference=os.path.exists(REF_SO))
@@ -124,18 +124,20 @@ def _cpu_worker(args):
     sub = np.ascontiguousarray(data[:, lo:lo + seg_bytes])
     nframes = (seg_bytes - nlut) // nstep
     t0 = time.perf_counter()
-    orc.run_raw(sub, 1 << 40, 1, dsd_fs, out_fs, nlut + 1, nframes, scale, 0.0, clip)
-    return nframes * nstep * 8 * data.shape[0], time.perf_counter() - t0
+    for _ in range(reps):
+        orc.run_raw(sub, 1 << 40, 1, dsd_fs, out_fs, nlut + 1, nframes, scale, 0.0, clip)
+    return reps * nframes * nstep * 8 * data.shape[0], time.perf_counter() - t0
 
 
-def cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, sample_seconds, pool=None):
+def cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, sample_seconds, pool=None, reps=1):
     """The reference's CPU decimator (getSamples loop only, like the GPU arm: no FLAC, no file
-    parsing) over the first `sample_seconds` of the stream, one process per core (the reference
-    is single threaded and keeps process-global state, so cores = processes).  -> (Mbit/s, bits)"""
+    parsing) over the first `sample_seconds` of the stream, `reps` times over, one process per core
+    (the reference is single threaded and keeps process-global state, so cores = processes).
+    -> (Mbit/s, bits, kind)"""
     from tests.oracle_lib import REF_SO
     nbytes = min(data.shape[1], int(dsd_fs // 8 * sample_seconds))
     seg = nbytes // cores // 4 * 4
-    jobs = [(seg, k, dsd_fs, out_fs, fir.nlut, fir.nstep, scale, clip) for k in range(cores)]
+    jobs = [(seg, k, dsd_fs, out_fs, fir.nlut, fir.nstep, scale, clip, reps) for k in range(cores)]
     own = pool is None
     if own:
         global _CPU_DATA
@@ -161,9 +163,9 @@ def run_reference_arm(args, wl):
     scale, _, clip = filters.app_params(bits_depth, dither=False)
     cores = len(os.sched_getaffinity(0))
     global _CPU_DATA
-    data = _CPU_DATA = synth_stream(dsd_fs, nch, min(seconds, 20))
+    data = _CPU_DATA = synth_stream(dsd_fs, nch, seconds)
     pool = mp.get_context("fork").Pool(cores)
-    # size the per-step sample so that the whole run stays within ~2 minutes
+    # a step is the whole file, like the GPU arm's, unless that would push the run past ~2 minutes
     probe, _, kind = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, 1.0, pool)
     budget_s = 100.0 / max(1, args.steps + args.warmup)
     sample_seconds = max(0.25, min(data.shape[1] * 8 / dsd_fs, budget_s * probe * 1e6 / (dsd_fs * nch)))
@@ -390,10 +392,14 @@ def run_gpu_arm(args, wl):
         cores = len(os.sched_getaffinity(0))
         cpu = None
         if world == 1 and args.cpu_seconds > 0:
-            v, b, kind = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, args.cpu_seconds)
-            v1, b1, _ = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, 1, min(args.cpu_seconds, 4.0))
+            # about args.cpu_seconds of wall time on every core: the whole file, as often as that takes
+            probe, _, kind = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, seconds)
+            reps = max(1, int(args.cpu_seconds * probe * 1e6 / bits_per_step))
+            v, b, kind = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, cores, seconds, reps=reps)
+            v1, b1, _ = cpu_reference_rate(data, dsd_fs, out_fs, fir, scale, clip, 1, seconds / 2)
             cpu = {"value": v, "unit": "Mbit/s", "cores": cores, "kind": kind,
-                   "sample": f"first {args.cpu_seconds:g} s of the stream, one process per core, decimator only",
+                   "sample": f"the whole {seconds} s file {reps} times over ({b / 1e9:.1f} Gbit), one process per core "
+                             f"(the reference is single threaded), decimator only",
                    "one_core": {"value": v1, "unit": "Mbit/s", "cores": 1, "x_realtime": v1 * 1e6 / (dsd_fs * nch)}}
         e2e_value = bits_per_step * args.steps * world / e2e_s / 1e6
         print(json.dumps({
@@ -630,7 +636,7 @@ def main():
     ap.add_argument("--files", type=int, default=256, help="files in the c5 batch (about 120 MB of pinned host memory each)")
     ap.add_argument("--slots", type=int, default=0, help="pipelined slots of the host entry point (1..4)")
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per pipelined host chunk")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="length of the CPU-baseline sample (stream seconds)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall seconds of CPU work in the cpu_baseline sample (0: skip)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
