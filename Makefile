@@ -9,7 +9,7 @@ PKG := dsf2flac_b200
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall \
            -I include -I $(PKG)/csrc
 HOSTSRC := $(PKG)/host/dsd_decimator.cpp $(PKG)/host/dsd_container.cpp $(PKG)/host/dsdhost_capi.cpp $(PKG)/host/dsd_synth.cpp
-HOSTHDR := $(wildcard $(PKG)/host/*.h) $(PKG)/host/dsd_filter_bits.inc include/dsdgpu.h
+HOSTHDR := $(wildcard $(PKG)/host/*.h) $(wildcard $(PKG)/host/*.inc) include/dsdgpu.h
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -I include -I $(PKG)/host
 
 all: gpu host oracle tests

@@ -38,6 +38,11 @@ WORKLOADS = {
     # the other two filters of the reference (dsd_decimator.cpp:57-65): same input, higher output rates
     "d16": (DSD64, 176400, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/176.4 kHz (divide-by-16 filter, 30 tables)"),
     "d8": (DSD64, 352800, 2, 60, 24, "DSD64 stereo 60 s -> 24-bit/352.8 kHz (divide-by-8 filter, 12 tables)"),
+    # EXTENSION filters (no reference counterpart): BASELINE configs[3] as literally stated
+    "x64": (8 * DSD64, 352800, 2, 60, 24, "DSD512 stereo 60 s -> 24-bit/352.8 kHz (divide-by-64 EXTENSION filter, 144 tables, "
+                                          "two passes of the segmented kernel)"),
+    "x128": (8 * DSD64, 176400, 2, 60, 24, "DSD512 stereo 60 s -> 24-bit/176.4 kHz (divide-by-128 EXTENSION filter, 288 tables)"),
+    "x256": (8 * DSD64, 88200, 2, 60, 24, "DSD512 stereo 60 s -> 24-bit/88.2 kHz (divide-by-256 EXTENSION filter, 576 tables)"),
 }
 # Sharded (strong-scaling) workloads, BASELINE configs[2..4]: (description, [(dsd_fs, out_fs, nch, seconds)...], lut, dither)
 def sharded_workloads(nfiles=256):
@@ -119,7 +124,10 @@ def _cpu_worker(args):
     seg_bytes, k, dsd_fs, out_fs, nlut, nstep, scale, clip, reps = args
     data = _CPU_DATA
     from tests.oracle_lib import Oracle, REF_SO
+    from dsf2flac_b200 import filters
     orc = Oracle(reference=os.path.exists(REF_SO))
+    if dsd_fs // out_fs not in filters.FILTERS:             # extension filter: the reference's arithmetic on it
+        orc.set_custom_filter(filters.EXTENSION_FILTERS[dsd_fs // out_fs])
     lo = k * seg_bytes
     sub = np.ascontiguousarray(data[:, lo:lo + seg_bytes])
     nframes = (seg_bytes - nlut) // nstep
@@ -159,7 +167,7 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     from dsf2flac_b200 import filters
-    fir = filters.pick(dsd_fs, out_fs)
+    fir = filters.pick(dsd_fs, out_fs, extensions=True)
     scale, _, clip = filters.app_params(bits_depth, dither=False)
     cores = len(os.sched_getaffinity(0))
     global _CPU_DATA
@@ -221,7 +229,7 @@ def run_gpu_arm(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    fir = filters.pick(dsd_fs, out_fs)
+    fir = filters.pick(dsd_fs, out_fs, extensions=True)
     lut = filters.build_lut(fir, 1)
     scale, amp, clip = filters.app_params(bits_depth, dither=args.dither)
     data = synth_stream(dsd_fs, nch, seconds)
@@ -230,7 +238,7 @@ def run_gpu_arm(args, wl):
     bits_per_step = nbytes * 8 * nch                       # DSD bits consumed per step per GPU
     g = capi.DsdGpu(lut, nch, fir.nstep, device=local, lut_precision=args.lut)
     if args.kernel:
-        g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2, "ring": 3}[args.kernel])
+        g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2, "ring": 3, "seg": 4}[args.kernel])
     if args.threads:
         g.set_option("threads", args.threads)
     if args.slots:
@@ -339,6 +347,7 @@ def run_gpu_arm(args, wl):
     plugin = None
     if rank == 0 and args.plugin_seconds > 0:
         host = capi.host_lib()
+        host.dsdhost_set_extension_filters(0 if fir.ratio in filters.FILTERS else 1)
         pb = min(nbytes, int(dsd_fs // 8 * args.plugin_seconds))
         cap = nframes + 2048
         out = capi.PinnedBuffer((cap, nch), np.int32)
@@ -630,7 +639,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c5", "dop"])
     ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
     ap.add_argument("--dither", type=int, default=0)
-    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring"])
+    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring", "seg"])
     ap.add_argument("--align", type=int, default=1, help="0: device buffer starts at stream byte 0 (frame grid off by one byte)")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--files", type=int, default=256, help="files in the c5 batch (about 120 MB of pinned host memory each)")

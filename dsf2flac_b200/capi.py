@@ -18,7 +18,7 @@ GPU_LIB = os.path.join(_HERE, "libdsdgpu.so")
 HOST_LIB = os.path.join(_HERE, "libdsdhost.so")
 
 OUT_INT32, OUT_FLOAT64 = 0, 1
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SKEW, KERNEL_RING = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SKEW, KERNEL_RING, KERNEL_SEGMENTED = 0, 1, 2, 3, 4
 ERR_NODEVICE = 3
 
 _u8p = C.POINTER(C.c_uint8)
@@ -87,6 +87,8 @@ def host_lib(path=None):
     i64, u32, dbl = C.c_int64, C.c_uint32, C.c_double
     lib.dsdhost_last_error.restype = C.c_char_p
     lib.dsdhost_last_error.argtypes = []
+    lib.dsdhost_set_extension_filters.restype = None
+    lib.dsdhost_set_extension_filters.argtypes = [C.c_int]
     lib.dsdhost_info.restype = C.c_int
     lib.dsdhost_info.argtypes = [u32, u32, i64, C.POINTER(C.c_int32), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
     lib.dsdhost_run_raw.restype = C.c_int

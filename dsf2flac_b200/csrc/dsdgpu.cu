@@ -17,6 +17,7 @@
 #include "dsdgpu.h"
 #include "skew_core.h"
 #include "ring_core.h"
+#include "seg_core.h"
 
 #include <cuda_runtime.h>
 
@@ -54,6 +55,12 @@ struct DecimateArgs {
     double unit;             // 32-bit tables: value of one table unit (2^-qbits); 1.0 otherwise
     void* out;
     int out_kind;
+    // multi-pass runs (filters longer than one shared-memory image): this launch adds
+    // tables [seg_first, seg_first + seg_n) to the running sum of every sample
+    int seg_first, seg_n;
+    const double* seg_init;  // [frame*nch + c] sums after tables 0..seg_first-1, or nullptr (start from 0.0)
+    double* seg_raw;         // where to leave the running sum instead of finishing the sample, or nullptr
+    long long plane_stride;  // ring kernel passes keep the running sums planar: [c*plane_stride + frame]
 };
 
 // Byte offset from a.in of source byte o (0 <= o < in_count) of channel c.  Planar rows, or the
@@ -99,25 +106,26 @@ __device__ __forceinline__ void store_sample(const DecimateArgs& a, long long fr
 // direct kernel: reference loop order, one thread per (channel, frame)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
-decimate_direct_kernel(DecimateArgs a, int nlut, int nstep) {
+decimate_direct_kernel(DecimateArgs a, int nstep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* lut_s = reinterpret_cast<double*>(smem_raw);
-    const double* lut_g = reinterpret_cast<const double*>(a.lut);
-    for (int i = threadIdx.x; i < nlut * 256; i += blockDim.x) lut_s[i] = lut_g[i];
+    const double* lut_g = reinterpret_cast<const double*>(a.lut) + (size_t)a.seg_first * 256;
+    for (int i = threadIdx.x; i < a.seg_n * 256; i += blockDim.x) lut_s[i] = lut_g[i];
     __syncthreads();
     const long long total = a.nframes * a.nch;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long f = idx / a.nch;               // idx is the output index: stores coalesce
         const int c = (int)(idx - f * a.nch);
-        const long long p = a.p0 + f * nstep;
-        double sum = 0.0;
-        for (int t = 0; t < nlut; ++t) {
+        const long long p = a.p0 + f * nstep - a.seg_first;
+        double sum = a.seg_init ? a.seg_init[idx] : 0.0;
+        for (int t = 0; t < a.seg_n; ++t) {
             const long long o = p - t - a.in_first;
             const unsigned b = (o >= 0 && o < a.in_count) ? (unsigned)a.in[src_offset(a, c, o)] : a.fill;
             sum = __dadd_rn(sum, lut_s[t * 256 + b]);
         }
-        store_sample(a, f, c, sum);
+        if (a.seg_raw) a.seg_raw[idx] = sum;
+        else store_sample(a, f, c, sum);
     }
 }
 
@@ -247,6 +255,154 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_skew_kernel(DecimateArgs 
 }
 
 // ---------------------------------------------------------------------------------------------
+// segmented kernel (seg_core.h): any geometry, one segment of the filter's tables per launch
+// ---------------------------------------------------------------------------------------------
+// Tile = NT = 512 * KS consecutive output samples (frame-major, channel-minor: stores and the reads /
+// writes of the running sums coalesce).  Byte buffer of a tile: one row per channel, row c holding
+// stream bytes [t0, t0 + row_stride) of channel c.
+struct SegTile {
+    long long t0;            // stream index of byte 0 of every row
+    long long i0;            // first output sample
+};
+
+template <int KS>
+__device__ __forceinline__ SegTile seg_tile_at(const DecimateArgs& a, long long tile, int nstep, int nsteps) {
+    SegTile t;
+    t.i0 = tile * (long long)(SegLayout::NTHR * KS);
+    const long long f_lo = t.i0 / a.nch;
+    const long long pmin = a.p0 + f_lo * nstep - a.seg_first;        // newest byte of the tile's first frame, this segment's tap 0
+    long long rel = pmin - nsteps - 16 - a.in_first;                  // lane 0 reads down to pmin - (nsteps - 1)
+    rel = (rel >= 0) ? (rel & ~15LL) : -((-rel + 15) & ~15LL);
+    t.t0 = a.in_first + rel;
+    return t;
+}
+
+__device__ __forceinline__ void seg_stage_tile(const DecimateArgs& a, long long t0, int row_stride, unsigned char* dst,
+                                               bool aligned16) {
+    const int chunks_per_row = row_stride / 16;
+    const long long o0 = t0 - a.in_first;
+    for (int k = threadIdx.x; k < a.nch * chunks_per_row; k += SegLayout::NTHR) {
+        const int c = k / chunks_per_row, kk = k - c * chunks_per_row;
+        const long long o = o0 + 16LL * kk;
+        unsigned char* d = dst + c * row_stride + 16 * kk;
+        if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
+            cp_async16(d, a.in + src_offset(a, c, o));
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const long long ob = o + 4 * q + b;
+                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
+                    v |= byte << (8 * b);
+                }
+                w[q] = v;
+            }
+            *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(DecimateArgs a, int nstep, int row_stride) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [0, LUT_BYTES): table image of this segment; then two byte tiles of nch * row_stride bytes.
+    constexpr int NTHR = SegLayout::NTHR, NT = NTHR * KS;
+    const int tid = threadIdx.x;
+    {
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
+        for (int k = tid; k < SegLayout::LUT_BYTES / 16; k += NTHR) cp_async16(smem + 16 * k, img + 16 * k);
+    }
+    const long long total = a.nframes * a.nch;
+    const long long ntiles = (total + NT - 1) / NT;
+    const bool aligned16 = src_aligned16(a);
+    const int nsteps = (a.seg_n + 15 + 3) / 4 * 4, ngroups = nsteps / 4;
+    const int tile_bytes = a.nch * row_stride;
+    const int j = tid & 15;
+    const uint32_t lut0 = (uint32_t)(SegLayout::GUARD_BYTES - 8 * j);
+
+    long long tile = blockIdx.x;
+    int buf = 0;
+    SegTile tl = seg_tile_at<KS>(a, tile, nstep, nsteps);
+    if (tile < ntiles) seg_stage_tile(a, tl.t0, row_stride, smem + SegLayout::LUT_BYTES, aligned16);
+    cp_async_commit();
+    while (tile < ntiles) {
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+            const SegTile tn = seg_tile_at<KS>(a, next, nstep, nsteps);
+            seg_stage_tile(a, tn.t0, row_stride, smem + SegLayout::LUT_BYTES + (buf ^ 1) * tile_bytes, aligned16);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();          // everything but the group just committed has landed
+        __syncthreads();
+
+        const uint32_t tile_off = (uint32_t)(SegLayout::LUT_BYTES + buf * tile_bytes);
+        double acc[KS];
+        uint32_t wlo[KS], lo[KS], shift[KS];
+        int fl[KS], ch[KS];          // frame (relative to the tile's first) and channel of each sample; fl < 0: past the end
+        const long long f_lo = tl.i0 / a.nch;
+        const unsigned r0 = (unsigned)(tl.i0 - f_lo * a.nch);
+        const long long left = total - tl.i0;                                 // samples from the tile's first to the end
+        const int pbase = (int)(a.p0 + f_lo * nstep - a.seg_first - tl.t0) + j;    // byte of step 0 of frame f_lo
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            unsigned n = (unsigned)(tid + k * NTHR);
+            const bool live = (long long)n < left;
+            if (!live) n = (unsigned)(left - 1);                               // lanes past the end recompute the last sample
+            const unsigned q = (r0 + n) / (unsigned)a.nch;
+            const int c = (int)(r0 + n - q * (unsigned)a.nch);
+            const int aoff = c * row_stride + pbase + (int)q * nstep;
+            const int phi = (aoff + 1) & 3;
+            shift[k] = 8u * (uint32_t)phi;
+            wlo[k] = tile_off + (uint32_t)(aoff - 3 - phi);
+            lo[k] = lds_u32(smem, wlo[k] + 4u);
+            acc[k] = a.seg_init ? a.seg_init[tl.i0 + n] : 0.0;
+            fl[k] = live ? (int)q : -1;
+            ch[k] = c;
+        }
+        uint32_t lut = lut0;
+#pragma unroll 2
+        for (int g = 0; g < ngroups; ++g) {
+            uint32_t x[KS];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const uint32_t hi = lo[k];
+                lo[k] = lds_u32(smem, wlo[k]);
+                wlo[k] -= 4u;
+                x[k] = funnel_r(lo[k], hi, shift[k]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    uint32_t e;
+                    if (u == 0) e = byte_of<3>(x[k]);
+                    else if (u == 1) e = byte_of<2>(x[k]);
+                    else if (u == 2) e = byte_of<1>(x[k]);
+                    else e = byte_of<0>(x[k]);
+                    acc[k] = __dadd_rn(acc[k], lds_f64(smem, e * (uint32_t)SegLayout::ROW_BYTES + lut + 8u * (uint32_t)u));
+                }
+            }
+            lut += 32u;
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            if (fl[k] >= 0) {
+                if (a.seg_raw) a.seg_raw[tl.i0 + tid + k * NTHR] = acc[k];
+                else store_sample(a, f_lo + fl[k], ch[k], acc[k]);
+            }
+        }
+        __syncthreads();             // tile `buf` is free again
+        tile = next;
+        buf ^= 1;
+        if (tile < ntiles) tl = seg_tile_at<KS>(a, tile, nstep, nsteps);
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // ring kernel
 // ---------------------------------------------------------------------------------------------
 // Stage both halves of a tile: bytes [t0_h, t0_h + HALF_BYTES) of channel c_h.
@@ -294,19 +450,23 @@ struct RingDest {
 // The ring kernel's emitter (protocol: ring_core.h, RingNoEmit): dsd_decimator.cpp:199-216 as
 // straight-line code -- scale, dither, clip by selects, C round() as trunc + exact remainder test,
 // saturating double->int -- and frame-pair stores.  Called from inside the main steps.
-template <bool F64OUT, bool DITHER>
+// OUT: 0 = int32 PCM, 1 = fp64 (scaled, dithered, clipped), 2 = the raw running sum into the planar plane
+// a.seg_raw (first pass of a two-pass filter).  INIT: sums start from the planar plane a.seg_init (second pass).
+template <int OUT, bool DITHER, bool INIT>
 struct RingEmitter {
     const DecimateArgs& a;
-    RingDest d;
+    RingDest d, nx;              // the frames being finished / the frames the lane starts in the next period
     int h;
     bool out_aligned16;
     int vi[4];
     double vd[4];
+    double iv[4];
 
-    __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, int h_, bool al)
-        : a(a_), d(d_), h(h_), out_aligned16(al) {}
+    __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, const RingDest& nx_, int h_, bool al)
+        : a(a_), d(d_), nx(nx_), h(h_), out_aligned16(al) {}
 
     __device__ __forceinline__ void quantise(int k, double sum) {
+        if (OUT == 2) { vd[k] = sum; return; }
         double x = __dmul_rn(sum, a.scale);
         if (DITHER) {
             const long long f = d.fb + k < a.nframes ? d.fb + k : 0;     // keep the load in bounds
@@ -315,7 +475,7 @@ struct RingEmitter {
         const bool clipping = a.clip > 0.0;
         x = (clipping && x > a.clip) ? a.clip : x;
         x = (clipping && x < -a.clip) ? -a.clip : x;
-        if (F64OUT) {
+        if (OUT == 1) {
             vd[k] = x;
         } else {
             // round(): half away from zero.  x - trunc(x) is exact, so this is C's round() bit for bit.
@@ -326,9 +486,36 @@ struct RingEmitter {
         }
     }
 
+    // running sums the lane's next four frames start from (planar plane: 32 contiguous bytes per lane)
+    __device__ __forceinline__ void prefetch() {
+        if (!INIT) return;
+        const double* src = a.seg_init + (long long)nx.c * a.plane_stride + nx.fb;
+        if (nx.fb + 3 < a.nframes) {
+            const double2 u = __ldg(reinterpret_cast<const double2*>(src));
+            const double2 v = __ldg(reinterpret_cast<const double2*>(src) + 1);
+            iv[0] = u.x; iv[1] = u.y; iv[2] = v.x; iv[3] = v.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) iv[k] = nx.fb + k < a.nframes ? __ldg(src + k) : 0.0;
+        }
+    }
+    __device__ __forceinline__ double init(int k) const { return INIT ? iv[k] : 0.0; }
+
     __device__ __forceinline__ void store() {
         const long long fb = d.fb, nf = a.nframes;
-        if (F64OUT) {
+        if (OUT == 2) {
+            double* dst = a.seg_raw + (long long)d.c * a.plane_stride + fb;
+            if (fb + 3 < nf) {
+                reinterpret_cast<double2*>(dst)[0] = make_double2(vd[0], vd[1]);
+                reinterpret_cast<double2*>(dst)[1] = make_double2(vd[2], vd[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (fb + k < nf) dst[k] = vd[k];
+            }
+            return;
+        }
+        if (OUT == 1) {
             double* out = reinterpret_cast<double*>(a.out);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -367,7 +554,7 @@ struct RingEmitter {
 //   empty[b]  a thread arrives when it has read buffer b for the last time (after the first 16
 //             steps of the NEXT tile, which still finish frames of this one); the buffer is
 //             refilled another tile later, so that wait does not block either.
-template <class G, bool F64OUT, bool DITHER>
+template <class G, int OUT, bool DITHER, bool INIT>
 __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     // [0, LUT_BYTES): table image; three tiles of two byte buffers each; six mbarriers.
@@ -404,10 +591,19 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
 
     RingDest prev;                   // nothing to emit in the very first period: every store is off
     prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
+    if (INIT) {                      // second pass: the sums of the first tile's frames start from the plane
+        const int c = h ? tl.c[1] : tl.c[0];
+        const long long fb = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            lane.n[k] = fb + k < a.nframes ? (typename RingLane<G>::acc_t)a.seg_init[(long long)c * a.plane_stride + fb + k] : 0;
+    }
     int b = 0, use = 0;              // buffer of the current tile, how often it has been used before
     for (long long i = 0; tile < ntiles; ++i) {
         const long long next = tile + gridDim.x;
         const int bn = b + 1 == NBUF ? 0 : b + 1;
+        RingDest after;              // first frames of the next tile (INIT: where the next period's sums start)
+        after.fb = a.nframes; after.c = 0; after.c0 = 0; after.pair = false;
         if (next < ntiles) {
             // buffer bn last held tile i-2; its use count is `use` when bn > b, else use + 1, minus one
             if (i + 1 >= NBUF) mbar_wait(&empty[bn], (unsigned)(((i + 1) / NBUF - 1) & 1));
@@ -415,6 +611,10 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16);
             __threadfence_block();
             mbar_arrive_after_cp_async(&full[bn]);
+            if (INIT) {
+                after.c = h ? tn.c[1] : tn.c[0];
+                after.fb = (h ? tn.f0[1] : tn.f0[0]) + 4LL * (16 * w + (l & 15));
+            }
         }
         mbar_wait(&full[b], (unsigned)(use & 1));
         RingDest cur;
@@ -427,7 +627,10 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             const uint32_t wnew = w0 + (uint32_t)(b * G::TILE_BYTES + n * G::HOP);
             ring_head<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
             if (n == 0 && i > 0) mbar_arrive(&empty[b == 0 ? NBUF - 1 : b - 1]);   // done with the previous tile's bytes
-            RingEmitter<F64OUT, DITHER> emit(a, prev, h, out_aligned16);
+            RingDest nx = cur;           // the frames this lane starts in the next period
+            nx.fb += 4LL * G::BLK_PER_ROUND;
+            if (n + 1 == G::KR) nx = after;
+            RingEmitter<OUT, DITHER, INIT> emit(a, prev, nx, h, out_aligned16);
             ring_tail<G>(lane, smem, wnew, loff, tid, n, emit, RingNoTrace());
             prev = cur;
             cur.fb += 4LL * G::BLK_PER_ROUND;
@@ -439,7 +642,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     }
     // the one drain of this CTA: 16 more steps finish the last frames
     ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
-    RingEmitter<F64OUT, DITHER> emit(a, prev, h, out_aligned16);
+    RingEmitter<OUT, DITHER, INIT> emit(a, prev, prev, h, out_aligned16);
 #pragma unroll
     for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));
     emit.store();
@@ -695,6 +898,8 @@ struct dsdgpu_slot {
     size_t out_cap = 0;
     double* d_dither = nullptr;
     size_t dither_cap = 0;
+    double* d_partial = nullptr;             // running fp64 sums between the passes of a long filter
+    size_t partial_cap = 0;
     bool busy = false;
 };
 
@@ -709,6 +914,8 @@ struct dsdgpu_ctx {
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
     unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only): fp64 or 32-bit entries
+    unsigned char* d_lut_seg = nullptr;      // nseg x SegLayout::LUT_BYTES images, SEG_DEFAULT tables each (any geometry)
+    int nseg = 0;
     double lut_unit = 1.0;                   // 32-bit tables: 2^-qbits
     std::vector<uint32_t> rand_pow16;        // host: x^(d * 16^k), d < 16, k < 12, [k][d][31]
     std::vector<uint32_t> rand_base;         // host: seed words r[3..94]
@@ -730,6 +937,7 @@ using Ring16x2 = RingGeom<16, 2>;
 using Ring16x2Q = RingGeom<16, 2, true>;
 using Ring30 = RingGeom<16, 2, false, 30, 2>;   // divide-by-16 filter: 30 tables, 2 bytes per frame
 using Ring12 = RingGeom<16, 2, false, 12, 1>;   // divide-by-8 filter: 12 tables, 1 byte per frame
+using Ring64 = RingGeom<16, 1, false, 72, 8>;   // one pass (72 of 144 tables) of the divide-by-64 extension filter
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -752,6 +960,7 @@ void free_slot(dsdgpu_slot& s) {
     if (s.d_raw) cudaFree(s.d_raw);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_dither) cudaFree(s.d_dither);
+    if (s.d_partial) cudaFree(s.d_partial);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = dsdgpu_slot();
 }
@@ -836,42 +1045,118 @@ int launch_skew(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     return DSDGPU_OK;
 }
 
-template <class G, bool F64OUT, bool DITHER>
+template <class G, int OUT, bool DITHER, bool INIT>
 int launch_ring_variant(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     const int smem = G::SMEM_BYTES;
     static thread_local int configured_device = -1;
     if (configured_device != ctx->device) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_ring_kernel<G, F64OUT, DITHER>,
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_ring_kernel<G, OUT, DITHER, INIT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured_device = ctx->device;
     }
     const long long tiles = ring_tile_count<G>(a.nframes, a.nch);
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    decimate_ring_kernel<G, F64OUT, DITHER><<<grid, G::NTHR, smem, st>>>(a);
+    decimate_ring_kernel<G, OUT, DITHER, INIT><<<grid, G::NTHR, smem, st>>>(a);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
 }
 
-template <class G>
+template <class G, bool INIT = false>
 int launch_ring(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     const bool f64 = a.out_kind != DSDGPU_OUT_INT32, dith = a.dither != nullptr;
-    if (f64) return dith ? launch_ring_variant<G, true, true>(ctx, a, st) : launch_ring_variant<G, true, false>(ctx, a, st);
-    return dith ? launch_ring_variant<G, false, true>(ctx, a, st) : launch_ring_variant<G, false, false>(ctx, a, st);
+    if (f64) return dith ? launch_ring_variant<G, 1, true, INIT>(ctx, a, st) : launch_ring_variant<G, 1, false, INIT>(ctx, a, st);
+    return dith ? launch_ring_variant<G, 0, true, INIT>(ctx, a, st) : launch_ring_variant<G, 0, false, INIT>(ctx, a, st);
 }
 
-int launch_direct(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
-    const int smem = ctx->nlut * 256 * (int)sizeof(double);
+// Decimation by 64 (EXTENSION filter, 144 tables): two passes of the ring kernel with 8-byte frame hop.
+// Pass 1 adds tables 0..71 and leaves the running sums in a planar fp64 plane; pass 2 starts from them,
+// adds tables 72..143 -- the byte of table 72 + t at frame position p is the byte of table t at p - 72 --
+// and finishes the samples.  The reference's sequential sum over all tables, cut once, bit for bit.
+template <class G>
+int launch_ring_two_pass(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+    a.plane_stride = (a.nframes + 3) & ~3LL;
+    int rc = ensure(ctx, &scratch.d_partial, &scratch.partial_cap, (size_t)a.plane_stride * a.nch * sizeof(double));
+    if (rc) return rc;
+    DecimateArgs first = a;
+    first.lut = ctx->d_lut_ring;
+    first.seg_raw = scratch.d_partial;
+    first.dither = nullptr;
+    rc = launch_ring_variant<G, 2, false, false>(ctx, first, st);
+    if (rc) return rc;
+    a.lut = ctx->d_lut_ring + G::LUT_BYTES;
+    a.p0 -= G::NLUT;
+    a.seg_init = scratch.d_partial;
+    return launch_ring<G, true>(ctx, a, st);
+}
+
+// The running sums of a multi-pass run live in scratch.d_partial, [frame*nch + c].
+int ensure_partial(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const DecimateArgs& a) {
+    return ensure(ctx, &scratch.d_partial, &scratch.partial_cap, (size_t)a.nframes * a.nch * sizeof(double));
+}
+
+// Direct kernel, in passes of up to 96 tables (what fits its [t][byte] shared-memory layout).
+int launch_direct(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+    constexpr int kSeg = 96;
     static thread_local int configured_device = -1;
     if (configured_device != ctx->device) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 256 * 8));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeg * 256 * 8));
         configured_device = ctx->device;
     }
     const long long total = a.nframes * a.nch;
     long long blocks = (total + 1023) / 1024;
     if (blocks > ctx->sm_count) blocks = ctx->sm_count;
-    decimate_direct_kernel<<<(int)blocks, 1024, smem, st>>>(a, ctx->nlut, ctx->nstep);
+    const int npass = (ctx->nlut + kSeg - 1) / kSeg;
+    if (npass > 1) { int rc = ensure_partial(ctx, scratch, a); if (rc) return rc; }
+    for (int s = 0; s < npass; ++s) {
+        a.seg_first = s * kSeg;
+        a.seg_n = ctx->nlut - a.seg_first < kSeg ? ctx->nlut - a.seg_first : kSeg;
+        a.seg_init = s > 0 ? scratch.d_partial : nullptr;
+        a.seg_raw = s + 1 < npass ? scratch.d_partial : nullptr;
+        decimate_direct_kernel<<<(int)blocks, 1024, a.seg_n * 256 * (int)sizeof(double), st>>>(a, ctx->nstep);
+        ctx->launches += 1;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+// Segmented kernel: one launch per SEG_DEFAULT tables, running sums in between.  KS (samples per
+// thread) is the largest of 4, 2, 1 whose two byte tiles fit beside the table image.
+template <int KS>
+int launch_seg_pass(dsdgpu_ctx* ctx, const DecimateArgs& a, int row_stride, int smem, cudaStream_t st) {
+    static thread_local int configured_device = -1;
+    if (configured_device != ctx->device) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_seg_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SegLayout::SMEM_LIMIT));
+        configured_device = ctx->device;
+    }
+    const long long total = a.nframes * a.nch, nt = SegLayout::NTHR * KS;
+    const long long tiles = (total + nt - 1) / nt;
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    decimate_seg_kernel<KS><<<grid, SegLayout::NTHR, smem, st>>>(a, ctx->nstep, row_stride);
     ctx->launches += 1;
+    return DSDGPU_OK;
+}
+
+int launch_seg(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+    if (!ctx->d_lut_seg) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: no table images");
+    int ks = 4;
+    while (ks >= 1 && SegLayout::smem_bytes(SegLayout::NTHR * ks, ctx->nch, ctx->nstep) > SegLayout::SMEM_LIMIT) ks >>= 1;
+    if (ks < 1) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: %d channels x %d bytes per frame do not fit shared memory", ctx->nch, ctx->nstep);
+    const int samples = SegLayout::NTHR * ks;
+    const int row_stride = (int)SegLayout::row_stride(samples, ctx->nch, ctx->nstep);
+    const int smem = (int)SegLayout::smem_bytes(samples, ctx->nch, ctx->nstep);
+    if (ctx->nseg > 1) { int rc = ensure_partial(ctx, scratch, a); if (rc) return rc; }
+    for (int s = 0; s < ctx->nseg; ++s) {
+        a.seg_first = s * SegLayout::SEG_DEFAULT;
+        a.seg_n = ctx->nlut - a.seg_first < SegLayout::SEG_DEFAULT ? ctx->nlut - a.seg_first : SegLayout::SEG_DEFAULT;
+        a.seg_init = s > 0 ? scratch.d_partial : nullptr;
+        a.seg_raw = s + 1 < ctx->nseg ? scratch.d_partial : nullptr;
+        a.lut = ctx->d_lut_seg + (size_t)s * SegLayout::LUT_BYTES;
+        int rc = ks == 4 ? launch_seg_pass<4>(ctx, a, row_stride, smem, st)
+               : ks == 2 ? launch_seg_pass<2>(ctx, a, row_stride, smem, st)
+                         : launch_seg_pass<1>(ctx, a, row_stride, smem, st);
+        if (rc) return rc;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
 }
@@ -919,6 +1204,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
     a.unit = ctx->lut_unit;
     a.out = d_out; a.out_kind = out_kind;
+    a.seg_first = 0; a.seg_n = ctx->nlut; a.seg_init = nullptr; a.seg_raw = nullptr; a.plane_stride = 0;
     if (dither_amp > 0.0) {
         const long long count = (nframes - 1) * a.dither_stride + ctx->nch;
         int rc = ensure(ctx, &scratch.d_dither, &scratch.dither_cap, (size_t)count * sizeof(double));
@@ -931,10 +1217,12 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     const bool ring_ok = ctx->d_lut_ring != nullptr;
     int kernel = ctx->kernel;
     if (kernel == DSDGPU_KERNEL_AUTO)
-        kernel = ring_ok ? DSDGPU_KERNEL_RING : skew_ok ? DSDGPU_KERNEL_SKEW : DSDGPU_KERNEL_DIRECT;
+        kernel = ring_ok ? DSDGPU_KERNEL_RING : skew_ok ? DSDGPU_KERNEL_SKEW
+               : ctx->d_lut_seg ? DSDGPU_KERNEL_SEGMENTED : DSDGPU_KERNEL_DIRECT;
     if (kernel == DSDGPU_KERNEL_RING) {
-        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) and tables without -0.0 entries");
+        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) or of the divide-by-64 extension (144/8), and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
+        if (ctx->nlut == 144) return launch_ring_two_pass<Ring64>(ctx, scratch, a, st);
         if (ctx->nlut == 30) return launch_ring<Ring30>(ctx, a, st);
         if (ctx->nlut == 12) return launch_ring<Ring12>(ctx, a, st);
         // (a 1024-thread instance of the 32-bit kernel fits in 64 registers but runs 13 % slower)
@@ -946,8 +1234,9 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         a.lut = ctx->d_lut_skew;
         return ctx->threads == 1024 ? launch_skew<Skew1024>(ctx, a, st) : launch_skew<Skew512>(ctx, a, st);
     }
+    if (kernel == DSDGPU_KERNEL_SEGMENTED) return launch_seg(ctx, scratch, a, st);
     a.lut = ctx->d_lut_direct;
-    return launch_direct(ctx, a, st);
+    return launch_direct(ctx, scratch, a, st);
 }
 
 }  // namespace
@@ -961,7 +1250,7 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
                   int lut_precision) {
     if (!out) return fail(nullptr, DSDGPU_ERR_ARG, "null ctx pointer");
     *out = nullptr;
-    if (nch < 1 || nlut < 1 || nlut > 96 || nstep < 1 || !lut)
+    if (nch < 1 || nlut < 1 || nlut > DSDGPU_MAX_TABLES || nstep < 1 || nstep > 64 || !lut)
         return fail(nullptr, DSDGPU_ERR_ARG, "bad geometry nch=%d nlut=%d nstep=%d", nch, nlut, nstep);
     if (lut_precision != 64 && lut_precision != 32)
         return fail(nullptr, DSDGPU_ERR_ARG, "lut_precision must be 64 or 32");
@@ -1040,10 +1329,28 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     } else if (nlut == 12 && nstep == 1 && plain) {
         rimg.resize(Ring12::LUT_BYTES);
         ring_build_lut_image<Ring12>(tab.data(), rimg.data());
+    } else if (nlut == 144 && nstep == 8 && plain && lut_precision == 64) {
+        // divide-by-64 extension filter: one image per pass of 72 tables
+        rimg.resize(2 * (size_t)Ring64::LUT_BYTES);
+        ring_build_lut_image<Ring64>(tab.data(), rimg.data());
+        ring_build_lut_image<Ring64>(tab.data() + (size_t)72 * 256, rimg.data() + Ring64::LUT_BYTES);
     }
     if (!rimg.empty()) {
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));
         CREATE_TRY(cudaMemcpy(ctx->d_lut_ring, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        // segmented kernel: one image per SEG_DEFAULT tables (fp64 entries; the 32-bit variant's rounded
+        // tables sum exactly in fp64 too, so it returns the integer kernel's bits)
+        ctx->nseg = (nlut + SegLayout::SEG_DEFAULT - 1) / SegLayout::SEG_DEFAULT;
+        std::vector<unsigned char> simg((size_t)ctx->nseg * SegLayout::LUT_BYTES);
+        for (int sidx = 0; sidx < ctx->nseg; ++sidx) {
+            const int first = sidx * SegLayout::SEG_DEFAULT;
+            seg_build_lut_image(tab.data(), first, nlut - first < SegLayout::SEG_DEFAULT ? nlut - first : SegLayout::SEG_DEFAULT,
+                                simg.data() + (size_t)sidx * SegLayout::LUT_BYTES);
+        }
+        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_seg), simg.size()));
+        CREATE_TRY(cudaMemcpy(ctx->d_lut_seg, simg.data(), simg.size(), cudaMemcpyHostToDevice));
     }
     // dither generator constants
     {
@@ -1110,6 +1417,7 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     if (ctx->d_lut_direct) cudaFree(ctx->d_lut_direct);
     if (ctx->d_lut_skew) cudaFree(ctx->d_lut_skew);
     if (ctx->d_lut_ring) cudaFree(ctx->d_lut_ring);
+    if (ctx->d_lut_seg) cudaFree(ctx->d_lut_seg);
     if (ctx->d_rand_lane) cudaFree(ctx->d_rand_lane);
     if (ctx->d_rand_jump) cudaFree(ctx->d_rand_jump);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1121,7 +1429,7 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx) { return ctx ? ctx->err : g
 int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     if (!ctx || !key) return DSDGPU_ERR_ARG;
     if (!strcmp(key, "kernel")) {
-        if (value < DSDGPU_KERNEL_AUTO || value > DSDGPU_KERNEL_RING) return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
+        if (value < DSDGPU_KERNEL_AUTO || value > DSDGPU_KERNEL_SEGMENTED) return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
         ctx->kernel = (int)value;
     } else if (!strcmp(key, "threads")) {
         if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");

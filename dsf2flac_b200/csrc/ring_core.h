@@ -59,6 +59,13 @@ namespace dsdgpu {
 // Other filters (NLUT = 30 tables, 2 bytes per frame; NLUT = 12, 1 byte per frame): the period is
 // NLUT rounded up to a multiple of 16 steps, the extra slots hold -0.0 (the identity of fp64
 // addition), so a wrapped lane needs no second copy: slot PERIOD + s - j is bank pair (s - j) mod 16.
+//
+// NSTEP = 8 (EXTENSION, decimation by 64: 144 tables, run as two passes of 72 over a plane of running
+// sums): frames lie 8 bytes apart, so frame k of a lane reads the word stream of frame 0 shifted by
+// 2k words -- six history words instead of three -- and a lane's sums start from the previous pass's
+// value (Emit::init) instead of 0.  Lanes are 32 bytes apart; the identity skew puts the 16 window
+// words of a half-warp in 16 distinct banks (8i + (i >> 2) mod 32), and the byte buffer of the upper
+// half starts 16 bytes further on so that its 16 words take the other 16 banks.
 template <int NWARP_, int KR_, bool Q32_ = false, int NLUT_ = 72, int NSTEP_ = 4>
 struct RingGeom {
     static constexpr bool Q32 = Q32_;
@@ -86,16 +93,17 @@ struct RingGeom {
     static constexpr int NTP = KR * FR_PER_ROUND;     // frames per half per tile
     static constexpr int HOP = NSTEP * FR_PER_ROUND;  // bytes between a lane's rounds
     static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
-    static constexpr int HALF_BYTES = NSTEP * NTP + 256;
+    static constexpr int QH = NSTEP == 8 ? 6 : 3;     // window words of history: frame k reads NSTEP*k bytes further on
+    static constexpr int HALF_BYTES = NSTEP * NTP + 256 + (NSTEP == 8 ? 16 : 0);
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
     static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
     static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
     // where the emitter is called from: spread over the groups after the early ones if there are enough
     static constexpr bool EMIT_SPREAD = GROUPS >= EARLY_GROUPS + 6;
     static_assert(!Q32 || DUP, "32-bit tables exist for the 72-table filter");
-    static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4, "frame hop of 8, 16 or 32 DSD samples");
+    static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8, "frame hop of 8, 16, 32 or 64 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
-    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == 0 && ROW_BYTES % 128 == 0, "staging chunks / bank pattern");
+    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == (NSTEP == 8 ? 16 : 0) && ROW_BYTES % 128 == 0, "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
     static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
 };
@@ -172,9 +180,13 @@ struct RingNoTrace {
 // main steps -- quantise(k, sum) before groups 5..8, store() before group 9 -- as straight-line
 // code the compiler can schedule into the shadow of the table loads, instead of a block of
 // scale/clip/round/store work that every warp of the CTA would hit at the same time.
+// Multi-pass filters: prefetch() is called once per period after the stores (the emitter's registers are
+// free again), init(k) at the hand-over -- the value the sum of the k-th frame of the NEXT period starts from.
 struct RingNoEmit {
     RING_HD void quantise(int, double) {}
     RING_HD void store() {}
+    RING_HD void prefetch() {}
+    RING_HD double init(int) const { return 0.0; }
 };
 
 // Skew of lane l (0..31) of a warp.
@@ -195,6 +207,7 @@ RING_HD int ring_lane_skew(int l) {
         return (g >> 1) + 4 * q;
     }
     const int h = (l >> 4) & 1, i = l & 15;
+    if (G::LANE_BYTES == 32) return i;                  // lane stride of eight words (see the top of this file)
     if (G::LANE_BYTES == 8) {
         // lane stride of two words: window word of lane i = 2*i + (j >> 2); found by search
         // upper half: j >> 2 = {3,3,3,2,2,2,2,3,0,1,1,1,1,0,0,0}[i], j & 3 = {0,1,2,0,1,2,3,3,0,0,1,2,3,1,2,3}[i]
@@ -216,7 +229,7 @@ struct RingLane {
     typedef typename RingAcc<G::Q32>::type acc_t;
     acc_t n[4];                 // sums of the frames started in the current period
     acc_t p[4];                 // sums of the frames started in the previous period (final after EARLY_STEPS)
-    uint32_t qn[3], qo[3];      // previous window words of the current / the previous frame set
+    uint32_t qn[G::QH], qo[G::QH];   // previous window words of the current / the previous frame set
     uint32_t ln, lo;            // last aligned word loaded from either window
     uint32_t wlast;             // smem offset of word L(0) of the previous period's window
     // constants of the lane
@@ -255,8 +268,8 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { r.n[k] = 0; r.p[k] = 0; }
-    r.qo[0] = r.qo[1] = r.qo[2] = 0u;
-    r.qn[0] = r.qn[1] = r.qn[2] = 0u;
+#pragma unroll
+    for (int i = 0; i < G::QH; ++i) { r.qo[i] = 0u; r.qn[i] = 0u; }
     r.lo = r.ln = 0u;
     r.wlast = 1024u;            // first period: the "previous window" is table bytes (finite garbage, never emitted)
     return a0 - 3 - phi;
@@ -265,8 +278,10 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
 // The 4-byte windows of the lane's four frames for one group: frame k reads NSTEP*k bytes further
 // on than frame 0, i.e. the word stream v = V(g), q[0..2] = V(g-1..g-3) shifted by NSTEP*k bytes.
 template <class G>
-RING_HD void ring_slot_words(uint32_t v, const uint32_t (&q)[3], uint32_t (&x)[4]) {
-    if (G::NSTEP == 4) {
+RING_HD void ring_slot_words(uint32_t v, const uint32_t (&q)[G::QH], uint32_t (&x)[4]) {
+    if constexpr (G::NSTEP == 8) {
+        x[0] = v; x[1] = q[1]; x[2] = q[3]; x[3] = q[5];
+    } else if (G::NSTEP == 4) {
         x[0] = v; x[1] = q[0]; x[2] = q[1]; x[3] = q[2];
     } else if (G::NSTEP == 2) {
         x[0] = v; x[1] = ring_funnel_r(v, q[0], 16u); x[2] = q[0]; x[3] = ring_funnel_r(q[0], q[1], 16u);
@@ -285,6 +300,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
         if (G::EMIT_SPREAD) {
             if (g > G::EARLY_GROUPS && g <= G::EARLY_GROUPS + 4) emit.quantise(g - G::EARLY_GROUPS - 1, r.value(g - G::EARLY_GROUPS - 1));
             if (g == G::EARLY_GROUPS + 5) emit.store();
+            if (g == G::EARLY_GROUPS + 6) emit.prefetch();
         }
         // window words: v[0] = V(g), v[1..3] = V(g-1..g-3); frame k reads the 4 bytes NSTEP*k further on
         uint32_t x[4];
@@ -295,7 +311,9 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             const uint32_t v = ring_funnel_r(w, r.ln, r.shift);
             r.ln = w;
             ring_slot_words<G>(v, r.qn, x);
-            r.qn[2] = r.qn[1]; r.qn[1] = r.qn[0]; r.qn[0] = v;
+#pragma unroll
+            for (int i = G::QH - 1; i > 0; --i) r.qn[i] = r.qn[i - 1];
+            r.qn[0] = v;
         }
         if (g < G::EARLY_GROUPS) {
             const uint32_t a = wold - 4u * (uint32_t)(G::GROUPS + g);
@@ -307,7 +325,9 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             ring_slot_words<G>(v, r.qo, y);
 #pragma unroll
             for (int k = 0; k < 4; ++k) x[k] = ring_prmt(x[k], y[k], r.sel[g]);
-            r.qo[2] = r.qo[1]; r.qo[1] = r.qo[0]; r.qo[0] = v;
+#pragma unroll
+            for (int i = G::QH - 1; i > 0; --i) r.qo[i] = r.qo[i - 1];
+            r.qo[0] = v;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -360,15 +380,16 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
 template <class G, class Trace>
 RING_HD void ring_head(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        const Trace& tr) {
-    // the three words ahead of group 0 (frames 1..3 start 4, 8, 12 bytes further on)
-    const uint32_t l4 = ring_lds_u32(smem, wnew + 16u), l3 = ring_lds_u32(smem, wnew + 12u);
-    const uint32_t l2 = ring_lds_u32(smem, wnew + 8u), l1 = ring_lds_u32(smem, wnew + 4u);
-    tr.word(tid, period, 100, wnew + 16u); tr.word(tid, period, 101, wnew + 12u);
-    tr.word(tid, period, 102, wnew + 8u); tr.word(tid, period, 103, wnew + 4u);
-    r.qn[2] = ring_funnel_r(l3, l4, r.shift);
-    r.qn[1] = ring_funnel_r(l2, l3, r.shift);
-    r.qn[0] = ring_funnel_r(l1, l2, r.shift);
-    r.ln = l1;
+    // the QH words ahead of group 0 (frames 1..3 start NSTEP, 2*NSTEP, 3*NSTEP bytes further on)
+    uint32_t l[G::QH + 1];                               // l[i] = word L(0) + 1 + i
+#pragma unroll
+    for (int i = G::QH; i >= 0; --i) {
+        l[i] = ring_lds_u32(smem, wnew + 4u * (uint32_t)(i + 1));
+        tr.word(tid, period, 100 + G::QH - i, wnew + 4u * (uint32_t)(i + 1));
+    }
+#pragma unroll
+    for (int i = 0; i < G::QH; ++i) r.qn[i] = ring_funnel_r(l[i], l[i + 1], r.shift);
+    r.ln = l[0];
     loff = r.lwrap;
     RingNoEmit none;
     ring_groups<G, 0, G::EARLY_GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, none, tr);
@@ -383,11 +404,13 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
 #pragma unroll
         for (int k = 0; k < 4; ++k) emit.quantise(k, r.value(k));
         emit.store();
+        emit.prefetch();
     }
     ring_groups<G, G::EARLY_GROUPS, G::GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = 0; }
-    r.qo[0] = r.qn[0]; r.qo[1] = r.qn[1]; r.qo[2] = r.qn[2];   // this window's last words = next period's history
+    for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = (typename RingLane<G>::acc_t)emit.init(k); }
+#pragma unroll
+    for (int i = 0; i < G::QH; ++i) r.qo[i] = r.qn[i];   // this window's last words = next period's history
     r.lo = r.ln;
     r.wlast = wnew;
 }

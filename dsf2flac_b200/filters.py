@@ -12,6 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _INC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "dsd_filter_bits.inc")
+_EXT_INC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "dsd_filter_ext_bits.inc")
 
 
 @dataclass(frozen=True)
@@ -30,8 +31,10 @@ class Fir:
         return self.ratio // 8
 
 
-def _load():
-    text = open(_INC).read()
+def _load(path=_INC):
+    if not os.path.exists(path):
+        return {}
+    text = open(path).read()
     out = {}
     for m in re.finditer(r"DSD_FILTER_BEGIN\((\w+), /\*ratio\*/ (\d+), /\*taps\*/ (\d+), /\*tzero\*/ (\d+)\)(.*?)DSD_FILTER_END",
                          text, re.S):
@@ -43,14 +46,21 @@ def _load():
 
 
 FILTERS = _load()
+# EXTENSION filters (/64, /128, /256; tools/design_ext_filters.py): no reference counterpart
+EXTENSION_FILTERS = _load(_EXT_INC)
 
 
-def pick(dsd_fs, out_fs):
+def pick(dsd_fs, out_fs, extensions=False):
     """Filter for a rate pair, or None where the reference says "Sorry, incompatible sample rate
-    combination" (dsd_decimator.cpp:57-68): the choice is by the integer ratio alone."""
+    combination" (dsd_decimator.cpp:57-68): the choice is by the integer ratio alone.
+    extensions=True also offers the /64, /128 and /256 extension filters."""
     if not out_fs:
         return None
-    return FILTERS.get(int(dsd_fs) // int(out_fs))
+    ratio = int(dsd_fs) // int(out_fs)
+    fir = FILTERS.get(ratio)
+    if fir is None and extensions:
+        fir = EXTENSION_FILTERS.get(ratio)
+    return fir
 
 
 def build_lut(fir, msb_flag):

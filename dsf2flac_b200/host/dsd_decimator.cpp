@@ -29,16 +29,35 @@ struct FirSpec { int ratio, ntaps, tzero; const dsf2flac_uint64* bits; };
     const dsf2flac_uint64 tag##_bits[taps_] = {
 #define DSD_FILTER_END(tag) };
 #include "dsd_filter_bits.inc"
+// EXTENSION (no reference counterpart): /64, /128, /256 -- the /32 response stretched to faster DSD
+// clocks (tools/design_ext_filters.py).  Off unless asked for: the reference rejects these ratios.
+#include "dsd_filter_ext_bits.inc"
 
 const FirSpec kFilters[3] = {
     {div8_ratio, div8_taps, div8_tzero, div8_bits},
     {div16_ratio, div16_taps, div16_tzero, div16_bits},
     {div32_ratio, div32_taps, div32_tzero, div32_bits},
 };
+const FirSpec kExtensionFilters[3] = {
+    {div64_ratio, div64_taps, div64_tzero, div64_bits},
+    {div128_ratio, div128_taps, div128_tzero, div128_bits},
+    {div256_ratio, div256_taps, div256_tzero, div256_bits},
+};
+
+int g_extensionFilters = -1;        // -1: ask the environment (DSDGPU_EXTENSION_FILTERS=1), 0 off, 1 on
+
+bool extensionFiltersEnabled() {
+    if (g_extensionFilters >= 0) return g_extensionFilters != 0;
+    const char* env = std::getenv("DSDGPU_EXTENSION_FILTERS");
+    return env && std::atoi(env) != 0;
+}
 
 const FirSpec* findFilter(dsf2flac_uint32 ratio) {
     for (const FirSpec& f : kFilters)
         if ((dsf2flac_uint32)f.ratio == ratio) return &f;
+    if (extensionFiltersEnabled())
+        for (const FirSpec& f : kExtensionFilters)
+            if ((dsf2flac_uint32)f.ratio == ratio) return &f;
     return nullptr;
 }
 
@@ -153,6 +172,8 @@ dsf2flac_float64 DsdDecimator::getLastValidSample()
 }
 
 void DsdDecimator::step() { pos += 1; }
+
+void DsdDecimator::setExtensionFilters(bool on) { g_extensionFilters = on ? 1 : 0; }
 
 void DsdDecimator::setReadAheadFrames(dsf2flac_uint32 frames) { readAhead = frames ? frames : 1; }
 

@@ -47,6 +47,11 @@ public:
             dsf2flac_float64 clipAmplitude = 0);
 
     // --- additions (not in the reference) ---------------------------------------------------
+    // Decimation by 64, 128 and 256 (DSD512 -> 352.8k, ... -> 88.2k): the reference answers "Sorry,
+    // incompatible sample rate combination" for these (dsd_decimator.cpp:64-68) and so does this
+    // class unless the extension filters are switched on here (or DSDGPU_EXTENSION_FILTERS=1 in the
+    // environment) before construction.  Same operator, longer impulse responses.
+    static void setExtensionFilters(bool on);
     // Frames decimated per GPU round trip; larger = fewer, bigger transfers. Default 1<<20.
     void setReadAheadFrames(dsf2flac_uint32 frames);
     // 64 (default, bit-exact) or 32 (32-bit fixed-point tables, exact integer sums: within +-1 LSB at

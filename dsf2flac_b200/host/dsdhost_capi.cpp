@@ -23,6 +23,9 @@ extern "C" {
 
 const char* dsdhost_last_error() { return g_error.c_str(); }
 
+// DsdDecimator::setExtensionFilters: decimation by 64, 128, 256 (the reference rejects these).
+void dsdhost_set_extension_filters(int on) { DsdDecimator::setExtensionFilters(on != 0); }
+
 // Geometry as the decimator reports it (reference dsd_decimator.cpp:44-72,85-101).
 // Returns 1 if the rate pair is accepted, 0 if not ("Sorry, incompatible ..."); a missing GPU
 // does not matter here: the getters do not depend on it.
@@ -32,7 +35,7 @@ int dsdhost_info(uint32_t dsd_fs, uint32_t out_fs, int64_t length_samples, int32
     MemorySampleReader rd(&dummy, 1, 0, length_samples, dsd_fs, true);
     DsdDecimator dec(&rd, out_fs);
     g_error = dec.getErrorMsg();
-    if (dec.getDecimationRatio() != 8 && dec.getDecimationRatio() != 16 && dec.getDecimationRatio() != 32) return 0;
+    if (g_error.rfind("Sorry", 0) == 0) return 0;            // the reference's rejection, not a missing GPU
     *ratio = (int32_t)dec.getDecimationRatio();
     *first_valid = dec.getFirstValidSample();
     *last_valid = dec.getLastValidSample();

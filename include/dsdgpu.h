@@ -56,8 +56,14 @@ enum {
     DSDGPU_KERNEL_AUTO = 0,   /* ring kernel when the geometry supports it, else direct */
     DSDGPU_KERNEL_DIRECT = 1, /* one thread per output sample, tables [t][byte] in smem */
     DSDGPU_KERNEL_SKEW = 2,   /* lane-skewed kernel, 80-step periods (divide-by-32 filters) */
-    DSDGPU_KERNEL_RING = 3    /* lane-skewed kernel, 72-step periods, 4 frames per lane (divide-by-32) */
+    DSDGPU_KERNEL_RING = 3,   /* lane-skewed kernel, 72-step periods, 4 frames per lane (divide-by-32) */
+    DSDGPU_KERNEL_SEGMENTED = 4 /* lane-skewed kernel for any geometry, <= 72 tables per pass; filters with
+                                   more tables (the /64, /128, /256 extension filters) run as a chain of
+                                   passes over a plane of running fp64 sums */
 };
+
+/* Largest filter a context accepts: 576 tables = the 4607-tap /256 extension filter. */
+#define DSDGPU_MAX_TABLES 640
 
 /*
  * Replaces: DsdDecimator::DsdDecimator + initLookupTable (dsd_decimator.cpp:44-72,117-151).
@@ -65,7 +71,9 @@ enum {
  * it over; the context uploads it (re-laid out for shared memory) and owns all device state.
  *   device        CUDA device ordinal
  *   nch           channels (>=1)
- *   nlut, nstep   nLookupTable and nStep of the reference (72/4, 30/2, 12/1; any nlut<=96 works)
+ *   nlut, nstep   nLookupTable and nStep of the reference (72/4, 30/2, 12/1); any other geometry with
+ *                 nlut <= DSDGPU_MAX_TABLES and nstep <= 64 runs on the segmented kernel (extension
+ *                 filters for the ratios the reference rejects: 144/8, 288/16, 576/32)
  *   lut           [nlut][256] doubles, row t = table t
  *   lut_precision 64: tables kept in fp64 (bit-exact path).
  *                 32: 32-bit tables -- every entry rounded to a multiple of 2^-30 (fixed point; a

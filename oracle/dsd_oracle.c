@@ -34,10 +34,27 @@ typedef struct {
     const uint64_t* bits;
 } fir_spec;
 
+/* EXTENSION filters (ratios the reference rejects).  A test registers one impulse
+ * response; the operator below then runs on it exactly as it runs on the reference's three.      */
+static struct { int ratio, ntaps, tzero; uint64_t* bits; } g_custom = {0, 0, 0, NULL};
+
+int dsdoracle_set_custom_filter(int ratio, int ntaps, int tzero, const double* coefs) {
+    free(g_custom.bits);
+    g_custom.bits = NULL; g_custom.ratio = 0;
+    if (ratio <= 0 || ntaps <= 0 || !coefs) return 0;
+    g_custom.bits = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)ntaps);
+    memcpy(g_custom.bits, coefs, sizeof(uint64_t) * (size_t)ntaps);
+    g_custom.ratio = ratio; g_custom.ntaps = ntaps; g_custom.tzero = tzero;
+    return 1;
+}
+
 /* dsd_decimator.cpp:52-68: ratio = dsdFs / outFs (integer divide), filter chosen by ratio only */
 static int pick_filter(uint32_t dsd_fs, uint32_t out_fs, fir_spec* f) {
     if (out_fs == 0) return 0;
     uint32_t ratio = dsd_fs / out_fs;
+    if (g_custom.ratio > 0 && ratio == (uint32_t)g_custom.ratio) {
+        f->ntaps = g_custom.ntaps; f->tzero = g_custom.tzero; f->bits = g_custom.bits;
+    } else
     if (ratio == 8) { f->ntaps = div8_taps; f->tzero = div8_tzero; f->bits = div8_bits; }
     else if (ratio == 16) { f->ntaps = div16_taps; f->tzero = div16_tzero; f->bits = div16_bits; }
     else if (ratio == 32) { f->ntaps = div32_taps; f->tzero = div32_tzero; f->bits = div32_bits; }

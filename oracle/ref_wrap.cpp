@@ -63,9 +63,42 @@ private:
     uint8_t idle_;
 };
 
+// EXTENSION filters.  The reference rejects every ratio but 8, 16 and 32
+// (dsd_decimator.cpp:57-68).  To run ITS arithmetic -- initLookupTable and getSamplesInternal, both
+// unmodified -- on a longer impulse response, the decimator is constructed for ratio 32 (valid) and
+// then given the registered filter through its own private initLookupTable.
+struct CustomFilter { int ratio = 0, ntaps = 0, tzero = 0; std::vector<double> coefs; } g_custom;
+
+class RefDecimator : public DsdDecimator {
+public:
+    RefDecimator(DsdSampleReader* rd, uint32_t out_fs)
+        : DsdDecimator(rd, custom_for(rd, out_fs) ? rd->getSamplingFreq() / 32 : out_fs) {
+        if (!custom_for(rd, out_fs)) return;
+        for (dsf2flac_uint32 n = 0; n < nLookupTable; n++) delete[] lookupTable[n];
+        delete[] lookupTable;
+        outputSampleRate = out_fs;
+        ratio = (dsf2flac_uint32)g_custom.ratio;
+        nStep = ratio / 8;
+        initLookupTable(g_custom.ntaps, g_custom.coefs.data(), g_custom.tzero);
+        if (nLookupTable > rd->getBufferLength()) rd->setBufferLength(nLookupTable);
+    }
+private:
+    static bool custom_for(DsdSampleReader* rd, uint32_t out_fs) {
+        return g_custom.ratio > 0 && out_fs != 0 && rd->getSamplingFreq() / out_fs == (uint32_t)g_custom.ratio;
+    }
+};
+
 }  // namespace
 
 extern "C" {
+
+int dsdref_set_custom_filter(int ratio, int ntaps, int tzero, const double* coefs) {
+    g_custom = CustomFilter();
+    if (ratio <= 0 || ntaps <= 0 || !coefs) return 0;
+    g_custom.ratio = ratio; g_custom.ntaps = ntaps; g_custom.tzero = tzero;
+    g_custom.coefs.assign(coefs, coefs + ntaps);
+    return 1;
+}
 
 // Geometry the reference derives for (dsd_fs, out_fs).  Returns 0 if the pair is rejected.
 int dsdref_info(uint32_t dsd_fs, uint32_t out_fs, int64_t length_samples, int32_t* ratio,
@@ -73,7 +106,7 @@ int dsdref_info(uint32_t dsd_fs, uint32_t out_fs, int64_t length_samples, int32_
                 double* last_valid, int64_t* length_pcm) {
     uint8_t dummy = 0;
     MemoryReader rd(&dummy, 1, 0, length_samples, dsd_fs, true, 0x69);
-    DsdDecimator dec(&rd, out_fs);
+    RefDecimator dec(&rd, out_fs);
     if (!dec.isValid()) return 0;
     *ratio = (int32_t)dec.getDecimationRatio();
     *nlut = (int32_t)dec.nLookupTable;
@@ -89,7 +122,7 @@ int dsdref_info(uint32_t dsd_fs, uint32_t out_fs, int64_t length_samples, int32_
 int dsdref_lut(uint32_t dsd_fs, uint32_t out_fs, int msb_flag, double* lut, int cap_tables) {
     uint8_t dummy = 0;
     MemoryReader rd(&dummy, 1, 0, 0, dsd_fs, msb_flag != 0, 0x69);
-    DsdDecimator dec(&rd, out_fs);
+    RefDecimator dec(&rd, out_fs);
     if (!dec.isValid()) return 0;
     int n = (int)dec.nLookupTable;
     for (int t = 0; t < n && t < cap_tables; ++t)
@@ -105,7 +138,7 @@ int dsdref_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t lengt
                    int64_t pre_steps, int64_t nframes, int64_t chunk_frames, double scale,
                    double dither, double clip, int reseed, int32_t* out_i32, double* out_f64) {
     MemoryReader rd(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
-    DsdDecimator dec(&rd, out_fs);
+    RefDecimator dec(&rd, out_fs);
     if (!dec.isValid()) return 1;
     if (reseed) srand(1);
     for (int64_t i = 0; i < pre_steps; ++i) dec.step();
@@ -120,7 +153,7 @@ int dsdref_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t lengt
     }
     if (out_f64) {
         MemoryReader rd2(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
-        DsdDecimator dec2(&rd2, out_fs);
+        RefDecimator dec2(&rd2, out_fs);
         if (reseed) srand(1);
         for (int64_t i = 0; i < pre_steps; ++i) dec2.step();
         for (int64_t f = 0; f < nframes; f += chunk_frames) {
@@ -139,7 +172,7 @@ int64_t dsdref_run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t l
                        double scale, double dither, double clip, int reseed, int32_t* out,
                        int64_t out_cap_frames) {
     MemoryReader rd(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
-    DsdDecimator dec(&rd, out_fs);
+    RefDecimator dec(&rd, out_fs);
     if (!dec.isValid()) return -1;
     if (reseed) srand(1);
     double startPos = dec.getFirstValidSample();

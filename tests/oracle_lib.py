@@ -59,9 +59,20 @@ class Oracle:
                     last_valid=d[1].value, length_pcm=n.value)
 
     def lut(self, dsd_fs, out_fs, msb_flag):
-        buf = np.zeros((96, 256), dtype=np.float64)
-        n = self._fn("lut")(dsd_fs, out_fs, int(msb_flag), buf.ctypes.data, 96)
+        buf = np.zeros((640, 256), dtype=np.float64)
+        n = self._fn("lut")(dsd_fs, out_fs, int(msb_flag), buf.ctypes.data, 640)
         return buf[:n].copy() if n else None
+
+    def set_custom_filter(self, fir):
+        """EXTENSION filters: run the operator on `fir` (dsf2flac_b200.filters.Fir) for its ratio, which the
+        reference itself rejects.  None clears the registration.  Process-global, like the reference's state."""
+        f = self._fn("set_custom_filter")
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_int, C.c_int, _vp]
+        if fir is None:
+            return f(0, 0, 0, None)
+        coefs = np.ascontiguousarray(fir.coefs, dtype=np.float64)
+        return f(fir.ratio, fir.ntaps, fir.tzero, coefs.ctypes.data)
 
     def run_raw(self, planar, length_samples, msb_flag, dsd_fs, out_fs, pre_steps, nframes, scale, dither=0.0,
                 clip=0.0, idle=0x69, want="i32", chunk_frames=0, rand_skip=0):
