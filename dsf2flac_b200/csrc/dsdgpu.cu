@@ -461,17 +461,26 @@ struct RingEmitter {
     int vi[4];
     double vd[4];
     double iv[4];
+    double dv[4];
+    static constexpr bool LATE = DITHER;
 
     __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, const RingDest& nx_, int h_, bool al)
         : a(a_), d(d_), nx(nx_), h(h_), out_aligned16(al) {}
 
+    // the dither terms of the four frames being finished, issued well ahead of quantise()
+    __device__ __forceinline__ void fetch() {
+        if (!DITHER) return;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long f = d.fb + k < a.nframes ? d.fb + k : 0;     // keep the load in bounds
+            dv[k] = __ldg(a.dither + f * a.dither_stride + d.c);
+        }
+    }
+
     __device__ __forceinline__ void quantise(int k, double sum) {
         if (OUT == 2) { vd[k] = sum; return; }
         double x = __dmul_rn(sum, a.scale);
-        if (DITHER) {
-            const long long f = d.fb + k < a.nframes ? d.fb + k : 0;     // keep the load in bounds
-            x = __dadd_rn(x, __dmul_rn(a.dither[f * a.dither_stride + d.c], a.dither_amp));
-        }
+        if (DITHER) x = __dadd_rn(x, __dmul_rn(dv[k], a.dither_amp));
         const bool clipping = a.clip > 0.0;
         x = (clipping && x > a.clip) ? a.clip : x;
         x = (clipping && x < -a.clip) ? -a.clip : x;
@@ -643,6 +652,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     // the one drain of this CTA: 16 more steps finish the last frames
     ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
     RingEmitter<OUT, DITHER, INIT> emit(a, prev, prev, h, out_aligned16);
+    emit.fetch();
 #pragma unroll
     for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));
     emit.store();

@@ -182,7 +182,12 @@ struct RingNoTrace {
 // scale/clip/round/store work that every warp of the CTA would hit at the same time.
 // Multi-pass filters: prefetch() is called once per period after the stores (the emitter's registers are
 // free again), init(k) at the hand-over -- the value the sum of the k-th frame of the NEXT period starts from.
+// An emitter that needs data from global memory for quantise() (the dither values) sets LATE: fetch() is
+// then called right after the early groups and the quantise / store / prefetch calls move five groups
+// further on, so that the loads have a quarter of a period to land.
 struct RingNoEmit {
+    static constexpr bool LATE = false;
+    RING_HD void fetch() {}
     RING_HD void quantise(int, double) {}
     RING_HD void store() {}
     RING_HD void prefetch() {}
@@ -298,9 +303,13 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
 #pragma unroll
     for (int g = G0; g < G1; ++g) {
         if (G::EMIT_SPREAD) {
-            if (g > G::EARLY_GROUPS && g <= G::EARLY_GROUPS + 4) emit.quantise(g - G::EARLY_GROUPS - 1, r.value(g - G::EARLY_GROUPS - 1));
-            if (g == G::EARLY_GROUPS + 5) emit.store();
-            if (g == G::EARLY_GROUPS + 6) emit.prefetch();
+            constexpr bool late = Emit::LATE && G::GROUPS >= G::EARLY_GROUPS + 12;
+            constexpr int q0 = G::EARLY_GROUPS + (late ? 6 : 1);       // group of the first quantise call
+            if (late && g == G::EARLY_GROUPS + 1) emit.fetch();
+            if (!late && g == q0) emit.fetch();
+            if (g >= q0 && g < q0 + 4) emit.quantise(g - q0, r.value(g - q0));
+            if (g == q0 + 4) emit.store();
+            if (g == q0 + 5) emit.prefetch();
         }
         // window words: v[0] = V(g), v[1..3] = V(g-1..g-3); frame k reads the 4 bytes NSTEP*k further on
         uint32_t x[4];
@@ -401,6 +410,7 @@ template <class G, class Emit, class Trace>
 RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        Emit& emit, const Trace& tr) {
     if (!G::EMIT_SPREAD) {               // short periods: the whole emitter before the remaining steps
+        emit.fetch();
 #pragma unroll
         for (int k = 0; k < 4; ++k) emit.quantise(k, r.value(k));
         emit.store();

@@ -104,8 +104,10 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
     long long lut_instr = 0, lut_wavefronts = 0, word_instr = 0, word_wavefronts = 0;
     struct Dest { long long fb; int c; };
     struct Collect {                      // the emulator's emitter: just keeps what the lane hands over
-        double sums[4]; int got = 0, stored = 0, fetched = 0;
+        enum { LATE = 1 };                    // the later call sites: what the dither variants of the kernel run
+        double sums[4]; int got = 0, stored = 0, fetched = 0, early = 0;
         double iv[4] = {0, 0, 0, 0};
+        void fetch() { if (!got) ++early; }
         void quantise(int k, double v) { sums[k] = v; got |= 1 << k; }
         void store() { ++stored; }
         void prefetch() { ++fetched; }
@@ -184,7 +186,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                         for (int k = 0; k < 4; ++k) col.iv[k] = init_of(cn, fbn + k);
                     }
                     ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, col, rec);
-                    if (col.got != 15 || col.stored != 1 || col.fetched != 1) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
+                    if (col.got != 15 || col.stored != 1 || col.fetched != 1 || col.early != 1) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
                     if (have_prev) check(prev[tid], col.sums, tid);
                     prev[tid] = {tl.f0[h] + 4LL * ((long long)n * G::BLK_PER_ROUND + 16 * w + (l & 15)), tl.c[h]};
                 }
