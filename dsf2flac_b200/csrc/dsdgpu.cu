@@ -468,8 +468,24 @@ struct RingEmitter {
         : a(a_), d(d_), nx(nx_), h(h_), out_aligned16(al) {}
 
     // the dither terms of the four frames being finished, issued well ahead of quantise()
+    // Pair tiles read them the way the stores go out: a lane loads the 16-byte pairs {D(f, c0), D(f, c0 + 1)}
+    // of the two frames it will store (f = fb + 2h, fb + 2h + 1) and trades the two values its partner
+    // (lane ^ 16, the other channel) needs -- two coalesced 16-byte loads and two 64-bit shuffles per lane
+    // instead of four 8-byte loads at a stride that touches a different cache line per lane.
     __device__ __forceinline__ void fetch() {
         if (!DITHER) return;
+        const bool wide = d.pair && ((a.dither_stride | d.c0) & 1) == 0 &&
+                          (reinterpret_cast<unsigned long long>(a.dither) & 15ULL) == 0;    // warp-uniform
+        if (wide) {
+            const long long f0 = d.fb + 2 * h, f1 = f0 + 1;
+            const double2 u = __ldg(reinterpret_cast<const double2*>(a.dither + (f0 < a.nframes ? f0 : 0) * a.dither_stride + d.c0));
+            const double2 v = __ldg(reinterpret_cast<const double2*>(a.dither + (f1 < a.nframes ? f1 : 0) * a.dither_stride + d.c0));
+            const double r0 = __shfl_xor_sync(0xffffffffu, h ? u.x : u.y, 16);
+            const double r1 = __shfl_xor_sync(0xffffffffu, h ? v.x : v.y, 16);
+            dv[0] = h ? r0 : u.x; dv[1] = h ? r1 : v.x;
+            dv[2] = h ? u.y : r0; dv[3] = h ? v.y : r1;
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const long long f = d.fb + k < a.nframes ? d.fb + k : 0;     // keep the load in bounds
@@ -718,44 +734,61 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
 dop_pack_wide_kernel(DecimateArgs a, long long pm0, int reverse) {
     const long long total = a.nframes * NCH, groups = (total + 3) / 4;
-    constexpr int FR = 4 / NCH;                                   // frames per thread
-    constexpr int NB = 2 * FR;                                    // source bytes per channel per thread
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < groups;
-         t += (long long)gridDim.x * blockDim.x) {
-        const long long f0 = t * FR;
-        const long long o = pm0 + 2 * f0 - a.in_first;           // source index of the group's first byte
-        int v[4];
-        if (o >= 0 && o + NB <= a.in_count && 4 * t + 3 < total) {
+    constexpr int FR = 4 / NCH;                                   // frames per group
+    constexpr int NB = 2 * FR;                                    // source bytes per channel per group
+    constexpr int NW = NB / 4;
+    constexpr int UN = 4;                                         // groups per thread per pass: all loads first
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int32_t* __restrict__ out = reinterpret_cast<int32_t*>(a.out);
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < groups; t0 += UN * stride) {
+        uint32_t w[UN][NCH][NW];
+        bool fast[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const long long t = t0 + u * stride;
+            const long long o = pm0 + 2 * t * FR - a.in_first;   // source index of the group's first byte
+            fast[u] = t < groups && o >= 0 && o + NB <= a.in_count && 4 * t + 3 < total;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                uint32_t w[NB / 4];
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(a.in + src_offset(a, c, o));
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(a.in + src_offset(a, c, fast[u] ? o : 0));
 #pragma unroll
-                for (int q = 0; q < NB / 4; ++q) w[q] = src[q];
-#pragma unroll
-                for (int k = 0; k < FR; ++k) {
-                    uint32_t pair = (w[(2 * k) / 4] >> (8 * ((2 * k) & 3))) & 0xffffu;   // bytes 2k (low), 2k+1 (high)
-                    uint32_t b1 = pair & 0xffu, b2 = pair >> 8;
-                    if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
-                    const long long pm = pm0 + 2 * (f0 + k) + 1;
-                    const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
-                    v[k * NCH + c] = marker + (int)(b1 << 8) + (int)b2;
-                }
+                for (int q = 0; q < NW; ++q) w[u][c][q] = fast[u] ? __ldg(src + q) : 0u;
             }
-            reinterpret_cast<int4*>(a.out)[t] = make_int4(v[0], v[1], v[2], v[3]);
-        } else {
-            for (int e = 0; e < 4; ++e) {
-                const long long idx = 4 * t + e;
-                if (idx >= total) break;
-                const long long i = idx / NCH;
-                const int c = (int)(idx - i * NCH);
-                const long long pm = pm0 + 2 * i + 1;
-                const long long o1 = pm - 1 - a.in_first, o2 = pm - a.in_first;
-                unsigned b1 = (o1 >= 0 && o1 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o1)] : a.fill;
-                unsigned b2 = (o2 >= 0 && o2 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o2)] : a.fill;
-                if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
-                const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
-                reinterpret_cast<int32_t*>(a.out)[idx] = marker + (int)(b1 << 8) + (int)b2;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const long long t = t0 + u * stride;
+            if (t >= groups) break;
+            const long long f0 = t * FR;
+            if (fast[u]) {
+                int v[4];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                    for (int k = 0; k < FR; ++k) {
+                        const uint32_t pair = (w[u][c][(2 * k) / 4] >> (8 * ((2 * k) & 3))) & 0xffffu;   // bytes 2k (low), 2k+1 (high)
+                        uint32_t b1 = pair & 0xffu, b2 = pair >> 8;
+                        if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
+                        const long long pm = pm0 + 2 * (f0 + k) + 1;
+                        const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
+                        v[k * NCH + c] = marker + (int)(b1 << 8) + (int)b2;
+                    }
+                }
+                reinterpret_cast<int4*>(out)[t] = make_int4(v[0], v[1], v[2], v[3]);
+            } else {
+                for (int e = 0; e < 4; ++e) {
+                    const long long idx = 4 * t + e;
+                    if (idx >= total) break;
+                    const long long i = idx / NCH;
+                    const int c = (int)(idx - i * NCH);
+                    const long long pm = pm0 + 2 * i + 1;
+                    const long long o1 = pm - 1 - a.in_first, o2 = pm - a.in_first;
+                    unsigned b1 = (o1 >= 0 && o1 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o1)] : a.fill;
+                    unsigned b2 = (o2 >= 0 && o2 < a.in_count) ? (unsigned)a.in[src_offset(a, c, o2)] : a.fill;
+                    if (reverse) { b1 = __brev(b1) >> 24; b2 = __brev(b2) >> 24; }
+                    const int marker = ((8 * pm - 8) % 32 != 0) ? (int)0xFFFA0000 : 0x00050000;
+                    out[idx] = marker + (int)(b1 << 8) + (int)b2;
+                }
             }
         }
     }
@@ -1635,8 +1668,9 @@ static int launch_dop(dsdgpu_ctx* ctx, const SourceView& v, uint8_t fill, int64_
                       (reinterpret_cast<unsigned long long>(d_out) & 15ULL) == 0;
     if (wide) {
         const long long groups = (total + 3) / 4;
-        long long blocks = (groups + 255) / 256;
-        if (blocks > 64LL * ctx->sm_count) blocks = 64LL * ctx->sm_count;
+        long long blocks = (groups + 4 * 256 - 1) / (4 * 256);       // four groups per thread per pass
+        if (blocks > 16LL * ctx->sm_count) blocks = 16LL * ctx->sm_count;
+        if (blocks < 1) blocks = 1;
         if (ctx->nch == 1) dop_pack_wide_kernel<1><<<(int)blocks, 256, 0, st>>>(a, pm0, reverse_bits);
         else dop_pack_wide_kernel<2><<<(int)blocks, 256, 0, st>>>(a, pm0, reverse_bits);
         ctx->launches += 1;
