@@ -53,6 +53,8 @@ def sharded_workloads(nfiles=256):
                [(4 * DSD64, 352800, 6, 60)], 64, 0),
         "c4": ("DSD512 stereo 600 s, divide-by-32, time segments with a 71-byte halo (BASELINE configs[3]; the "
                "reference has no divide-by-64 filter for 352.8 kHz)", [(8 * DSD64, 705600, 2, 600)], 64, 0),
+        "c4x": ("DSD512 stereo 600 s -> 24-bit/352.8 kHz as BASELINE configs[3] states it: divide-by-64 EXTENSION filter "
+                "(the reference rejects this ratio), time segments with a 143-byte halo", [(8 * DSD64, 352800, 2, 600)], 64, 0),
         "c5": (f"{nfiles} files, DSD64->88.2k / DSD128->176.4k alternating, 30-90 s, TPDF dither on, 32-bit tables "
                "(BASELINE configs[4])", c5, 32, 1),
     }
@@ -460,7 +462,7 @@ def run_sharded_arm(args, spec):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    firs = [filters.pick(f[0], f[1]) for f in files]
+    firs = [filters.pick(f[0], f[1], extensions=True) for f in files]
     frames = [filters.app_frames(f[0] * f[3], fir) for f, fir in zip(files, firs)]
     shards = capi.plan_shards(frames, [f[2] for f in files], [fir.nlut for fir in firs], rank, world, 1024)
     base = {}                                              # one second of modulator output per (rate, channel)
@@ -485,11 +487,13 @@ def run_sharded_arm(args, spec):
             one, phase = second(fs, c0 + c), lo % sec
             pin.array[c] = np.tile(one, (hi - lo + phase) // sec + 2)[phase:phase + hi - lo]
         job = batch.Job(pin.array, fs, out_fs, msb_flag=True, length_samples=fs * seconds, bits=24, dither=bool(dither),
-                        lut_precision=lut_bits, first_byte=lo)
+                        lut_precision=lut_bits, first_byte=lo, extensions=True)
         job_nch = nch
         out = capi.PinnedBuffer((nf, k), np.int32)
         ctx = runner.ctx_for(job, k)
-        d_in = torch.from_numpy(pin.array).cuda()
+        # device rows on a 256-byte pitch: the kernels stage 16-byte chunks with cp.async when rows are aligned
+        d_in = torch.empty((k, (hi - lo + 255) // 256 * 256), dtype=torch.uint8, device="cuda")
+        d_in[:, :hi - lo] = torch.from_numpy(pin.array).cuda()
         d_out = torch.empty((nf, k), dtype=torch.int32, device="cuda")
         work.append((job, (j, c0, k, f0, nf), pin, out, ctx, d_in, d_out, job_nch))
     scale_of = lambda job: filters.app_params(job.bits, job.scale_db, job.dither)
@@ -639,7 +643,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c5", "dop"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c4x", "c5", "dop"])
     ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
     ap.add_argument("--dither", type=int, default=0)
     ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring", "seg"])
@@ -650,16 +654,19 @@ def main():
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per pipelined host chunk")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall seconds of CPU work in the cpu_baseline sample (0: skip)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
+    ap.add_argument("--seconds", type=int, default=0, help="stream length of the unsharded workloads (default: 60)")
     ap.add_argument("--dop-seconds", type=int, default=600, help="stream length of the dop workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload == "dop":
         return run_dop_arm(args)
-    if args.workload in ("c3", "c4", "c5"):
+    if args.workload in ("c3", "c4", "c4x", "c5"):
         if args.impl == "reference":
             raise SystemExit("the reference arm runs the unsharded workloads (c1, c2)")
         return run_sharded_arm(args, sharded_workloads(args.files)[args.workload])
     wl = WORKLOADS[args.workload]
+    if args.seconds:
+        wl = wl[:3] + (args.seconds, wl[4], wl[5].replace(" 60 s", f" {args.seconds} s"))
     if args.impl == "reference":
         run_reference_arm(args, wl)
     else:

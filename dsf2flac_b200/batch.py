@@ -32,12 +32,13 @@ class Job:
     lut_precision: int = 64
     idle: int = 0x69
     first_byte: int = 0           # stream index of planar[:, 0] when only a window of the stream is held
+    extensions: bool = False      # accept the ratios the reference rejects (64, 128, 256: extension filters)
     fir: object = field(init=False)
 
     def __post_init__(self):
         if self.length_samples < 0:
             self.length_samples = 8 * (self.first_byte + self.planar.shape[1])
-        self.fir = filters.pick(self.dsd_fs, self.out_fs)
+        self.fir = filters.pick(self.dsd_fs, self.out_fs, extensions=self.extensions)
         if self.fir is None:
             raise ValueError("Sorry, incompatible sample rate combination")
 

@@ -164,6 +164,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     }
 }
 
+// One 16-byte chunk of a tile's byte buffer: stream bytes o .. o+15 (relative to in_first) of channel c.
+//   interior, 16-byte aligned source   cp.async (LDGSTS), coalesced
+//   interior, any other alignment      five aligned words funnel-shifted into four (a caller's odd pointer
+//                                      or row pitch costs bandwidth, not 16 byte loads per chunk)
+//   touching the ends of the source    byte by byte, with the fill value outside
+__device__ __forceinline__ void stage_chunk16(const DecimateArgs& a, int c, long long o, unsigned char* d, bool aligned16) {
+    if (o >= 0 && o + 16 <= a.in_count) {
+        const uint8_t* p = a.in + src_offset(a, c, o);
+        if (aligned16) { cp_async16(d, p); return; }
+        const unsigned mis = (unsigned)(reinterpret_cast<unsigned long long>(p) & 3ULL);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p - mis);
+        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+        const uint32_t w4 = mis ? q[4] : 0u;             // shares its aligned word with byte o+15: never a stray access
+        const unsigned sh = 8u * mis;
+        *reinterpret_cast<uint4*>(d) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                                  __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        return;
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const long long ob = o + 4 * q + b;
+            const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
+            v |= byte << (8 * b);
+        }
+        w[q] = v;
+    }
+    *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // Tiles are numbered channel-fastest: the CTAs that run side by side write the same frames of
 // neighbouring channels, so the 4-byte slots of one 32-byte output sector meet in L2 before the
 // sector goes to HBM (frame-major interleaved output, dsd_decimator.cpp:213).
@@ -187,23 +220,7 @@ __device__ __forceinline__ void skew_stage_tile(const DecimateArgs& a, int c, lo
     for (int k = threadIdx.x; k < G::TILE_BYTES / 16; k += G::NTHR) {
         const long long o = o0 + 16LL * k;
         unsigned char* d = dst + 16 * k;
-        if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
-            cp_async16(d, a.in + src_offset(a, c, o));
-        } else {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const long long ob = o + 4 * q + b;
-                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
-                    v |= byte << (8 * b);
-                }
-                w[q] = v;
-            }
-            *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        stage_chunk16(a, c, o, d, aligned16);
     }
 }
 
@@ -285,23 +302,7 @@ __device__ __forceinline__ void seg_stage_tile(const DecimateArgs& a, long long 
         const int c = k / chunks_per_row, kk = k - c * chunks_per_row;
         const long long o = o0 + 16LL * kk;
         unsigned char* d = dst + c * row_stride + 16 * kk;
-        if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
-            cp_async16(d, a.in + src_offset(a, c, o));
-        } else {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const long long ob = o + 4 * q + b;
-                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
-                    v |= byte << (8 * b);
-                }
-                w[q] = v;
-            }
-            *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        stage_chunk16(a, c, o, d, aligned16);
     }
 }
 
@@ -418,23 +419,7 @@ __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const Rin
         const int c = h ? tl.c[1] : tl.c[0];
         const long long o = t0 - a.in_first + 16LL * kk;
         unsigned char* d = dst + h * G::HALF_BYTES + 16 * kk;
-        if (aligned16 && o >= 0 && o + 16 <= a.in_count) {
-            cp_async16(d, a.in + src_offset(a, c, o));
-        } else {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const long long ob = o + 4 * q + b;
-                    const unsigned byte = (ob >= 0 && ob < a.in_count) ? (unsigned)a.in[src_offset(a, c, ob)] : a.fill;
-                    v |= byte << (8 * b);
-                }
-                w[q] = v;
-            }
-            *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        stage_chunk16(a, c, o, d, aligned16);
     }
 }
 

@@ -266,3 +266,45 @@ def test_gpu_drop_in_class_extension(ext_oracle):
             assert np.array_equal(out[:got], orc.run_app(data, L, 1, DSD512, 352800, scale, amp, clip))
     finally:
         host.dsdhost_set_extension_filters(0)
+
+
+def _ext_jobs():
+    from dsf2flac_b200 import batch
+    return [batch.Job(seeded_bytes(2, 64 * 700, 1), DSD512, 352800, msb_flag=True, bits=24, dither=True, extensions=True,
+                      length_samples=64 * 700 * 8 - 11),
+            batch.Job(seeded_bytes(3, 128 * 300, 2), DSD512, 176400, msb_flag=False, bits=16, dither=True, extensions=True),
+            batch.Job(seeded_bytes(1, 5000, 3), DSD64, 88200, bits=20, dither=False)]
+
+
+def _check_stitched(orc_for, jobs, results):
+    from dsf2flac_b200 import batch
+    for j, got in zip(jobs, batch.stitch(jobs, results)):
+        scale, amp, clip = filters.app_params(j.bits, j.scale_db, j.dither)
+        want = orc_for(j).run_app(j.planar, j.length_samples, j.msb_flag, j.dsd_fs, j.out_fs, scale, amp, clip)
+        assert np.array_equal(got, want), j.fir.ratio
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_extension_shards_stitch_cpu(ext_oracle, oracle, world):
+    """Time segments of a divide-by-64 / -128 stream carry a 143- / 287-byte halo; the plan, the halo and the
+    positional dither give every world size the unsharded result (CPU stand-in of the C ABI)."""
+    from dsf2flac_b200 import batch
+    from tests import standin
+    jobs = _ext_jobs()
+    runner = batch.BatchRunner(make_ctx=standin.make_ctx)
+    results = []
+    for r in range(world):
+        results += runner.run(jobs, r, world, align_frames=64)
+    _check_stitched(lambda j: ext_oracle.use(j.fir.ratio) if j.extensions else oracle, jobs, results)
+
+
+@pytest.mark.gpu
+def test_gpu_extension_shards_stitch(ext_oracle, oracle):
+    from dsf2flac_b200 import batch
+    jobs = _ext_jobs()
+    runner = batch.BatchRunner()
+    results = []
+    for r in range(4):
+        results += runner.run(jobs, r, 4, align_frames=64)
+    runner.close()
+    _check_stitched(lambda j: ext_oracle.use(j.fir.ratio) if j.extensions else oracle, jobs, results)
