@@ -358,7 +358,7 @@ def run_gpu_arm(args, wl):
         # (b) the same class with the file's bytes handed over in bulk (DsdDecimator::setBulkSource)
         for name, fn, count in (("stepped_reader", host.dsdhost_run_app, pb), ("bulk_source", host.dsdhost_run_app_bulk, nbytes)):
             best = None
-            for _ in range(2):                              # the first call pays context creation
+            for _ in range(3):                              # the first call pays context creation and page-locking
                 t0 = time.perf_counter()
                 n = fn(pin_in.ptr, nch, nbytes, count * 8, 0x69, 1, dsd_fs, out_fs, scale, amp, clip, args.lut, 0, out.ptr, cap)
                 dt = time.perf_counter() - t0

@@ -112,6 +112,19 @@ private:
 
     const dsf2flac_uint8* bulk;          // bulk source (nullptr: drain the reader)
     dsf2flac_int64 bulkBlock, bulkCount, bulkStride;
+
+    // Bulk sources only: while the caller consumes `block` (FLAC-encodes it), the block after it is already
+    // on its way -- submitted on a slot of its own into `ahead` with the parameters of the last call.
+    // refill() takes it if position, parameters and dither position still match, else drops it.
+    void prefetch(int outKind);
+    void dropAhead();
+    void* ahead;
+    size_t aheadCap;
+    bool aheadBusy;
+    int aheadKind;
+    dsf2flac_int64 aheadPos, aheadFrames;
+    dsf2flac_uint64 aheadSample0;
+    dsf2flac_float64 aheadScale, aheadDither, aheadClip;
 };
 
 #endif // DSDDECIMATOR_H

@@ -126,6 +126,41 @@ int64_t dsdhost_run_app_bulk(const uint8_t* planar, int nch, int64_t nbytes, int
                    read_ahead, out, out_cap_frames, true);
 }
 
+// A scripted caller, for tests of the block cache and the read-ahead: ops[2k] = what, ops[2k+1] = argument.
+//   0: step() x arg          1: getSamples(arg frames, scale_a)     2: getSamples(arg frames, scale_b)
+//   3: setLutPrecision(arg)  4: setReadAheadFrames(arg)
+// int32 output frames are appended to `out`.  Returns frames written, -1 on error, -2 if `out` is too small.
+int64_t dsdhost_run_script(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples, uint8_t idle,
+                           int msb_flag, uint32_t dsd_fs, uint32_t out_fs, int bulk, const int64_t* ops, int nops,
+                           double scale_a, double scale_b, double dither, double clip, int32_t* out,
+                           int64_t out_cap_frames) {
+    MemorySampleReader rd(planar, (uint32_t)nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    if (bulk) {
+        int64_t delivered = (length_samples + 7) / 8 + 1;
+        if (delivered > nbytes) delivered = nbytes;
+        if (!dec.setBulkSource(planar, 0, delivered, nbytes)) { g_error = dec.getErrorMsg(); return -1; }
+    }
+    int64_t done = 0;
+    for (int k = 0; k < nops; ++k) {
+        const int64_t what = ops[2 * k], arg = ops[2 * k + 1];
+        if (what == 0) {
+            for (int64_t i = 0; i < arg; ++i) dec.step();
+        } else if (what == 1 || what == 2) {
+            if (done + arg > out_cap_frames) return -2;
+            dec.getSamples(out + done * nch, (dsf2flac_uint32)(arg * nch), what == 1 ? scale_a : scale_b, dither, clip);
+            done += arg;
+        } else if (what == 3) {
+            if (!dec.setLutPrecision((int)arg)) { g_error = dec.getErrorMsg(); return -1; }
+        } else if (what == 4) {
+            dec.setReadAheadFrames((dsf2flac_uint32)arg);
+        }
+        if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    }
+    return done;
+}
+
 // Header facts of a DSF / DSDIFF file as the reference's readers report them, plus what the bulk
 // path derives: info = {channels, sampling frequency, msbIsPlayedFirst, kind (1 DSF, 2 DSDIFF),
 // source_block_bytes}; *length_samples = getLength(); *delivered_bytes = stream bytes per channel

@@ -21,6 +21,13 @@ struct dsdgpu_ctx {
     long long dither_stride = 0;
     long long source_block = 0;        // include/dsdgpu.h "source_block_bytes"
     char err[128] = "";
+    // dsdgpu_submit is DEFERRED here: the arguments are kept and the work is done in dsdgpu_wait, so a host
+    // that touches its buffers between submit and wait (which the real, asynchronous library forbids) fails
+    struct Pending {
+        bool busy = false;
+        const uint8_t* in; size_t in_stride; int64_t in_first, in_count; uint8_t fill; int64_t p0, nframes;
+        double scale, dither_amp, clip; uint64_t dither_first_sample; int out_kind; void* out;
+    } pending[DSDGPU_SLOTS];
 };
 
 namespace {
@@ -126,12 +133,23 @@ int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t*, size_t, int64_t, int
     snprintf(ctx->err, sizeof ctx->err, "stand-in has no device");
     return DSDGPU_ERR_NODEVICE;
 }
-int dsdgpu_submit(dsdgpu_ctx* ctx, int, const uint8_t*, size_t, int64_t, int64_t, uint8_t, int64_t, int64_t,
-                  double, double, double, uint64_t, int, void*) {
-    snprintf(ctx->err, sizeof ctx->err, "stand-in has no device");
-    return DSDGPU_ERR_NODEVICE;
+int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride, int64_t in_first, int64_t in_count,
+                  uint8_t fill, int64_t p0, int64_t nframes, double scale, double dither_amp, double clip,
+                  uint64_t dither_first_sample, int out_kind, void* out) {
+    if (slot < 0 || slot >= DSDGPU_SLOTS) return DSDGPU_ERR_ARG;
+    dsdgpu_ctx::Pending& p = ctx->pending[slot];
+    if (p.busy) { snprintf(ctx->err, sizeof ctx->err, "slot %d is still in flight", slot); return DSDGPU_ERR_STATE; }
+    p = {true, in, in_stride, in_first, in_count, fill, p0, nframes, scale, dither_amp, clip, dither_first_sample, out_kind, out};
+    return DSDGPU_OK;
 }
-int dsdgpu_wait(dsdgpu_ctx*, int) { return DSDGPU_ERR_STATE; }
+int dsdgpu_wait(dsdgpu_ctx* ctx, int slot) {
+    if (slot < 0 || slot >= DSDGPU_SLOTS) return DSDGPU_ERR_ARG;
+    dsdgpu_ctx::Pending& p = ctx->pending[slot];
+    if (!p.busy) { snprintf(ctx->err, sizeof ctx->err, "slot %d has nothing in flight", slot); return DSDGPU_ERR_STATE; }
+    p.busy = false;
+    return dsdgpu_decimate_host(ctx, p.in, p.in_stride, p.in_first, p.in_count, p.fill, p.p0, p.nframes, p.scale, p.dither_amp,
+                                p.clip, p.dither_first_sample, p.out_kind, p.out);
+}
 int dsdgpu_dither_fill_device(dsdgpu_ctx*, uint64_t, int64_t, double*, void*) { return DSDGPU_ERR_NODEVICE; }
 
 }  // extern "C"

@@ -65,3 +65,21 @@ def test_dropin_bulk_source_equals_stepped_reader(oracle):
         out = np.zeros((len(want) + 16, 2), dtype=np.int32)
         n = fn(data.ctypes.data, 2, nbytes, L, 0x69, 1, DSD64, 88200, scale, amp, clip, 64, 50_000, out.ctypes.data, len(out))
         assert n == len(want) and np.array_equal(out[:n], want)
+
+
+def test_read_ahead_of_bulk_sources_on_gpu(oracle):
+    """DsdDecimator over a bulk source keeps the next block in flight on a slot of its own; a scripted caller
+    that carries on, changes parameters, seeks and switches table precision gets the stepped reader's samples."""
+    from tests.test_host_logic import run_script
+    host = capi.host_lib()
+    fir = filters.pick(DSD64, 88200)
+    data = seeded_bytes(2, 400000, 77)
+    L = 400000 * 8 - 6
+    sa, amp, clip = filters.app_params(24, dither=True)
+    ops = [(4, 20000), (0, fir.nlut + 1), (1, 1024), (1, 1), (1, 30000), (2, 500), (1, 10), (0, 3), (1, 25000), (0, 1), (1, 5),
+           (4, 1700), (1, 3000), (3, 32), (1, 2000), (3, 64), (1, 2000), (4, 50000), (1, 30000)]
+    want = run_script(host, data, L, 88200, False, ops, sa, sa * 0.5, amp, clip)
+    got = run_script(host, data, L, 88200, True, ops, sa, sa * 0.5, amp, clip)
+    assert np.array_equal(got, want)
+    first = oracle.run_raw(data, L, 1, DSD64, 88200, fir.nlut + 1, 31025, sa, amp, clip)
+    assert np.array_equal(got[:31025], first)

@@ -94,3 +94,39 @@ def test_bulk_source_equals_stepped_reader(host, oracle):
         out = np.zeros((len(want) + 16, 3), dtype=np.int32)
         n = fn(data.ctypes.data, 3, nbytes, L, 0x69, 0, DSD64, 176400, scale, amp, clip, 64, 4000, out.ctypes.data, len(out))
         assert n == len(want) and np.array_equal(out[:n], want)
+
+
+def run_script(host, data, L, fs, bulk, ops, scale_a, scale_b, dither, clip, dsd_fs=DSD64):
+    nch, nbytes = data.shape
+    flat = (C.c_int64 * (2 * len(ops)))(*[int(x) for pair in ops for x in pair])
+    cap = sum(a for w, a in ops if w in (1, 2)) + 8
+    out = np.zeros((cap, nch), dtype=np.int32)
+    n = host.dsdhost_run_script(data.ctypes.data, nch, nbytes, L, 0x69, 1, dsd_fs, fs, int(bulk), flat, len(ops), scale_a,
+                                scale_b, dither, clip, out.ctypes.data, cap)
+    assert n >= 0, host.dsdhost_last_error()
+    return out[:n]
+
+
+@pytest.mark.parametrize("ratio", list(RATES))
+def test_read_ahead_of_bulk_sources_is_invisible(host, oracle, ratio):
+    """With a bulk source the class submits the next block while the caller consumes the current one (the
+    stand-in defers that work until the block is claimed).  Whatever the caller does next -- carries on,
+    changes the scale, skips bytes with step(), switches table precision, shrinks the read-ahead -- the
+    samples are those of the stepped reader path, which other tests hold to the oracle."""
+    fs = RATES[ratio]
+    data = seeded_bytes(2, 9000, 40 + ratio)
+    L = 9000 * 8 - 6
+    sa, amp, clip = filters.app_params(24, dither=True)
+    sb = sa * 0.5
+    fir = filters.pick(DSD64, fs)
+    ops = [(4, 300), (0, fir.nlut + 1), (1, 1024), (1, 1), (1, 700),        # carries on across block boundaries
+           (2, 500), (2, 64), (1, 10),                                       # scale changes: block in flight is dropped
+           (0, 3), (1, 400), (0, 1), (1, 5),                                 # seeks: position no longer matches
+           (4, 17), (1, 300), (3, 32), (1, 200), (3, 64), (1, 200),          # read-ahead shrinks; table precision switches
+           (4, 5000), (1, 3000)]                                             # runs far past the end of the data
+    want = run_script(host, data, L, fs, False, ops, sa, sb, amp, clip)
+    got = run_script(host, data, L, fs, True, ops, sa, sb, amp, clip)
+    assert np.array_equal(got, want)
+    # and the plain part of it against the oracle directly
+    first = oracle.run_raw(data, L, 1, DSD64, fs, fir.nlut + 1, 1725, sa, amp, clip)
+    assert np.array_equal(got[:1725], first)
