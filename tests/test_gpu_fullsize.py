@@ -123,3 +123,50 @@ def test_config4_size_device_resident_periodicity(oracle):
         g.decimate_device(d_in, stride, -front, nbytes + front, 0x69, fir.nlut + (n - cnt) * fir.nstep, cnt, scale, amp, clip,
                           0, capi.OUT_INT32, d_chk)
         assert torch.equal(d_chk, d_out[n - cnt:])
+
+
+def test_config4_as_stated_divide_by_64_extension(oracle):
+    """BASELINE config 4 as it is written -- DSD512 stereo, 600 s -> 352.8 kHz -- is a ratio (64) the reference
+    rejects; with the extension filter it runs as two passes of the ring kernel over a 3.4 GB plane of running
+    sums.  Same size-independent checks: the first second against the reference's arithmetic on the extension
+    filter (the C restatement, pinned to oracle/_ref by tests/test_extension.py), periodicity of a tiled
+    stream across all ten minutes, and the segmented and direct kernels on the last 100 000 frames."""
+    import torch
+    fs = 8 * DSD64
+    sec = fs // 8
+    seconds = 600
+    nbytes = sec * seconds
+    fir = filters.pick(fs, 352800, extensions=True)
+    assert (fir.ratio, fir.nlut, fir.nstep) == (64, 144, 8)
+    n = filters.app_frames(nbytes * 8, fir)
+    assert n == nbytes // 8 - 17 == 211679983
+    one = sdm_stream(2, sec, fs)
+    scale, amp, clip = filters.app_params(24, dither=False)
+    front = 3                                                # (p0 - in_first + 1) % 4 == 0 with p0 = 144
+    stride = (nbytes + front + 255) // 256 * 256
+    d_in = torch.full((2, stride), 0x69, dtype=torch.uint8, device="cuda")
+    d_in[:, front:front + nbytes] = torch.from_numpy(one).cuda().repeat(1, seconds)
+    d_out = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    oracle.set_custom_filter(fir)
+    try:
+        with capi.DsdGpu(filters.build_lut(fir, 1), 2, fir.nstep) as g:
+            g.decimate_device(d_in, stride, -front, nbytes + front, 0x69, fir.nlut, n, scale, amp, clip, 0, capi.OUT_INT32, d_out)
+            torch.cuda.synchronize()
+            fps = sec // fir.nstep
+            want = oracle.run_raw(np.ascontiguousarray(np.tile(one, (1, 2))[:, :sec + 400]), 1 << 40, 1, fs, 352800,
+                                  fir.nlut + 1, fps, scale, amp, clip)
+            assert np.array_equal(d_out[:fps].cpu().numpy(), want)
+            base = d_out[fps:2 * fps]
+            for k in (2, 77, 300, 598):
+                assert torch.equal(d_out[k * fps:(k + 1) * fps], base), k
+            tail = d_out[599 * fps:n]
+            assert torch.equal(tail[:len(tail) - 32], base[:len(tail) - 32])
+            cnt = 100_000
+            for kernel in (capi.KERNEL_SEGMENTED, capi.KERNEL_DIRECT):
+                g.set_option("kernel", kernel)
+                d_chk = torch.empty((cnt, 2), dtype=torch.int32, device="cuda")
+                g.decimate_device(d_in, stride, -front, nbytes + front, 0x69, fir.nlut + (n - cnt) * fir.nstep, cnt, scale, amp,
+                                  clip, 0, capi.OUT_INT32, d_chk)
+                assert torch.equal(d_chk, d_out[n - cnt:]), kernel
+    finally:
+        oracle.set_custom_filter(None)
