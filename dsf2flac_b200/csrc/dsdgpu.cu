@@ -1165,10 +1165,16 @@ int launch_seg_pass(dsdgpu_ctx* ctx, const DecimateArgs& a, int row_stride, int 
     return DSDGPU_OK;
 }
 
-int launch_seg(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
-    if (!ctx->d_lut_seg) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: no table images");
+// samples per thread of the segmented kernel: the largest of 4, 2, 1 that fits shared memory, 0 = none does
+int seg_samples_per_thread(const dsdgpu_ctx* ctx) {
     int ks = 4;
     while (ks >= 1 && SegLayout::smem_bytes(SegLayout::NTHR * ks, ctx->nch, ctx->nstep) > SegLayout::SMEM_LIMIT) ks >>= 1;
+    return ctx->d_lut_seg ? ks : 0;
+}
+
+int launch_seg(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+    if (!ctx->d_lut_seg) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: no table images");
+    const int ks = seg_samples_per_thread(ctx);
     if (ks < 1) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: %d channels x %d bytes per frame do not fit shared memory", ctx->nch, ctx->nstep);
     const int samples = SegLayout::NTHR * ks;
     const int row_stride = (int)SegLayout::row_stride(samples, ctx->nch, ctx->nstep);
@@ -1246,7 +1252,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     int kernel = ctx->kernel;
     if (kernel == DSDGPU_KERNEL_AUTO)
         kernel = ring_ok ? DSDGPU_KERNEL_RING : skew_ok ? DSDGPU_KERNEL_SKEW
-               : ctx->d_lut_seg ? DSDGPU_KERNEL_SEGMENTED : DSDGPU_KERNEL_DIRECT;
+               : seg_samples_per_thread(ctx) > 0 ? DSDGPU_KERNEL_SEGMENTED : DSDGPU_KERNEL_DIRECT;
     if (kernel == DSDGPU_KERNEL_RING) {
         if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) or of the divide-by-64 extension (144/8), and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;

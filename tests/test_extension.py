@@ -308,3 +308,44 @@ def test_gpu_extension_shards_stitch(ext_oracle, oracle):
         results += runner.run(jobs, r, 4, align_frames=64)
     runner.close()
     _check_stitched(lambda j: ext_oracle.use(j.fir.ratio) if j.extensions else oracle, jobs, results)
+
+
+@pytest.mark.gpu
+def test_gpu_odd_geometries_and_limits():
+    """Geometries nobody ships: the any-geometry kernels take them (or decline with a message), never crash.
+    100 tables x 3-byte frame hop, 5 channels; 40 channels at a 32-byte hop (does not fit the segmented
+    kernel's shared memory: AUTO falls back to the direct kernel, asking for the segmented one is an error)."""
+    rng = np.random.default_rng(5)
+
+    def reference_sums(lut, data, nstep, p0, nframes, fill=0x69):
+        nch, nbytes = data.shape
+        out = np.zeros((nframes, nch))
+        for i in range(nframes):
+            for c in range(nch):
+                s = 0.0
+                for t in range(lut.shape[0]):
+                    j = p0 + i * nstep - t
+                    s = s + lut[t, data[c, j] if 0 <= j < nbytes else fill]
+                out[i, c] = s
+        return out
+
+    lut = (rng.random((100, 256)) - 0.5) * 0.3
+    data = seeded_bytes(5, 700, 8)
+    want = reference_sums(lut, data, 3, 40, 230)
+    for kernel in (capi.KERNEL_AUTO, capi.KERNEL_SEGMENTED, capi.KERNEL_DIRECT):
+        with capi.DsdGpu(lut, 5, 3) as g:
+            g.set_option("kernel", kernel)
+            got = g.decimate_host(data, 40, 230, 1.0, out_kind=capi.OUT_FLOAT64)
+            assert got.tobytes() == want.tobytes(), kernel
+    lut = (rng.random((80, 256)) - 0.5) * 0.3
+    data = seeded_bytes(40, 1200, 9)
+    want = reference_sums(lut, data, 32, 100, 30)
+    with capi.DsdGpu(lut, 40, 32) as g:
+        got = g.decimate_host(data, 100, 30, 1.0, out_kind=capi.OUT_FLOAT64)
+        assert got.tobytes() == want.tobytes()
+        g.set_option("kernel", capi.KERNEL_SEGMENTED)
+        with pytest.raises(capi.DsdGpuError, match="shared memory"):
+            g.decimate_host(data, 100, 30, 1.0, out_kind=capi.OUT_FLOAT64)
+    for nlut, nstep in ((641, 8), (72, 65), (0, 4)):
+        with pytest.raises(capi.DsdGpuError):
+            capi.DsdGpu(np.zeros((max(nlut, 1), 256)) if nlut else np.zeros((1, 256))[:0].reshape(0, 256), 2, nstep)
