@@ -60,6 +60,14 @@ namespace dsdgpu {
 // NLUT rounded up to a multiple of 16 steps, the extra slots hold -0.0 (the identity of fp64
 // addition), so a wrapped lane needs no second copy: slot PERIOD + s - j is bank pair (s - j) mod 16.
 //
+// Short filters (NLUT = 30, NLUT = 12) keep COPIES = 2 / 4 images of their (small) tables, image a shifted by
+// a * 16 / COPIES slots against the bank pattern.  Lane i of a half-warp reads image i % COPIES with skew
+// j = i / COPIES, so that its bank pair is (tap + (16 / COPIES) * (i % COPIES)) mod 16 -- 16 distinct values
+// with only 16 / COPIES distinct skews: the "early" steps, in which a lane may still be finishing its
+// previous frames (two FMAs per table value, two byte windows), shrink from 16 to 8 (of 32) and to 4 (of 12;
+// with four images the divide-by-8 period needs no pad slots at all).  The byte buffer of the upper
+// half-warp starts 64 bytes further on: its 16 window words then take the banks the lower half leaves free.
+//
 // NSTEP = 8 (EXTENSION, decimation by 64: 144 tables, run as two passes of 72 over a plane of running
 // sums): frames lie 8 bytes apart, so frame k of a lane reads the word stream of frame 0 shifted by
 // 2k words -- six history words instead of three -- and a lane's sums start from the previous pass's
@@ -72,20 +80,23 @@ struct RingGeom {
     static constexpr int NLUT = NLUT_;                // tables
     static constexpr int NSTEP = NSTEP_;              // bytes between successive frames
     static constexpr bool DUP = (NLUT == 72);         // 72-step periods with tail copies (see above)
-    static constexpr int PERIOD = DUP ? 72 : (NLUT + 15) / 16 * 16;   // steps per period
+    static constexpr int COPIES = (!Q32 && NLUT == 12) ? 4 : (!Q32 && NLUT == 30) ? 2 : 1;   // images of the tables
+    static constexpr int PERIOD = DUP ? 72 : COPIES == 4 ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
     static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
     static constexpr int KF = 4;                      // consecutive frames per lane
     static constexpr int KR = KR_;                    // rounds (periods) per tile
     static constexpr int NWARP = NWARP_;
     static constexpr int NTHR = 32 * NWARP;
     static constexpr int ELEM = Q32 ? 4 : 8;          // bytes per table entry
-    static constexpr int SKEW_LANES = Q32 ? 32 : 16;  // lanes of one conflict-free load = skew values
-    static constexpr int EARLY_GROUPS = SKEW_LANES / 4;   // 4-step groups in which some lane is still wrapped
-    static constexpr int EARLY_STEPS = SKEW_LANES;
-    static constexpr int ROW = Q32 ? 96 : (DUP ? 80 : PERIOD);   // slots per table row
+    static constexpr int SKEW_LANES = Q32 ? 32 : 16;  // lanes of one conflict-free load
+    static constexpr int NSKEW = SKEW_LANES / COPIES; // distinct skew values
+    static constexpr int EARLY_GROUPS = (NSKEW + 3) / 4;  // 4-step groups in which some lane is still wrapped
+    static constexpr int EARLY_STEPS = NSKEW;
+    static constexpr int ROW = Q32 ? 96 : (DUP ? 80 : (PERIOD + 15) / 16 * 16);   // slots per table row
     static constexpr int ROW_BYTES = ROW * ELEM;      // a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
-    static constexpr int LUT_BYTES = GUARD_BYTES + 256 * ROW_BYTES;
+    static constexpr int COPY_STRIDE = 256 * ROW_BYTES + (COPIES > 1 ? 128 : 0);   // image a: + a * (COPY_STRIDE + ELEM * NSKEW)
+    static constexpr int LUT_BYTES = GUARD_BYTES + COPIES * COPY_STRIDE;
     // a tile has two halves (lanes 0-15 / 16-31 of every warp), each with its own byte buffer
     static constexpr int LANE_BYTES = KF * NSTEP;     // bytes between the windows of neighbouring lanes
     static constexpr int BLK_PER_ROUND = 16 * NWARP;  // 4-frame blocks per half per round
@@ -94,16 +105,20 @@ struct RingGeom {
     static constexpr int HOP = NSTEP * FR_PER_ROUND;  // bytes between a lane's rounds
     static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
     static constexpr int QH = NSTEP == 8 ? 6 : 3;     // window words of history: frame k reads NSTEP*k bytes further on
-    static constexpr int HALF_BYTES = NSTEP * NTP + 256 + (NSTEP == 8 ? 16 : 0);
+    static constexpr int HALF_SHIFT = NSTEP == 8 ? 16 : COPIES > 1 ? 64 : 0;   // bank offset of the upper half-warp's buffer
+    static constexpr int HALF_BYTES = NSTEP * NTP + 256 + HALF_SHIFT;
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
     static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
     static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
     // where the emitter is called from: spread over the groups after the early ones if there are enough
-    static constexpr bool EMIT_SPREAD = GROUPS >= EARLY_GROUPS + 6;
+    static constexpr bool EMIT_SPREAD = GROUPS >= EARLY_GROUPS + 7;   // fetch, four quantise calls, store, prefetch: one group each
+    static constexpr int LATE_GROUPS = GROUPS - EARLY_GROUPS;
+    static constexpr bool EMIT_SHORT = !EMIT_SPREAD && LATE_GROUPS >= 1;     // quantise calls shared out over the late groups
+    static constexpr int EMIT_PER_GROUP = EMIT_SHORT ? (4 + LATE_GROUPS - 1) / LATE_GROUPS : 0;
     static_assert(!Q32 || DUP, "32-bit tables exist for the 72-table filter");
     static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8, "frame hop of 8, 16, 32 or 64 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
-    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == (NSTEP == 8 ? 16 : 0) && ROW_BYTES % 128 == 0, "staging chunks / bank pattern");
+    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == HALF_SHIFT && ROW_BYTES % 128 == 0 && PERIOD % 4 == 0, "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
     static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
 };
@@ -212,6 +227,7 @@ RING_HD int ring_lane_skew(int l) {
         return (g >> 1) + 4 * q;
     }
     const int h = (l >> 4) & 1, i = l & 15;
+    if (G::COPIES > 1) return i / G::COPIES;            // image i % COPIES (ring_lane_init); see the top of this file
     if (G::LANE_BYTES == 32) return i;                  // lane stride of eight words (see the top of this file)
     if (G::LANE_BYTES == 8) {
         // lane stride of two words: window word of lane i = 2*i + (j >> 2); found by search
@@ -261,8 +277,10 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     r.unit = unit;
     r.one = unit > 0.0 ? 1 : 0;
     r.shift = 8u * (uint32_t)phi;
-    r.lnew = (uint32_t)(G::GUARD_BYTES - G::ELEM * j);
-    r.lwrap = (uint32_t)(G::GUARD_BYTES + G::ELEM * (G::PERIOD - j));
+    const int image = G::COPIES > 1 ? (l & 15) % G::COPIES : 0;
+    const int base = G::GUARD_BYTES + image * (G::COPY_STRIDE + G::ELEM * G::NSKEW);
+    r.lnew = (uint32_t)(base - G::ELEM * j);
+    r.lwrap = (uint32_t)(base + G::ELEM * (G::PERIOD - j));
     r.lalt = (uint32_t)(G::DUP ? G::ELEM * 8 * (j >> 3) : 0);
 #pragma unroll
     for (int g = 0; g < G::EARLY_GROUPS; ++g) {
@@ -310,6 +328,14 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             if (g >= q0 && g < q0 + 4) emit.quantise(g - q0, r.value(g - q0));
             if (g == q0 + 4) emit.store();
             if (g == q0 + 5) emit.prefetch();
+        } else if (G::EMIT_SHORT) {
+            // few groups after the early ones: the quantise calls shared out in front of them, the store after the last (ring_tail)
+            if (g == G::EARLY_GROUPS) emit.fetch();
+            if (g >= G::EARLY_GROUPS) {
+#pragma unroll
+                for (int k = (g - G::EARLY_GROUPS) * G::EMIT_PER_GROUP; k < (g - G::EARLY_GROUPS + 1) * G::EMIT_PER_GROUP && k < 4; ++k)
+                    emit.quantise(k, r.value(k));
+            }
         }
         // window words: v[0] = V(g), v[1..3] = V(g-1..g-3); frame k reads the 4 bytes NSTEP*k further on
         uint32_t x[4];
@@ -409,7 +435,7 @@ RING_HD void ring_head(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
 template <class G, class Emit, class Trace>
 RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        Emit& emit, const Trace& tr) {
-    if (!G::EMIT_SPREAD) {               // short periods: the whole emitter before the remaining steps
+    if (!G::EMIT_SPREAD && !G::EMIT_SHORT) {   // shortest periods: the whole emitter before the remaining steps
         emit.fetch();
 #pragma unroll
         for (int k = 0; k < 4; ++k) emit.quantise(k, r.value(k));
@@ -417,6 +443,10 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
         emit.prefetch();
     }
     ring_groups<G, G::EARLY_GROUPS, G::GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
+    if (G::EMIT_SHORT) {
+        emit.store();
+        emit.prefetch();
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = (typename RingLane<G>::acc_t)emit.init(k); }
 #pragma unroll
@@ -476,16 +506,17 @@ inline void ring_build_lut_image(const double* lut, unsigned char* image, double
     for (int i = 0; i < G::LUT_BYTES; ++i) image[i] = 0;
     if (!G::Q32)                                        // pad slots: -0.0, the identity of fp64 addition
         for (int i = 0; i < G::LUT_BYTES / 8; ++i) reinterpret_cast<double*>(image)[i] = -0.0;
-    auto put = [&](int e, int slot, double v) {
-        unsigned char* at = image + G::GUARD_BYTES + e * G::ROW_BYTES + slot * G::ELEM;
+    auto put = [&](int image_no, int e, int slot, double v) {
+        unsigned char* at = image + G::GUARD_BYTES + image_no * (G::COPY_STRIDE + G::ELEM * G::NSKEW) + e * G::ROW_BYTES + slot * G::ELEM;
         if (G::Q32) *reinterpret_cast<int32_t*>(at) = (int32_t)(v / unit);
         else *reinterpret_cast<double*>(at) = v;
     };
-    for (int e = 0; e < 256; ++e) {
-        for (int t = 0; t < G::NLUT; ++t) put(e, t, lut[t * 256 + e]);
-        for (int copy = 1; G::DUP && G::NLUT + 8 * copy <= G::ROW; ++copy)      // tail copies: slot = tap + 8*copy
-            for (int m = 0; m < 8; ++m) put(e, 64 + m + 8 * copy, lut[(64 + m) * 256 + e]);
-    }
+    for (int c = 0; c < G::COPIES; ++c)
+        for (int e = 0; e < 256; ++e) {
+            for (int t = 0; t < G::NLUT; ++t) put(c, e, t, lut[t * 256 + e]);
+            for (int copy = 1; G::DUP && G::NLUT + 8 * copy <= G::ROW; ++copy)      // tail copies: slot = tap + 8*copy
+                for (int m = 0; m < 8; ++m) put(c, e, 64 + m + 8 * copy, lut[(64 + m) * 256 + e]);
+        }
 }
 
 }  // namespace dsdgpu

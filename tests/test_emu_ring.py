@@ -47,7 +47,7 @@ def test_ring_lanes(nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid)
     assert rep["checked"] == nframes * nch and rep["mismatches"] == 0
     assert rep["missing"] == 0 and rep["duplicates"] == 0 and rep["oob"] == 0
     assert rep["lut_wavefronts"] == rep["lut_halfwarp_loads"]
-    if (p0 - in_first + 1) % 4 == 0 and nwarp != 12:     # one-word lane stride (divide-by-8): two-way by construction
+    if (p0 - in_first + 1) % 4 == 0:
         assert rep["word_wavefronts"] == rep["word_loads"]
     else:
         assert rep["word_wavefronts"] <= 2 * rep["word_loads"]
