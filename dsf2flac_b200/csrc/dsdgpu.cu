@@ -955,6 +955,10 @@ struct dsdgpu_ctx {
     dsdgpu_slot own;                         // scratch for the device entry point
     unsigned long long launches = 0;
     char err[256] = "";
+    // "trace" option: per-chunk timeline of dsdgpu_decimate_host (events on the slot streams), printed to stderr
+    bool trace = false;
+    struct TraceRow { cudaEvent_t e[4]; int slot; long long frames; };
+    std::vector<TraceRow> trace_rows;
 };
 
 namespace {
@@ -1479,6 +1483,8 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "slots")) {
         if (value < 1 || value > DSDGPU_SLOTS) return fail(ctx, DSDGPU_ERR_ARG, "slots must be 1..%d", DSDGPU_SLOTS);
         ctx->pipeline_slots = (int)value;
+    } else if (!strcmp(key, "trace")) {
+        ctx->trace = value != 0;
     } else if (!strcmp(key, "chunk_frames")) {
         if (value < 1) return fail(ctx, DSDGPU_ERR_ARG, "chunk_frames must be >= 1");
         ctx->chunk_frames = value;
@@ -1636,14 +1642,38 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
     int64_t lo, hi;
     run_window(ctx, in_first, in_count, p0, nframes, lo, hi);
     SourceView v;
+    dsdgpu_ctx::TraceRow tr;
+    if (ctx->trace) {
+        for (auto& e : tr.e) CUDA_TRY(ctx, cudaEventCreate(&e));
+        tr.slot = slot; tr.frames = nframes;
+        CUDA_TRY(ctx, cudaEventRecord(tr.e[0], s.stream));
+    }
     rc = stage_source(ctx, s, in, in_stride, in_first, in_count, fill, lo, hi, p0 - (ctx->nlut - 1), p0 + 1, v);
     if (rc) return rc;
+    if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tr.e[1], s.stream));
     rc = enqueue_decimate(ctx, s, v.d, v.stride, v.block_shift, v.first, v.count, fill, p0, nframes, scale, dither_amp,
                           clip, dither_first_sample, out_kind, s.d_out, s.stream);
     if (rc) return rc;
+    if (ctx->trace) CUDA_TRY(ctx, cudaEventRecord(tr.e[2], s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    if (ctx->trace) { CUDA_TRY(ctx, cudaEventRecord(tr.e[3], s.stream)); ctx->trace_rows.push_back(tr); }
     s.busy = true;
     return DSDGPU_OK;
+}
+
+// prints and clears the timeline collected since the last call (times in ms from the first chunk's submission point)
+static void dump_trace(dsdgpu_ctx* ctx) {
+    if (ctx->trace_rows.empty()) return;
+    cudaEvent_t base = ctx->trace_rows[0].e[0];
+    fprintf(stderr, "# dsdgpu trace: chunk slot frames | upload starts, upload done, kernel done, download done [ms]\n");
+    for (size_t k = 0; k < ctx->trace_rows.size(); ++k) {
+        float t[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], base, ctx->trace_rows[k].e[i]);
+        fprintf(stderr, "%3zu %d %8lld | %7.3f %7.3f %7.3f %7.3f\n", k, ctx->trace_rows[k].slot, ctx->trace_rows[k].frames, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& r : ctx->trace_rows)
+        for (auto& e : r.e) cudaEventDestroy(e);
+    ctx->trace_rows.clear();
 }
 
 static int launch_dop(dsdgpu_ctx* ctx, const SourceView& v, uint8_t fill, int64_t pm0, int64_t nframes, int reverse_bits,
@@ -1776,6 +1806,7 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
     }
     for (int s = 0; s < DSDGPU_SLOTS; ++s)
         if (inflight[s]) { int r2 = dsdgpu_wait(ctx, s); if (!rc) rc = r2; }
+    if (ctx->trace) dump_trace(ctx);
     return rc;
 }
 
