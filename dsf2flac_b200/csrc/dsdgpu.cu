@@ -783,7 +783,8 @@ dop_pack_wide_kernel(DecimateArgs a, long long pm0, int reverse) {
 // glibc rand() by position.  r[i] = r[i-31] + r[i-3] (mod 2^32) for i >= 34, draw k = r[344+k]>>1.
 // With x^31 = x^28 + 1:  r[3+m+i] = sum_k c_k r[3+i+k],  c = x^m mod (x^31 - x^28 - 1).
 //
-// The stream is cut into pieces of 248 values (124 output samples) per lane, 32 lanes per warp.
+// The stream is cut into pieces of 248 values (124 output samples) per lane, 32 lanes per warp
+// (twice that per lane is slower: the kernel is bound by latency and occupancy, not by instruction count).
 // The host jumps to the first value of the call: c = x^m as a product of precomputed powers
 // (4 bits of m at a time), applied to the seed words -> 61 consecutive words ("segment").
 // glibc_rand_fill_kernel: every warp advances that segment to its own start by up to three
@@ -867,7 +868,7 @@ glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ l
         rand_apply_poly(jump_polys + ((size_t)level * kRandLevel + u) * kRandDeg, cur, oth, poly_s[wl], lane);
         uint32_t* tmp = cur; cur = oth; oth = tmp;
     }
-    // this lane's state: x^(248*lane) applied to the warp's segment
+    // this lane's state: x^(kRandLaneValues*lane) applied to the warp's segment
     uint32_t ring[kRandDeg];                                        // ring[i] = r[n - 31 + i]
     {
         uint32_t c[kRandDeg];
@@ -882,7 +883,8 @@ glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ l
         }
     }
     const double rmax = 2147483647.0, rcp = 1.0 / 2147483647.0;
-    const long long s_lane = s_warp + (long long)lane * kRandLaneSamples;
+    const bool whole = s_warp + kRandWarpSamples <= count;         // every sample of this warp is wanted
+    double* const row0 = out + s_warp + lane;                       // row r of a block: + r * kRandLaneSamples + blk * 31
 #pragma unroll 1
     for (int blk = 0; blk < kRandLaneValues / 62; ++blk) {
         double r1 = 0.0;
@@ -892,8 +894,9 @@ glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ l
             const uint32_t v = ring[slot] + ring[(slot + 28) % kRandDeg];   // r[i-31] + r[i-3]
             ring[slot] = v;
             // draw / RAND_MAX, correctly rounded: q0 = a*rcp, q0 + (a - q0*d)*rcp (checked against
-            // a/d for all 2^31 possible draws)
-            const double a = (double)(int)(v >> 1);
+            // a/d for all 2^31 possible draws).  The draw becomes a double exactly as 2^52 + draw - 2^52
+            // (one add on the fp64 pipe instead of a conversion instruction).
+            const double a = __dsub_rn(__hiloint2double(0x43300000, (int)(v >> 1)), 4503599627370496.0);
             const double q0 = __dmul_rn(a, rcp);
             const double q = __fma_rn(__fma_rn(-q0, rmax, a), rcp, q0);
             if (k & 1) stage_s[wl][lane][k >> 1] = __dsub_rn(r1, q);
@@ -901,14 +904,21 @@ glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ l
         }
         __syncwarp();
         // row r of the stage = 31 consecutive samples of lane r
+        double* const dst = row0 + blk * 31;
+        if (whole) {
+            if (lane < 31) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) dst[r * kRandLaneSamples] = stage_s[wl][r][lane];
+            }
+        } else {
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            const long long s = s_warp + (long long)r * kRandLaneSamples + blk * 31 + lane;
-            if (lane < 31 && s < count) out[s] = stage_s[wl][r][lane];
+            for (int r = 0; r < 32; ++r) {
+                const long long s = s_warp + (long long)r * kRandLaneSamples + blk * 31 + lane;
+                if (lane < 31 && s < count) out[s] = stage_s[wl][r][lane];
+            }
         }
         __syncwarp();
     }
-    (void)s_lane;
 }
 
 }  // namespace
@@ -947,8 +957,8 @@ struct dsdgpu_ctx {
     double lut_unit = 1.0;                   // 32-bit tables: 2^-qbits
     std::vector<uint32_t> rand_pow16;        // host: x^(d * 16^k), d < 16, k < 12, [k][d][31]
     std::vector<uint32_t> rand_base;         // host: seed words r[3..94]
-    uint32_t* d_rand_lane = nullptr;         // x^(248*l), l < 32, stored [k][l]
-    uint32_t* d_rand_jump = nullptr;         // x^(7936 * 128^level * u), [level][u][k]
+    uint32_t* d_rand_lane = nullptr;         // x^(kRandLaneValues*l), l < 32, stored [k][l]
+    uint32_t* d_rand_jump = nullptr;         // x^(kRandWarpValues * 128^level * u), [level][u][k]
     cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
     dsdgpu_slot slots[DSDGPU_SLOTS];
     int pipeline_slots = DSDGPU_SLOTS;       // slots dsdgpu_decimate_host cycles through
