@@ -976,7 +976,7 @@ namespace {
 using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x2 = RingGeom<16, 2>;
-using Ring16x2Q = RingGeom<16, 2, true>;
+using Ring16x2Q = RingGeom<16, 1, true>;   // 32-bit tables: two images (197 KB) leave room for one round per tile
 using Ring30 = RingGeom<16, 2, false, 30, 2>;   // divide-by-16 filter: 30 tables, 2 bytes per frame
 using Ring12 = RingGeom<16, 2, false, 12, 1>;   // divide-by-8 filter: 12 tables, 1 byte per frame
 using Ring64 = RingGeom<16, 1, false, 72, 8>;   // one pass (72 of 144 tables) of the divide-by-64 extension filter

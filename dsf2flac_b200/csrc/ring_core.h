@@ -54,7 +54,8 @@ namespace dsdgpu {
 //              LDS.32 = one 128-byte wavefront), rows are 96 slots = 384 B with THREE extra
 //              copies of taps 64..71: a wrapped lane whose lower neighbour in its residue class
 //              (j - 8) has already restarted reads slot tap + 8*(j >> 3), which puts it on the
-//              bank nobody else can be on.
+//              bank nobody else can be on.  Two images of the (half-size) tables, the second shifted by 16
+//              slots: 16 distinct skews instead of 32 (see "short filters" below), so 16 early steps of 72.
 //
 // Other filters (NLUT = 30 tables, 2 bytes per frame; NLUT = 12, 1 byte per frame): the period is
 // NLUT rounded up to a multiple of 16 steps, the extra slots hold -0.0 (the identity of fp64
@@ -80,7 +81,7 @@ struct RingGeom {
     static constexpr int NLUT = NLUT_;                // tables
     static constexpr int NSTEP = NSTEP_;              // bytes between successive frames
     static constexpr bool DUP = (NLUT == 72);         // 72-step periods with tail copies (see above)
-    static constexpr int COPIES = (!Q32 && NLUT == 12) ? 4 : (!Q32 && NLUT == 30) ? 2 : 1;   // images of the tables
+    static constexpr int COPIES = NLUT == 12 ? 4 : (NLUT == 30 || Q32) ? 2 : 1;   // images of the tables (whatever fits shared memory)
     static constexpr int PERIOD = DUP ? 72 : COPIES == 4 ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
     static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
     static constexpr int KF = 4;                      // consecutive frames per lane
@@ -221,13 +222,18 @@ struct RingNoEmit {
 // neighbouring group vacates.
 template <class G>
 RING_HD int ring_lane_skew(int l) {
+    const int h = (l >> 4) & 1, i = l & 15;
+    if (G::Q32 && G::COPIES > 1) {
+        // 16 skews, each used by one lane of either image (ring_lane_image); the window word of lane (h, i) is
+        // 4*i + (j >> 2): the four lanes that share 4*i mod 32 -- (h, i), (h, i ^ 8) for h = 0, 1 -- get the four values of j >> 2
+        return 4 * (2 * h + (i >> 3)) + (i & 3);
+    }
     if (G::Q32) {
         const int g = l & 7, r = (l >> 3) & 3;
         const int q = ((g & 1) ? 2 : 0) + (r & 1) + ((r >> 1) ? 4 : 0);
         return (g >> 1) + 4 * q;
     }
-    const int h = (l >> 4) & 1, i = l & 15;
-    if (G::COPIES > 1) return i / G::COPIES;            // image i % COPIES (ring_lane_init); see the top of this file
+    if (G::COPIES > 1) return i / G::COPIES;            // image i % COPIES (ring_lane_image); see the top of this file
     if (G::LANE_BYTES == 32) return i;                  // lane stride of eight words (see the top of this file)
     if (G::LANE_BYTES == 8) {
         // lane stride of two words: window word of lane i = 2*i + (j >> 2); found by search
@@ -238,6 +244,14 @@ RING_HD int ring_lane_skew(int l) {
     // lane stride of four words (and, with two-way conflicts on the window loads, of one word)
     const int q = 2 * (((i >> 2) & 1) ^ h) + ((i >> 3) & 1);
     return (i & 3) + 4 * q;
+}
+
+// Which image of the tables lane l reads (COPIES > 1).
+template <class G>
+RING_HD int ring_lane_image(int l) {
+    const int i = l & 15;
+    if (G::COPIES == 1) return 0;
+    return G::Q32 ? (i >> 2) & 1 : i % G::COPIES;
 }
 
 template <bool Q32> struct RingAcc { typedef double type; };
@@ -277,7 +291,7 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     r.unit = unit;
     r.one = unit > 0.0 ? 1 : 0;
     r.shift = 8u * (uint32_t)phi;
-    const int image = G::COPIES > 1 ? (l & 15) % G::COPIES : 0;
+    const int image = ring_lane_image<G>(l);
     const int base = G::GUARD_BYTES + image * (G::COPY_STRIDE + G::ELEM * G::NSKEW);
     r.lnew = (uint32_t)(base - G::ELEM * j);
     r.lwrap = (uint32_t)(base + G::ELEM * (G::PERIOD - j));
