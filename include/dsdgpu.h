@@ -104,8 +104,10 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
  * "threads"
  * (skew kernel CTA size, 512 or 1024), "dither_stride" (output samples per frame of the WHOLE
  * stream when this context only holds a channel subset of it: sample m of frame i, local channel
- * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default). Unknown keys are an
- * error. */
+ * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default), "trace" (1: every
+ * dsdgpu_decimate_host call prints the timeline of its chunks -- upload, kernel, download, from events
+ * on the slot streams -- to stderr; for looking at the PCIe pipeline, off by default). Unknown keys are
+ * an error. */
 int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
