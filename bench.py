@@ -71,8 +71,14 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+DATA_KIND = "sdm"            # --data: "sdm" (sigma-delta sines, the default) or "random" (uniform bytes, seed 1234)
+
+
 def synth_stream(dsd_fs, nch, seconds, lsb_first=1):
-    """One second of 2nd-order sigma-delta sine per channel (host/dsd_synth.cpp), tiled."""
+    """One second of 2nd-order sigma-delta sine per channel (host/dsd_synth.cpp), tiled; or uniform random
+    bytes (shared-memory behaviour depends on the byte statistics, so both are reported)."""
+    if DATA_KIND == "random":
+        return np.random.default_rng(1234).integers(0, 256, size=(nch, dsd_fs // 8 * seconds), dtype=np.uint8)
     from dsf2flac_b200 import capi
     host = capi.host_lib()
     sec = dsd_fs // 8
@@ -416,7 +422,7 @@ def run_gpu_arm(args, wl):
         print(json.dumps({
             "metric": "dsd_mbit_per_s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic" if DATA_KIND == "sdm" else "synthetic (uniform random bytes)",
             "per_gpu_mbit_per_s": value / world, "x_realtime": value * 1e6 / (dsd_fs * nch) / 1.0,
             "config": {"workload": desc, "dither": bool(args.dither), "lut": f"fp{args.lut}",
                        "kernel": args.kernel or "auto", "frames_per_step": nframes, "channels": nch,
@@ -654,10 +660,13 @@ def main():
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per pipelined host chunk")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall seconds of CPU work in the cpu_baseline sample (0: skip)")
     ap.add_argument("--plugin-seconds", type=float, default=2.0)
+    ap.add_argument("--data", default="sdm", choices=["sdm", "random"], help="synthetic input: sigma-delta sines or uniform random bytes")
     ap.add_argument("--seconds", type=int, default=0, help="stream length of the unsharded workloads (default: 60)")
     ap.add_argument("--dop-seconds", type=int, default=600, help="stream length of the dop workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global DATA_KIND
+    DATA_KIND = args.data
     if args.workload == "dop":
         return run_dop_arm(args)
     if args.workload in ("c3", "c4", "c4x", "c5"):
