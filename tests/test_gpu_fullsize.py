@@ -170,3 +170,36 @@ def test_config4_as_stated_divide_by_64_extension(oracle):
                 assert torch.equal(d_chk, d_out[n - cnt:]), kernel
     finally:
         oracle.set_custom_filter(None)
+
+
+@pytest.mark.parametrize("out_fs", [176400, 88200])
+def test_divide_by_128_and_256_extension_full_size(oracle, out_fs):
+    """DSD512 stereo, 60 s -> 176.4 / 88.2 kHz (ratios 128 and 256: 4 and 8 passes of the segmented kernel over
+    the plane of running sums): the segmented and the direct kernel (96-table passes, a different cut of the
+    same sequential sum) agree over the whole stream, and windows at the start, in the middle and at the end
+    equal the reference's arithmetic on the extension filter."""
+    fs = 8 * DSD64
+    nbytes = fs * 60 // 8
+    data = sdm_stream(2, nbytes, fs)
+    fir = filters.pick(fs, out_fs, extensions=True)
+    n = filters.app_frames(nbytes * 8, fir)
+    scale, amp, clip = filters.app_params(24, dither=False)
+    lut = filters.build_lut(fir, 1)
+    outs = {}
+    for name, k in (("seg", capi.KERNEL_SEGMENTED), ("direct", capi.KERNEL_DIRECT)):
+        with capi.DsdGpu(lut, 2, fir.nstep) as g:
+            g.set_option("kernel", k)
+            outs[name] = g.decimate_host(data, fir.nlut, n, scale, amp, clip)
+    assert np.array_equal(outs["seg"], outs["direct"])
+    oracle.set_custom_filter(fir)
+    try:
+        for f0 in (0, n // 2, n - 20000):
+            b0 = max(0, fir.nlut + f0 * fir.nstep - 2 * fir.nlut)
+            b1 = min(nbytes, fir.nlut + (f0 + 20000) * fir.nstep + 8)
+            sub = np.ascontiguousarray(data[:, b0:b1])
+            pre = fir.nlut + f0 * fir.nstep - b0 + 1
+            cnt = min(20000, n - f0)
+            want = oracle.run_raw(sub, 1 << 40, 1, fs, out_fs, pre, cnt, scale, amp, clip)
+            assert np.array_equal(outs["seg"][f0:f0 + cnt], want), f0
+    finally:
+        oracle.set_custom_filter(None)
