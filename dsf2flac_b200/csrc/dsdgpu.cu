@@ -306,7 +306,7 @@ __device__ __forceinline__ void seg_stage_tile(const DecimateArgs& a, long long 
     }
 }
 
-template <int KS>
+template <int KS, class L>
 __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(DecimateArgs a, int nstep, int row_stride) {
     extern __shared__ __align__(128) unsigned char smem[];
     // [0, LUT_BYTES): table image of this segment; then two byte tiles of nch * row_stride bytes.
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
     const int tid = threadIdx.x;
     {
         const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
-        for (int k = tid; k < SegLayout::LUT_BYTES / 16; k += NTHR) cp_async16(smem + 16 * k, img + 16 * k);
+        for (int k = tid; k < L::LUT_BYTES / 16; k += NTHR) cp_async16(smem + 16 * k, img + 16 * k);
     }
     const long long total = a.nframes * a.nch;
     const long long ntiles = (total + NT - 1) / NT;
@@ -322,24 +322,24 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
     const int nsteps = (a.seg_n + 15 + 3) / 4 * 4, ngroups = nsteps / 4;
     const int tile_bytes = a.nch * row_stride;
     const int j = tid & 15;
-    const uint32_t lut0 = (uint32_t)(SegLayout::GUARD_BYTES - 8 * j);
+    const uint32_t lut0 = (uint32_t)(L::GUARD_BYTES - 8 * j);
 
     long long tile = blockIdx.x;
     int buf = 0;
     SegTile tl = seg_tile_at<KS>(a, tile, nstep, nsteps);
-    if (tile < ntiles) seg_stage_tile(a, tl.t0, row_stride, smem + SegLayout::LUT_BYTES, aligned16);
+    if (tile < ntiles) seg_stage_tile(a, tl.t0, row_stride, smem + L::LUT_BYTES, aligned16);
     cp_async_commit();
     while (tile < ntiles) {
         const long long next = tile + gridDim.x;
         if (next < ntiles) {
             const SegTile tn = seg_tile_at<KS>(a, next, nstep, nsteps);
-            seg_stage_tile(a, tn.t0, row_stride, smem + SegLayout::LUT_BYTES + (buf ^ 1) * tile_bytes, aligned16);
+            seg_stage_tile(a, tn.t0, row_stride, smem + L::LUT_BYTES + (buf ^ 1) * tile_bytes, aligned16);
         }
         cp_async_commit();
         cp_async_wait<1>();          // everything but the group just committed has landed
         __syncthreads();
 
-        const uint32_t tile_off = (uint32_t)(SegLayout::LUT_BYTES + buf * tile_bytes);
+        const uint32_t tile_off = (uint32_t)(L::LUT_BYTES + buf * tile_bytes);
         double acc[KS];
         uint32_t wlo[KS], lo[KS], shift[KS];
         int fl[KS], ch[KS];          // frame (relative to the tile's first) and channel of each sample; fl < 0: past the end
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
                     else if (u == 1) e = byte_of<2>(x[k]);
                     else if (u == 2) e = byte_of<1>(x[k]);
                     else e = byte_of<0>(x[k]);
-                    acc[k] = __dadd_rn(acc[k], lds_f64(smem, e * (uint32_t)SegLayout::ROW_BYTES + lut + 8u * (uint32_t)u));
+                    acc[k] = __dadd_rn(acc[k], lds_f64(smem, e * (uint32_t)L::ROW_BYTES + lut + 8u * (uint32_t)u));
                 }
             }
             lut += 32u;
@@ -952,8 +952,9 @@ struct dsdgpu_ctx {
     double* d_lut_direct = nullptr;          // [nlut][256]
     unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
     unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only): fp64 or 32-bit entries
-    unsigned char* d_lut_seg = nullptr;      // nseg x SegLayout::LUT_BYTES images, SEG_DEFAULT tables each (any geometry)
+    unsigned char* d_lut_seg = nullptr;      // nseg x LUT_BYTES images, SEG_DEFAULT tables each (any geometry)
     int nseg = 0;
+    bool seg_narrow = false;                 // SegLayoutNarrow (80-slot rows, 64 tables per pass): frame hops of 16 bytes and more
     double lut_unit = 1.0;                   // 32-bit tables: 2^-qbits
     std::vector<uint32_t> rand_pow16;        // host: x^(d * 16^k), d < 16, k < 12, [k][d][31]
     std::vector<uint32_t> rand_base;         // host: seed words r[3..94]
@@ -1164,49 +1165,58 @@ int launch_direct(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStr
 
 // Segmented kernel: one launch per SEG_DEFAULT tables, running sums in between.  KS (samples per
 // thread) is the largest of 4, 2, 1 whose two byte tiles fit beside the table image.
-template <int KS>
+template <int KS, class L>
 int launch_seg_pass(dsdgpu_ctx* ctx, const DecimateArgs& a, int row_stride, int smem, cudaStream_t st) {
     static thread_local int configured_device = -1;
     if (configured_device != ctx->device) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_seg_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SegLayout::SMEM_LIMIT));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_seg_kernel<KS, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_LIMIT));
         configured_device = ctx->device;
     }
-    const long long total = a.nframes * a.nch, nt = SegLayout::NTHR * KS;
+    const long long total = a.nframes * a.nch, nt = L::NTHR * KS;
     const long long tiles = (total + nt - 1) / nt;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    decimate_seg_kernel<KS><<<grid, SegLayout::NTHR, smem, st>>>(a, ctx->nstep, row_stride);
+    decimate_seg_kernel<KS, L><<<grid, L::NTHR, smem, st>>>(a, ctx->nstep, row_stride);
     ctx->launches += 1;
     return DSDGPU_OK;
 }
 
 // samples per thread of the segmented kernel: the largest of 4, 2, 1 that fits shared memory, 0 = none does
-int seg_samples_per_thread(const dsdgpu_ctx* ctx) {
+template <class L>
+int seg_samples_per_thread_of(const dsdgpu_ctx* ctx) {
     int ks = 4;
-    while (ks >= 1 && SegLayout::smem_bytes(SegLayout::NTHR * ks, ctx->nch, ctx->nstep) > SegLayout::SMEM_LIMIT) ks >>= 1;
+    while (ks >= 1 && L::smem_bytes(L::NTHR * ks, ctx->nch, ctx->nstep) > L::SMEM_LIMIT) ks >>= 1;
     return ctx->d_lut_seg ? ks : 0;
 }
+int seg_samples_per_thread(const dsdgpu_ctx* ctx) {
+    return ctx->seg_narrow ? seg_samples_per_thread_of<SegLayoutNarrow>(ctx) : seg_samples_per_thread_of<SegLayout>(ctx);
+}
 
-int launch_seg(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+template <class L>
+int launch_seg_as(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
     if (!ctx->d_lut_seg) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: no table images");
-    const int ks = seg_samples_per_thread(ctx);
+    const int ks = seg_samples_per_thread_of<L>(ctx);
     if (ks < 1) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: %d channels x %d bytes per frame do not fit shared memory", ctx->nch, ctx->nstep);
-    const int samples = SegLayout::NTHR * ks;
-    const int row_stride = (int)SegLayout::row_stride(samples, ctx->nch, ctx->nstep);
-    const int smem = (int)SegLayout::smem_bytes(samples, ctx->nch, ctx->nstep);
+    const int samples = L::NTHR * ks;
+    const int row_stride = (int)L::row_stride(samples, ctx->nch, ctx->nstep);
+    const int smem = (int)L::smem_bytes(samples, ctx->nch, ctx->nstep);
     if (ctx->nseg > 1) { int rc = ensure_partial(ctx, scratch, a); if (rc) return rc; }
     for (int s = 0; s < ctx->nseg; ++s) {
-        a.seg_first = s * SegLayout::SEG_DEFAULT;
-        a.seg_n = ctx->nlut - a.seg_first < SegLayout::SEG_DEFAULT ? ctx->nlut - a.seg_first : SegLayout::SEG_DEFAULT;
+        a.seg_first = s * L::SEG_DEFAULT;
+        a.seg_n = ctx->nlut - a.seg_first < L::SEG_DEFAULT ? ctx->nlut - a.seg_first : L::SEG_DEFAULT;
         a.seg_init = s > 0 ? scratch.d_partial : nullptr;
         a.seg_raw = s + 1 < ctx->nseg ? scratch.d_partial : nullptr;
-        a.lut = ctx->d_lut_seg + (size_t)s * SegLayout::LUT_BYTES;
-        int rc = ks == 4 ? launch_seg_pass<4>(ctx, a, row_stride, smem, st)
-               : ks == 2 ? launch_seg_pass<2>(ctx, a, row_stride, smem, st)
-                         : launch_seg_pass<1>(ctx, a, row_stride, smem, st);
+        a.lut = ctx->d_lut_seg + (size_t)s * L::LUT_BYTES;
+        int rc = ks == 4 ? launch_seg_pass<4, L>(ctx, a, row_stride, smem, st)
+               : ks == 2 ? launch_seg_pass<2, L>(ctx, a, row_stride, smem, st)
+                         : launch_seg_pass<1, L>(ctx, a, row_stride, smem, st);
         if (rc) return rc;
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
+}
+
+int launch_seg(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const DecimateArgs& a, cudaStream_t st) {
+    return ctx->seg_narrow ? launch_seg_as<SegLayoutNarrow>(ctx, scratch, a, st) : launch_seg_as<SegLayout>(ctx, scratch, a, st);
 }
 
 int check_call(dsdgpu_ctx* ctx, const void* in, int64_t in_count, int64_t nframes, int out_kind, const void* out) {
@@ -1390,12 +1400,15 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     {
         // segmented kernel: one image per SEG_DEFAULT tables (fp64 entries; the 32-bit variant's rounded
         // tables sum exactly in fp64 too, so it returns the integer kernel's bits)
-        ctx->nseg = (nlut + SegLayout::SEG_DEFAULT - 1) / SegLayout::SEG_DEFAULT;
-        std::vector<unsigned char> simg((size_t)ctx->nseg * SegLayout::LUT_BYTES);
+        ctx->seg_narrow = nstep >= 16;
+        const int seg = ctx->seg_narrow ? SegLayoutNarrow::SEG_DEFAULT : SegLayout::SEG_DEFAULT;
+        const size_t img_bytes = ctx->seg_narrow ? SegLayoutNarrow::LUT_BYTES : SegLayout::LUT_BYTES;
+        ctx->nseg = (nlut + seg - 1) / seg;
+        std::vector<unsigned char> simg((size_t)ctx->nseg * img_bytes);
         for (int sidx = 0; sidx < ctx->nseg; ++sidx) {
-            const int first = sidx * SegLayout::SEG_DEFAULT;
-            seg_build_lut_image(tab.data(), first, nlut - first < SegLayout::SEG_DEFAULT ? nlut - first : SegLayout::SEG_DEFAULT,
-                                simg.data() + (size_t)sidx * SegLayout::LUT_BYTES);
+            const int first = sidx * seg, count = nlut - first < seg ? nlut - first : seg;
+            if (ctx->seg_narrow) seg_build_lut_image<SegLayoutNarrow>(tab.data(), first, count, simg.data() + (size_t)sidx * img_bytes);
+            else seg_build_lut_image<SegLayout>(tab.data(), first, count, simg.data() + (size_t)sidx * img_bytes);
         }
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_seg), simg.size()));
         CREATE_TRY(cudaMemcpy(ctx->d_lut_seg, simg.data(), simg.size(), cudaMemcpyHostToDevice));

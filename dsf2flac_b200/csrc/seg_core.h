@@ -24,14 +24,20 @@
 
 namespace dsdgpu {
 
-struct SegLayout {
+// ROW = 96 slots per table row: up to 81 tables per pass, 72 by default (144 = 2 x 72).  ROW = 80: up to 65,
+// 64 by default -- a 33 KB smaller image, which buys twice the samples per tile where frames are 16 or 32
+// bytes apart (decimation by 128 and 256: 5 and 9 passes instead of 4 and 8, each with twice the work per
+// barrier and per thread).
+template <int ROW_>
+struct SegLayoutT {
     static constexpr int NTHR = 512;
-    static constexpr int ROW = 96;                       // slots per table row
+    static constexpr int ROW = ROW_;                     // slots per table row
     static constexpr int ROW_BYTES = ROW * 8;
     static constexpr int GUARD_BYTES = 128;              // pads of "row -1"
     static constexpr int LUT_BYTES = GUARD_BYTES + 256 * ROW_BYTES;
-    static constexpr int SEG_MAX = ROW - 15;             // 81 tables per pass at most
-    static constexpr int SEG_DEFAULT = 72;               // 144 = 2 x 72, 288 = 4 x 72, 576 = 8 x 72
+    static constexpr int SEG_MAX = ROW - 15;             // tables per pass at most
+    static constexpr int SEG_DEFAULT = ROW == 96 ? 72 : ROW - 16;
+    static_assert(ROW % 16 == 0, "bank pattern: a row is a whole number of 128-byte lines");
     static constexpr int SLACK = 160;                    // bytes per tile row beyond (frames - 1) * nstep
     static constexpr int SMEM_LIMIT = 232448;            // 227 KB opt-in maximum per CTA (sm_100)
 
@@ -45,15 +51,18 @@ struct SegLayout {
         return LUT_BYTES + 2 * nch * row_stride(samples, nch, nstep);
     }
 };
+typedef SegLayoutT<96> SegLayout;
+typedef SegLayoutT<80> SegLayoutNarrow;
 
 // Host side of the layout: the shared-memory image of tables [seg_first, seg_first + seg_n).
 //   lut   [nlut][256] doubles as the reference builds them (dsd_decimator.cpp:117-151)
+template <class L>
 inline void seg_build_lut_image(const double* lut, int seg_first, int seg_n, unsigned char* image) {
     double* d = reinterpret_cast<double*>(image);
-    for (int i = 0; i < SegLayout::LUT_BYTES / 8; ++i) d[i] = -0.0;
-    double* rows = reinterpret_cast<double*>(image + SegLayout::GUARD_BYTES);
+    for (int i = 0; i < L::LUT_BYTES / 8; ++i) d[i] = -0.0;
+    double* rows = reinterpret_cast<double*>(image + L::GUARD_BYTES);
     for (int e = 0; e < 256; ++e)
-        for (int t = 0; t < seg_n; ++t) rows[e * SegLayout::ROW + t] = lut[(size_t)(seg_first + t) * 256 + e];
+        for (int t = 0; t < seg_n; ++t) rows[e * L::ROW + t] = lut[(size_t)(seg_first + t) * 256 + e];
 }
 
 }  // namespace dsdgpu

@@ -313,8 +313,8 @@ def test_gpu_extension_shards_stitch(ext_oracle, oracle):
 @pytest.mark.gpu
 def test_gpu_odd_geometries_and_limits():
     """Geometries nobody ships: the any-geometry kernels take them (or decline with a message), never crash.
-    100 tables x 3-byte frame hop, 5 channels; 40 channels at a 32-byte hop (does not fit the segmented
-    kernel's shared memory: AUTO falls back to the direct kernel, asking for the segmented one is an error)."""
+    100 tables x 3-byte frame hop, 5 channels; 40 channels at a 32-byte hop; 100 channels at a 32-byte hop (does not
+    fit the segmented kernel's shared memory: AUTO falls back to the direct kernel, asking for the segmented one is an error)."""
     rng = np.random.default_rng(5)
 
     def reference_sums(lut, data, nstep, p0, nframes, fill=0x69):
@@ -340,12 +340,19 @@ def test_gpu_odd_geometries_and_limits():
     lut = (rng.random((80, 256)) - 0.5) * 0.3
     data = seeded_bytes(40, 1200, 9)
     want = reference_sums(lut, data, 32, 100, 30)
-    with capi.DsdGpu(lut, 40, 32) as g:
-        got = g.decimate_host(data, 100, 30, 1.0, out_kind=capi.OUT_FLOAT64)
+    for kernel in (capi.KERNEL_AUTO, capi.KERNEL_SEGMENTED, capi.KERNEL_DIRECT):        # 40 channels at a 32-byte hop
+        with capi.DsdGpu(lut, 40, 32) as g:
+            g.set_option("kernel", kernel)
+            got = g.decimate_host(data, 100, 30, 1.0, out_kind=capi.OUT_FLOAT64)
+            assert got.tobytes() == want.tobytes(), kernel
+    data = seeded_bytes(100, 900, 10)
+    want = reference_sums(lut, data, 32, 100, 20)
+    with capi.DsdGpu(lut, 100, 32) as g:                                                # 100 channels: no room for the tiles
+        got = g.decimate_host(data, 100, 20, 1.0, out_kind=capi.OUT_FLOAT64)
         assert got.tobytes() == want.tobytes()
         g.set_option("kernel", capi.KERNEL_SEGMENTED)
         with pytest.raises(capi.DsdGpuError, match="shared memory"):
-            g.decimate_host(data, 100, 30, 1.0, out_kind=capi.OUT_FLOAT64)
+            g.decimate_host(data, 100, 20, 1.0, out_kind=capi.OUT_FLOAT64)
     for nlut, nstep in ((641, 8), (72, 65), (0, 4)):
         with pytest.raises(capi.DsdGpuError):
             capi.DsdGpu(np.zeros((max(nlut, 1), 256)) if nlut else np.zeros((1, 256))[:0].reshape(0, 256), 2, nstep)

@@ -9,15 +9,19 @@ import itertools
 
 import pytest
 
-NTHR, ROW, GUARD, SLACK, LIMIT = 512, 96, 128, 160, 232448
-LUT_BYTES = GUARD + 256 * ROW * 8
+NTHR, GUARD, SLACK, LIMIT = 512, 128, 160, 232448
+
+
+def row_slots(nstep):
+    """SegLayout (96 slots per table row) up to 8 bytes per frame, SegLayoutNarrow (80) from 16 on (dsdgpu_create)."""
+    return 80 if nstep >= 16 else 96
 
 
 def layout(ks, nch, nstep):
     samples = NTHR * ks
     frames = (samples + nch - 1) // nch + 1
     stride = ((frames - 1) * nstep + SLACK + 15) // 16 * 16
-    return samples, stride, LUT_BYTES + 2 * nch * stride
+    return samples, stride, GUARD + 256 * row_slots(nstep) * 8 + 2 * nch * stride
 
 
 def floor16_rel(x):
@@ -28,8 +32,12 @@ def floor16_rel(x):
 def test_window_words_stay_inside_the_row(nch, nstep):
     ks = next(k for k in (4, 2, 1) if layout(k, nch, nstep)[2] <= LIMIT)
     samples, stride, smem = layout(ks, nch, nstep)
+    ROW = row_slots(nstep)
+    LUT_BYTES = GUARD + 256 * ROW * 8
     assert smem <= LIMIT and stride % 16 == 0
-    for seg_n, seg_first, p0, in_first, total in itertools.product((1, 12, 72, 81), (0, 72), (-1, 0, 143, 1000003), (0, 5, -7),
+    if nstep == 32 and nch <= 2:
+        assert ks >= 2                                            # what the narrow rows are for
+    for seg_n, seg_first, p0, in_first, total in itertools.product((1, 12, ROW - 32, ROW - 24, ROW - 15), (0, 72), (-1, 0, 143, 1000003), (0, 5, -7),
                                                                    (1, samples - 1, samples * 3 + 17)):
         nsteps = (seg_n + 15 + 3) // 4 * 4
         ngroups = nsteps // 4
@@ -67,7 +75,8 @@ def test_window_words_stay_inside_the_row(nch, nstep):
         assert len({(s - j) % 16 for j in range(16)}) == 16
 
 
-def test_pad_slots_cover_every_idle_step():
+@pytest.mark.parametrize("ROW", [96, 80])
+def test_pad_slots_cover_every_idle_step(ROW):
     """A lane runs nsteps = roundup4(seg_n + 15) steps; outside its seg_n real taps it must read -0.0: slots
     seg_n .. nsteps - 1 of its own row and slots ROW - 15 .. ROW - 1 of the row before it (or the guard)."""
     for seg_n in range(1, ROW - 15 + 1):
