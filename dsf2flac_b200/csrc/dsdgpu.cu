@@ -282,10 +282,14 @@ struct SegTile {
     long long i0;            // first output sample
 };
 
+// The CTA works as two groups of 256 threads, each with its own tiles and tile buffers and its own named
+// barrier: while one group stages, sets up or stores, the other keeps the shared-memory pipe busy.
+constexpr int kSegGroupThreads = SegLayout::NTHR / 2;
+
 template <int KS>
 __device__ __forceinline__ SegTile seg_tile_at(const DecimateArgs& a, long long tile, int nstep, int nsteps) {
     SegTile t;
-    t.i0 = tile * (long long)(SegLayout::NTHR * KS);
+    t.i0 = tile * (long long)(kSegGroupThreads * KS);
     const long long f_lo = t.i0 / a.nch;
     const long long pmin = a.p0 + f_lo * nstep - a.seg_first;        // newest byte of the tile's first frame, this segment's tap 0
     long long rel = pmin - nsteps - 16 - a.in_first;                  // lane 0 reads down to pmin - (nsteps - 1)
@@ -295,10 +299,10 @@ __device__ __forceinline__ SegTile seg_tile_at(const DecimateArgs& a, long long 
 }
 
 __device__ __forceinline__ void seg_stage_tile(const DecimateArgs& a, long long t0, int row_stride, unsigned char* dst,
-                                               bool aligned16) {
+                                               bool aligned16, int gt) {
     const int chunks_per_row = row_stride / 16;
     const long long o0 = t0 - a.in_first;
-    for (int k = threadIdx.x; k < a.nch * chunks_per_row; k += SegLayout::NTHR) {
+    for (int k = gt; k < a.nch * chunks_per_row; k += kSegGroupThreads) {
         const int c = k / chunks_per_row, kk = k - c * chunks_per_row;
         const long long o = o0 + 16LL * kk;
         unsigned char* d = dst + c * row_stride + 16 * kk;
@@ -306,12 +310,16 @@ __device__ __forceinline__ void seg_stage_tile(const DecimateArgs& a, long long 
     }
 }
 
+__device__ __forceinline__ void seg_group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + group), "n"(kSegGroupThreads) : "memory");
+}
+
 template <int KS, class L>
 __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(DecimateArgs a, int nstep, int row_stride) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // [0, LUT_BYTES): table image of this segment; then two byte tiles of nch * row_stride bytes.
-    constexpr int NTHR = SegLayout::NTHR, NT = NTHR * KS;
-    const int tid = threadIdx.x;
+    // [0, LUT_BYTES): table image of this segment; then, per group, two byte tiles of nch * row_stride bytes.
+    constexpr int NTHR = SegLayout::NTHR, GT = kSegGroupThreads, NT = GT * KS;
+    const int tid = threadIdx.x, group = tid / GT, gt = tid - group * GT;
     {
         const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
         for (int k = tid; k < L::LUT_BYTES / 16; k += NTHR) cp_async16(smem + 16 * k, img + 16 * k);
@@ -321,25 +329,29 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
     const bool aligned16 = src_aligned16(a);
     const int nsteps = (a.seg_n + 15 + 3) / 4 * 4, ngroups = nsteps / 4;
     const int tile_bytes = a.nch * row_stride;
+    unsigned char* const bufs = smem + L::LUT_BYTES + group * 2 * tile_bytes;
     const int j = tid & 15;
     const uint32_t lut0 = (uint32_t)(L::GUARD_BYTES - 8 * j);
 
-    long long tile = blockIdx.x;
+    const long long tstride = 2LL * gridDim.x;
+    long long tile = 2LL * blockIdx.x + group;
     int buf = 0;
     SegTile tl = seg_tile_at<KS>(a, tile, nstep, nsteps);
-    if (tile < ntiles) seg_stage_tile(a, tl.t0, row_stride, smem + L::LUT_BYTES, aligned16);
+    if (tile < ntiles) seg_stage_tile(a, tl.t0, row_stride, bufs, aligned16, gt);
     cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();                 // the table image (loaded by all 512 threads) is in place for both groups
     while (tile < ntiles) {
-        const long long next = tile + gridDim.x;
+        const long long next = tile + tstride;
         if (next < ntiles) {
             const SegTile tn = seg_tile_at<KS>(a, next, nstep, nsteps);
-            seg_stage_tile(a, tn.t0, row_stride, smem + L::LUT_BYTES + (buf ^ 1) * tile_bytes, aligned16);
+            seg_stage_tile(a, tn.t0, row_stride, bufs + (buf ^ 1) * tile_bytes, aligned16, gt);
         }
         cp_async_commit();
         cp_async_wait<1>();          // everything but the group just committed has landed
-        __syncthreads();
+        seg_group_barrier(group);
 
-        const uint32_t tile_off = (uint32_t)(L::LUT_BYTES + buf * tile_bytes);
+        const uint32_t tile_off = (uint32_t)(L::LUT_BYTES + (group * 2 + buf) * tile_bytes);
         double acc[KS];
         uint32_t wlo[KS], lo[KS], shift[KS];
         int fl[KS], ch[KS];          // frame (relative to the tile's first) and channel of each sample; fl < 0: past the end
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
         const int pbase = (int)(a.p0 + f_lo * nstep - a.seg_first - tl.t0) + j;    // byte of step 0 of frame f_lo
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
-            unsigned n = (unsigned)(tid + k * NTHR);
+            unsigned n = (unsigned)(gt + k * GT);
             const bool live = (long long)n < left;
             if (!live) n = (unsigned)(left - 1);                               // lanes past the end recompute the last sample
             const unsigned q = (r0 + n) / (unsigned)a.nch;
@@ -391,11 +403,11 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
             if (fl[k] >= 0) {
-                if (a.seg_raw) a.seg_raw[tl.i0 + tid + k * NTHR] = acc[k];
+                if (a.seg_raw) a.seg_raw[tl.i0 + gt + k * GT] = acc[k];
                 else store_sample(a, f_lo + fl[k], ch[k], acc[k]);
             }
         }
-        __syncthreads();             // tile `buf` is free again
+        seg_group_barrier(group);    // tile `buf` of this group is free again
         tile = next;
         buf ^= 1;
         if (tile < ntiles) tl = seg_tile_at<KS>(a, tile, nstep, nsteps);
@@ -1172,9 +1184,9 @@ int launch_seg_pass(dsdgpu_ctx* ctx, const DecimateArgs& a, int row_stride, int 
         CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_seg_kernel<KS, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_LIMIT));
         configured_device = ctx->device;
     }
-    const long long total = a.nframes * a.nch, nt = L::NTHR * KS;
-    const long long tiles = (total + nt - 1) / nt;
-    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    const long long total = a.nframes * a.nch, nt = L::NTHR / 2 * KS;           // tile of one 256-thread group
+    const long long tiles = (total + nt - 1) / nt, pairs = (tiles + 1) / 2;
+    const int grid = (int)(pairs < ctx->sm_count ? pairs : ctx->sm_count);
     decimate_seg_kernel<KS, L><<<grid, L::NTHR, smem, st>>>(a, ctx->nstep, row_stride);
     ctx->launches += 1;
     return DSDGPU_OK;
@@ -1184,7 +1196,7 @@ int launch_seg_pass(dsdgpu_ctx* ctx, const DecimateArgs& a, int row_stride, int 
 template <class L>
 int seg_samples_per_thread_of(const dsdgpu_ctx* ctx) {
     int ks = 4;
-    while (ks >= 1 && L::smem_bytes(L::NTHR * ks, ctx->nch, ctx->nstep) > L::SMEM_LIMIT) ks >>= 1;
+    while (ks >= 1 && L::smem_bytes(L::NTHR / 2 * ks, ctx->nch, ctx->nstep) > L::SMEM_LIMIT) ks >>= 1;
     return ctx->d_lut_seg ? ks : 0;
 }
 int seg_samples_per_thread(const dsdgpu_ctx* ctx) {
@@ -1196,7 +1208,7 @@ int launch_seg_as(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStr
     if (!ctx->d_lut_seg) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: no table images");
     const int ks = seg_samples_per_thread_of<L>(ctx);
     if (ks < 1) return fail(ctx, DSDGPU_ERR_ARG, "segmented kernel: %d channels x %d bytes per frame do not fit shared memory", ctx->nch, ctx->nstep);
-    const int samples = L::NTHR * ks;
+    const int samples = L::NTHR / 2 * ks;                                     // per 256-thread group
     const int row_stride = (int)L::row_stride(samples, ctx->nch, ctx->nstep);
     const int smem = (int)L::smem_bytes(samples, ctx->nch, ctx->nstep);
     if (ctx->nseg > 1) { int rc = ensure_partial(ctx, scratch, a); if (rc) return rc; }

@@ -47,8 +47,9 @@ struct SegLayoutT {
     static long long row_stride(int samples, int nch, int nstep) {
         return ((tile_frames(samples, nch) - 1) * nstep + SLACK + 15) / 16 * 16;
     }
+    // two groups of NTHR / 2 threads, each with two tile buffers for tiles of `samples` output samples
     static long long smem_bytes(int samples, int nch, int nstep) {
-        return LUT_BYTES + 2 * nch * row_stride(samples, nch, nstep);
+        return LUT_BYTES + 4 * nch * row_stride(samples, nch, nstep);
     }
 };
 typedef SegLayoutT<96> SegLayout;
