@@ -1,6 +1,6 @@
 // ring_core.h -- per-lane logic of the "ring" decimation kernel (divide-by-32 filters, 72 tables).
 //
-// Shared between the CUDA kernel (dsdgpu.cu) and the host-side lane emulator
+// Shared between the CUDA kernel (dsd_kernels.cuh) and the host-side lane emulator
 // (tests/cpp/emu_ring.cpp): a lane never talks to another lane inside this function, so running
 // it once per thread id over a byte image of the CTA's shared memory reproduces the kernel, and
 // the recorded addresses give the exact wavefront count of every shared-memory instruction.

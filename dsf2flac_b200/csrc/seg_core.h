@@ -1,4 +1,4 @@
-// seg_core.h -- geometry of the "segmented" decimation kernel (dsdgpu.cu, decimate_seg_kernel): the
+// seg_core.h -- geometry of the "segmented" decimation kernel (dsd_kernels.cuh, decimate_seg_kernel): the
 // bank-conflict-free lane-skewed LUT gather for ANY filter geometry, one segment of at most SEG_MAX
 // tables per launch, so that filters whose tables do not fit one SM's shared memory (the /64, /128
 // and /256 extension filters: 144, 288, 576 tables) run as a chain of passes over a plane of running

@@ -1,6 +1,6 @@
 // skew_core.h -- per-lane logic of the bank-conflict-free ("skewed") decimation kernel.
 //
-// Shared between the CUDA kernel (dsdgpu.cu) and a host-side lane emulator
+// Shared between the CUDA kernel (dsd_kernels.cuh) and a host-side lane emulator
 // (tests/cpp/emu_skew.cpp) so the index arithmetic can be proven on the CPU box: a lane never
 // talks to another lane, so running this function once per thread id over a byte image of the
 // shared memory reproduces the kernel exactly.

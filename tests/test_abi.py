@@ -44,7 +44,7 @@ def test_no_oracle_in_product():
         assert "oracle" not in deps and "dsdref" not in deps
     for dirpath, _, files in os.walk(os.path.join(ROOT, "dsf2flac_b200")):
         for f in files:
-            if f.endswith((".py", ".cpp", ".cu", ".h")):
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".inc")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in text and "libdsdoracle" not in text and "libdsdref" not in text, f
 

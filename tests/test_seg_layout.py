@@ -1,4 +1,4 @@
-"""Bounds of the segmented kernel's shared-memory accesses (dsf2flac_b200/csrc/dsdgpu.cu: seg_tile_at,
+"""Bounds of the segmented kernel's shared-memory accesses (dsf2flac_b200/csrc/dsd_kernels.cuh: seg_tile_at,
 seg_stage_tile, decimate_seg_kernel; csrc/seg_core.h), restated in Python and swept over channel counts,
 frame hops, segment lengths, start positions and source origins.  compute-sanitizer is not available on the
 GPU pool, so what it would check is checked here by arithmetic: every window word a lane loads lies inside
