@@ -208,6 +208,73 @@ def run_reference_arm(args, wl):
     }), flush=True)
 
 
+def _cpu_file_worker(job):
+    """One whole file through the reference's decimator with main.cpp's loop (dither on): what one
+    dsf2flac process would do for it, minus container parsing and FLAC."""
+    dsd_fs, out_fs, nch, seconds, bits_depth, dither = job
+    from tests.oracle_lib import Oracle, REF_SO
+    from dsf2flac_b200 import filters
+    orc = Oracle(reference=os.path.exists(REF_SO))
+    fir = filters.pick(dsd_fs, out_fs, extensions=True)
+    if fir.ratio not in filters.FILTERS:
+        orc.set_custom_filter(fir)
+    one = _CPU_DATA[dsd_fs][:nch]
+    data = np.ascontiguousarray(np.tile(one, (1, seconds)))
+    scale, amp, clip = filters.app_params(bits_depth, dither=bool(dither))
+    t0 = time.perf_counter()
+    out = orc.run_app(data, data.shape[1] * 8, 1, dsd_fs, out_fs, scale, amp, clip)
+    return data.shape[1] * 8 * nch, time.perf_counter() - t0, len(out)
+
+
+def run_reference_arm_batch(args, spec):
+    """Reference arm of the sharded workloads: the job's files (time segments of one long stream count as
+    files of their own) converted by independent reference processes, one per host core -- the reference is
+    single threaded and its only batch notion is a serial shell loop (scripts/batch_dsf2flac.sh:16-19).  A step
+    is a bounded sample: the first files of the list, as many as keep the run within a few minutes."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    desc, files, lut_bits, dither = spec
+    cores = len(os.sched_getaffinity(0))
+    global _CPU_DATA
+    _CPU_DATA = {}
+    for fs in sorted({f[0] for f in files}):
+        _CPU_DATA[fs] = synth_stream(fs, max(f[2] for f in files if f[0] == fs), 1)
+    # a long stream is cut into 60 s pieces (what the GPU arm's time segments are, without the halo)
+    jobs = []
+    for fs, out_fs, nch, seconds in files:
+        for lo in range(0, seconds, 60):
+            jobs.append((fs, out_fs, nch, min(60, seconds - lo), 24, dither))
+    pool = mp.get_context("fork").Pool(cores)
+    probe = pool.map(_cpu_file_worker, jobs[:cores])
+    rate = sum(p[0] for p in probe) / max(p[1] for p in probe)          # bits/s with every core busy
+    budget_bits = rate * 100.0 / max(1, args.steps + args.warmup)
+    take, acc = 0, 0
+    while take < len(jobs) and (take < cores or acc < budget_bits):
+        acc += jobs[take][0] * jobs[take][2] * jobs[take][3]
+        take += 1
+    sample = jobs[:take]
+    for _ in range(args.warmup):
+        pool.map(_cpu_file_worker, sample, chunksize=1)
+    t0 = time.perf_counter()
+    bits = 0
+    for _ in range(args.steps):
+        bits += sum(r[0] for r in pool.map(_cpu_file_worker, sample, chunksize=1))
+    wall = time.perf_counter() - t0
+    pool.close()
+    v = bits / wall / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": "dsd_mbit_per_s", "value": v, "unit": "Mbit/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "files": len(files), "dither": bool(dither), "lut": "fp64 (the reference has no 32-bit variant)"},
+        "cpu_baseline": {"value": v, "unit": "Mbit/s", "cores": cores, "kind": "reference" if os.path.exists(
+            os.path.join(ROOT, "oracle", "_ref", "libdsdref.so")) else "port",
+                         "sample": f"the first {take} of {len(jobs)} files / 60 s pieces per step, one reference process per core"},
+        "e2e": {"value": v, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
 # ---- GPU arm ----------------------------------------------------------------------------------
 
 def run_gpu_arm(args, wl):
@@ -671,7 +738,7 @@ def main():
         return run_dop_arm(args)
     if args.workload in ("c3", "c4", "c4x", "c5"):
         if args.impl == "reference":
-            raise SystemExit("the reference arm runs the unsharded workloads (c1, c2)")
+            return run_reference_arm_batch(args, sharded_workloads(args.files)[args.workload])
         return run_sharded_arm(args, sharded_workloads(args.files)[args.workload])
     wl = WORKLOADS[args.workload]
     if args.seconds:
