@@ -325,20 +325,36 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
     SegTile tl = seg_tile_at<KS>(a, tile, nstep, nsteps);
     if (tile < ntiles) seg_stage_tile(a, tl.t0, row_stride, bufs, aligned16, gt);
     cp_async_commit();
+    // running sums this thread's samples start from (later passes): loaded one tile ahead of their use
+    double init_next[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const long long i = tl.i0 + gt + k * GT;
+        init_next[k] = (a.seg_init && tile < ntiles) ? a.seg_init[i < total ? i : total - 1] : 0.0;
+    }
     cp_async_wait<0>();
     __syncthreads();                 // the table image (loaded by all 512 threads) is in place for both groups
     while (tile < ntiles) {
         const long long next = tile + tstride;
+        double acc[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[k] = init_next[k];
         if (next < ntiles) {
             const SegTile tn = seg_tile_at<KS>(a, next, nstep, nsteps);
             seg_stage_tile(a, tn.t0, row_stride, bufs + (buf ^ 1) * tile_bytes, aligned16, gt);
+            if (a.seg_init) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    const long long i = tn.i0 + gt + k * GT;
+                    init_next[k] = a.seg_init[i < total ? i : total - 1];
+                }
+            }
         }
         cp_async_commit();
         cp_async_wait<1>();          // everything but the group just committed has landed
         seg_group_barrier(group);
 
         const uint32_t tile_off = (uint32_t)(L::LUT_BYTES + (group * 2 + buf) * tile_bytes);
-        double acc[KS];
         uint32_t wlo[KS], lo[KS], shift[KS];
         int fl[KS], ch[KS];          // frame (relative to the tile's first) and channel of each sample; fl < 0: past the end
         const long long f_lo = tl.i0 / a.nch;
@@ -357,7 +373,6 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
             shift[k] = 8u * (uint32_t)phi;
             wlo[k] = tile_off + (uint32_t)(aoff - 3 - phi);
             lo[k] = lds_u32(smem, wlo[k] + 4u);
-            acc[k] = a.seg_init ? a.seg_init[tl.i0 + n] : 0.0;
             fl[k] = live ? (int)q : -1;
             ch[k] = c;
         }
