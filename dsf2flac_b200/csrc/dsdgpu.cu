@@ -86,6 +86,8 @@ namespace {
 using Skew512 = SkewGeom<72, 4, 512, 12>;
 using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x2 = RingGeom<16, 2>;
+using Ring16x1 = RingGeom<16, 1>;               // the same kernel with one round per tile: half-size tiles for short launches
+static_assert(Ring16x1::LUT_BYTES == Ring16x2::LUT_BYTES, "both read the same table image");
 using Ring16x2Q = RingGeom<16, 1, true>;   // 32-bit tables: two images (197 KB) leave room for one round per tile
 using Ring30 = RingGeom<16, 2, false, 30, 2>;   // divide-by-16 filter: 30 tables, 2 bytes per frame
 using Ring12 = RingGeom<16, 2, false, 12, 1>;   // divide-by-8 filter: 12 tables, 1 byte per frame
@@ -393,7 +395,12 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         if (ctx->nlut == 30) return launch_ring<Ring30>(ctx, a, st);
         if (ctx->nlut == 12) return launch_ring<Ring12>(ctx, a, st);
         // (a 1024-thread instance of the 32-bit kernel fits in 64 registers but runs 13 % slower)
-        return ctx->lut_precision == 32 ? launch_ring<Ring16x2Q>(ctx, a, st) : launch_ring<Ring16x2>(ctx, a, st);
+        if (ctx->lut_precision == 32) return launch_ring<Ring16x2Q>(ctx, a, st);
+        // Tiles of 2 x 2048 frames run 1 % faster on a long stream; a short launch (a 60 s DSD64 file, a chunk of
+        // the pipelined host path) leaves the CTAs with an uneven handful of them: tiles of 2 x 1024 frames then
+        // (measured: configs[0] +2 %, configs[1] -1 %)
+        if (ring_tile_count<Ring16x2>(a.nframes, a.nch) < 24LL * ctx->sm_count) return launch_ring<Ring16x1>(ctx, a, st);
+        return launch_ring<Ring16x2>(ctx, a, st);
     }
     if (kernel == DSDGPU_KERNEL_SKEW) {
         if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
