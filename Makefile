@@ -9,8 +9,10 @@ PKG := dsf2flac_b200
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall \
            -I include -I $(PKG)/csrc
 HOSTSRC := $(PKG)/host/dsd_decimator.cpp $(PKG)/host/dsd_container.cpp $(PKG)/host/dsdhost_capi.cpp $(PKG)/host/dsd_synth.cpp
-HOSTHDR := $(wildcard $(PKG)/host/*.h) $(wildcard $(PKG)/host/*.inc) include/dsdgpu.h
-CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -I include -I $(PKG)/host
+HOSTHDR := $(wildcard $(PKG)/host/*.h) $(wildcard $(PKG)/host/standalone/*.h) $(wildcard $(PKG)/host/*.inc) include/dsdgpu.h
+# host/standalone holds the Boost/id3lib-free mirror of the reference's dsd_sample_reader.h; inside dsf2flac (and in
+# oracle/_ref/libdropin_ref*.so, see oracle/Makefile) the same dsd_decimator.{h,cpp} compile against the reference's own header
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -I include -I $(PKG)/host -I $(PKG)/host/standalone
 
 all: gpu host oracle tests
 
@@ -22,13 +24,10 @@ host: $(PKG)/libdsdhost.so
 $(PKG)/libdsdhost.so: $(HOSTSRC) $(HOSTHDR) $(PKG)/libdsdgpu.so
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) -L$(PKG) -ldsdgpu -Wl,-rpath,'$$ORIGIN'
 
-oracle:
+oracle: gpu
 	$(MAKE) -C oracle all
 
-tests: tests/cpp/_build/emu_skew tests/cpp/_build/emu_ring tests/cpp/_build/libdsdhost_cpu.so
-tests/cpp/_build/emu_skew: tests/cpp/emu_skew.cpp $(PKG)/csrc/skew_core.h
-	mkdir -p tests/cpp/_build
-	$(CXX) -O2 -std=c++17 -I $(PKG)/csrc -o $@ tests/cpp/emu_skew.cpp
+tests: tests/cpp/_build/emu_ring tests/cpp/_build/libdsdhost_cpu.so
 tests/cpp/_build/emu_ring: tests/cpp/emu_ring.cpp $(PKG)/csrc/ring_core.h
 	mkdir -p tests/cpp/_build
 	$(CXX) -O2 -std=c++17 -I $(PKG)/csrc -o $@ tests/cpp/emu_ring.cpp

@@ -313,9 +313,7 @@ def run_gpu_arm(args, wl):
     bits_per_step = nbytes * 8 * nch                       # DSD bits consumed per step per GPU
     g = capi.DsdGpu(lut, nch, fir.nstep, device=local, lut_precision=args.lut)
     if args.kernel:
-        g.set_option("kernel", {"auto": 0, "direct": 1, "skew": 2, "ring": 3, "seg": 4}[args.kernel])
-    if args.threads:
-        g.set_option("threads", args.threads)
+        g.set_option("kernel", {"auto": 0, "direct": 1, "ring": 3, "seg": 4}[args.kernel])
     if args.slots:
         g.set_option("slots", args.slots)
     if args.chunk_frames:
@@ -719,9 +717,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c4x", "c5", "dop"])
     ap.add_argument("--lut", type=int, default=64, choices=[64, 32])
     ap.add_argument("--dither", type=int, default=0)
-    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "skew", "ring", "seg"])
+    ap.add_argument("--kernel", default="", choices=["", "auto", "direct", "ring", "seg"])
     ap.add_argument("--align", type=int, default=1, help="0: device buffer starts at stream byte 0 (frame grid off by one byte)")
-    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--files", type=int, default=256, help="files in the c5 batch (about 120 MB of pinned host memory each)")
     ap.add_argument("--slots", type=int, default=0, help="pipelined slots of the host entry point (1..4)")
     ap.add_argument("--chunk-frames", type=int, default=0, help="frames per pipelined host chunk")

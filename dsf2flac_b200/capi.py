@@ -18,7 +18,7 @@ GPU_LIB = os.path.join(_HERE, "libdsdgpu.so")
 HOST_LIB = os.path.join(_HERE, "libdsdhost.so")
 
 OUT_INT32, OUT_FLOAT64 = 0, 1
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SKEW, KERNEL_RING, KERNEL_SEGMENTED = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RING, KERNEL_SEGMENTED = 0, 1, 3, 4
 ERR_NODEVICE = 3
 
 _u8p = C.POINTER(C.c_uint8)
@@ -94,6 +94,9 @@ def host_lib(path=None):
     lib.dsdhost_run_raw.restype = C.c_int
     lib.dsdhost_run_raw.argtypes = [_vp, C.c_int, i64, i64, C.c_uint8, C.c_int, u32, u32, i64, i64, i64, dbl, dbl, dbl,
                                     C.c_int, u32, _vp, _vp]
+    lib.dsdhost_run_raw_typed.restype = C.c_int
+    lib.dsdhost_run_raw_typed.argtypes = [_vp, C.c_int, i64, i64, C.c_uint8, C.c_int, u32, u32, i64, i64, i64, dbl, dbl, dbl,
+                                          C.c_int, u32, C.c_int, _vp]
     lib.dsdhost_run_app.restype = i64
     lib.dsdhost_run_app.argtypes = [_vp, C.c_int, i64, i64, C.c_uint8, C.c_int, u32, u32, dbl, dbl, dbl, C.c_int, u32,
                                     _vp, i64]

@@ -3,14 +3,12 @@
 //   decimate_ring_kernel    production kernel (ring_core.h): divide-by-32 / -16 / -8 filters, 32-bit tables, and the
 //                           two 72-table passes of the divide-by-64 extension filter
 //   decimate_seg_kernel     any geometry, <= 72 (64) tables per pass over a plane of running sums (seg_core.h)
-//   decimate_skew_kernel    the ring kernel's predecessor (skew_core.h), kept for A/B measurements
 //   decimate_direct_kernel  one thread per output sample, reference loop order: the cross-check partner
 //   deinterleave_kernel     DSDIFF byte-interleaved source -> planar rows
 //   dop_pack_*_kernel       DoP packing (reference dop_packer.cpp:100-141)
 // Reference path replaced: DsdDecimator::getSamplesInternal (reference src/dsd_decimator.cpp:173-222).
 #pragma once
 #include "dsdgpu.h"
-#include "skew_core.h"
 #include "ring_core.h"
 #include "seg_core.h"
 
@@ -116,7 +114,7 @@ decimate_direct_kernel(DecimateArgs a, int nstep) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// skewed kernel
+// staging helpers: cp.async, mbarriers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -181,80 +179,6 @@ __device__ __forceinline__ void stage_chunk16(const DecimateArgs& a, int c, long
         w[q] = v;
     }
     *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// Tiles are numbered channel-fastest: the CTAs that run side by side write the same frames of
-// neighbouring channels, so the 4-byte slots of one 32-byte output sector meet in L2 before the
-// sector goes to HBM (frame-major interleaved output, dsd_decimator.cpp:213).
-template <class G>
-__device__ __forceinline__ void skew_tile_geometry(const DecimateArgs& a, long long tile,
-                                                   long long tiles_per_ch, int& c, long long& f0,
-                                                   long long& t0, int& a_tile) {
-    (void)tiles_per_ch;
-    c = (int)(tile % a.nch);
-    f0 = (tile / a.nch) * G::NT;
-    skew_tile_origin<G>(a.p0, a.in_first, f0, t0, a_tile);
-}
-
-// Stage the tile's bytes [t0, t0 + TILE_BYTES) of channel c.  Interior chunks go through
-// cp.async (LDGSTS, 16 B, coalesced); chunks that touch the ends of the source are assembled
-// byte by byte with the fill value.
-template <class G>
-__device__ __forceinline__ void skew_stage_tile(const DecimateArgs& a, int c, long long t0,
-                                                unsigned char* dst, bool aligned16) {
-    const long long o0 = t0 - a.in_first;
-    for (int k = threadIdx.x; k < G::TILE_BYTES / 16; k += G::NTHR) {
-        const long long o = o0 + 16LL * k;
-        unsigned char* d = dst + 16 * k;
-        stage_chunk16(a, c, o, d, aligned16);
-    }
-}
-
-template <class G>
-__global__ void __launch_bounds__(G::NTHR, 1) decimate_skew_kernel(DecimateArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    // [0, LUT_BYTES): table image; then two byte tiles.
-    const int tid = threadIdx.x;
-    {
-        const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
-        for (int k = tid; k < G::LUT_BYTES / 16; k += G::NTHR) cp_async16(smem + 16 * k, img + 16 * k);
-    }
-    const long long tiles_per_ch = (a.nframes + G::NT - 1) / G::NT;
-    const long long ntiles = tiles_per_ch * a.nch;
-    const bool aligned16 = src_aligned16(a);
-
-    long long tile = blockIdx.x;
-    int buf = 0;
-    int c; long long f0, t0; int a_tile;
-    if (tile < ntiles) {
-        skew_tile_geometry<G>(a, tile, tiles_per_ch, c, f0, t0, a_tile);
-        skew_stage_tile<G>(a, c, t0, smem + G::LUT_BYTES, aligned16);
-    }
-    cp_async_commit();
-    while (tile < ntiles) {
-        const long long next = tile + gridDim.x;
-        if (next < ntiles) {
-            int cn; long long f0n, t0n; int an;
-            skew_tile_geometry<G>(a, next, tiles_per_ch, cn, f0n, t0n, an);
-            skew_stage_tile<G>(a, cn, t0n, smem + G::LUT_BYTES + (buf ^ 1) * G::TILE_BYTES, aligned16);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();          // everything but the group just committed has landed
-        __syncthreads();
-
-        const long long fbase = f0 + tid;
-        skew_tile_lane<G>(smem, (uint32_t)(G::LUT_BYTES + buf * G::TILE_BYTES), tid, a_tile,
-                          [&](int k, double sum) {
-                              const long long f = fbase + (long long)k * G::NTHR;
-                              if (f < a.nframes) store_sample(a, f, c, sum);
-                          },
-                          NoTrace());
-        __syncthreads();             // tile `buf` is free again
-        tile = next;
-        buf ^= 1;
-        if (tile < ntiles) skew_tile_geometry<G>(a, tile, tiles_per_ch, c, f0, t0, a_tile);
-    }
-    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,7 +296,7 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
             const int phi = (aoff + 1) & 3;
             shift[k] = 8u * (uint32_t)phi;
             wlo[k] = tile_off + (uint32_t)(aoff - 3 - phi);
-            lo[k] = lds_u32(smem, wlo[k] + 4u);
+            lo[k] = ring_lds_u32(smem, wlo[k] + 4u);
             fl[k] = live ? (int)q : -1;
             ch[k] = c;
         }
@@ -383,20 +307,20 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
 #pragma unroll
             for (int k = 0; k < KS; ++k) {
                 const uint32_t hi = lo[k];
-                lo[k] = lds_u32(smem, wlo[k]);
+                lo[k] = ring_lds_u32(smem, wlo[k]);
                 wlo[k] -= 4u;
-                x[k] = funnel_r(lo[k], hi, shift[k]);
+                x[k] = ring_funnel_r(lo[k], hi, shift[k]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
 #pragma unroll
                 for (int k = 0; k < KS; ++k) {
                     uint32_t e;
-                    if (u == 0) e = byte_of<3>(x[k]);
-                    else if (u == 1) e = byte_of<2>(x[k]);
-                    else if (u == 2) e = byte_of<1>(x[k]);
-                    else e = byte_of<0>(x[k]);
-                    acc[k] = __dadd_rn(acc[k], lds_f64(smem, e * (uint32_t)L::ROW_BYTES + lut + 8u * (uint32_t)u));
+                    if (u == 0) e = ring_byte<3>(x[k]);
+                    else if (u == 1) e = ring_byte<2>(x[k]);
+                    else if (u == 2) e = ring_byte<1>(x[k]);
+                    else e = ring_byte<0>(x[k]);
+                    acc[k] = __dadd_rn(acc[k], ring_lds_f64(smem, e * (uint32_t)L::ROW_BYTES + lut + 8u * (uint32_t)u));
                 }
             }
             lut += 32u;
@@ -455,15 +379,15 @@ struct RingEmitter {
     const DecimateArgs& a;
     RingDest d, nx;              // the frames being finished / the frames the lane starts in the next period
     int h;
-    bool out_aligned16;
+    bool out_aligned16, out_aligned8;      // of a.out: the 16- and 8-byte stores below need them (a caller's device pointer may be a slice)
     int vi[4];
     double vd[4];
     double iv[4];
     double dv[4];
     static constexpr bool LATE = DITHER;
 
-    __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, const RingDest& nx_, int h_, bool al)
-        : a(a_), d(d_), nx(nx_), h(h_), out_aligned16(al) {}
+    __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, const RingDest& nx_, int h_, unsigned out_low_bits)
+        : a(a_), d(d_), nx(nx_), h(h_), out_aligned16((out_low_bits & 15u) == 0), out_aligned8((out_low_bits & 7u) == 0) {}
 
     // the dither terms of the four frames being finished, issued well ahead of quantise()
     // Pair tiles read them the way the stores go out: a lane loads the 16-byte pairs {D(f, c0), D(f, c0 + 1)}
@@ -555,9 +479,12 @@ struct RingEmitter {
             const int2 hi2 = h ? make_int2(s1, vi[3]) : make_int2(vi[1], s1);
             if (a.nch == 2 && out_aligned16 && f + 1 < nf) {
                 *reinterpret_cast<int4*>(out + f * 2) = make_int4(lo2.x, lo2.y, hi2.x, hi2.y);
-            } else {
+            } else if (out_aligned8) {
                 if (f < nf) *reinterpret_cast<int2*>(out + f * a.nch + d.c0) = lo2;
                 if (f + 1 < nf) *reinterpret_cast<int2*>(out + (f + 1) * a.nch + d.c0) = hi2;
+            } else {                // output base only 4-byte aligned: scalar stores
+                if (f < nf) { out[f * a.nch + d.c0] = lo2.x; out[f * a.nch + d.c0 + 1] = lo2.y; }
+                if (f + 1 < nf) { out[(f + 1) * a.nch + d.c0] = hi2.x; out[(f + 1) * a.nch + d.c0 + 1] = hi2.y; }
             }
         } else if (a.nch == 1 && out_aligned16 && fb + 3 < nf) {
             *reinterpret_cast<int4*>(out + fb) = make_int4(vi[0], vi[1], vi[2], vi[3]);
@@ -595,7 +522,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     }
     const long long ntiles = ring_tile_count<G>(a.nframes, a.nch);
     const bool aligned16 = src_aligned16(a);
-    const bool out_aligned16 = (reinterpret_cast<unsigned long long>(a.out) & 15ULL) == 0;
+    const unsigned out_low_bits = (unsigned)(reinterpret_cast<unsigned long long>(a.out) & 15ULL);
     int a_tile;
     {
         long long t0;
@@ -653,7 +580,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             RingDest nx = cur;           // the frames this lane starts in the next period
             nx.fb += 4LL * G::BLK_PER_ROUND;
             if (n + 1 == G::KR) nx = after;
-            RingEmitter<OUT, DITHER, INIT> emit(a, prev, nx, h, out_aligned16);
+            RingEmitter<OUT, DITHER, INIT> emit(a, prev, nx, h, out_low_bits);
             ring_tail<G>(lane, smem, wnew, loff, tid, n, emit, RingNoTrace());
             prev = cur;
             cur.fb += 4LL * G::BLK_PER_ROUND;
@@ -665,7 +592,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     }
     // the one drain of this CTA: 16 more steps finish the last frames
     ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
-    RingEmitter<OUT, DITHER, INIT> emit(a, prev, prev, h, out_aligned16);
+    RingEmitter<OUT, DITHER, INIT> emit(a, prev, prev, h, out_low_bits);
     emit.fetch();
 #pragma unroll
     for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));

@@ -2,11 +2,10 @@
 //
 // Hot path replaced: DsdDecimator::getSamplesInternal (reference src/dsd_decimator.cpp:173-222)
 // -- the per-byte lookup-table FIR (:194-198) fused with scale / TPDF dither / clip / round
-// (:199-216).  The kernels live in dsd_kernels.cuh (lane logic: ring_core.h, seg_core.h, skew_core.h),
+// (:199-216).  The kernels live in dsd_kernels.cuh (lane logic: ring_core.h, seg_core.h),
 // the positional reconstruction of the reference's dither stream in dsd_rand.cuh.
 // There is no CPU fallback anywhere in this library.
 #include "dsdgpu.h"
-#include "skew_core.h"
 #include "ring_core.h"
 #include "seg_core.h"
 
@@ -54,12 +53,10 @@ struct dsdgpu_ctx {
     int device = 0, nch = 0, nlut = 0, nstep = 0, lut_precision = 64;
     int sm_count = 0;
     int kernel = DSDGPU_KERNEL_AUTO;
-    int threads = 512;
     int dither_stride = 0;                   // 0 = nch
     long long source_block = 0;              // 0: planar rows; 1: byte-interleaved; 2^k >= 16: block-planar
     long long chunk_frames = 1LL << 20;
     double* d_lut_direct = nullptr;          // [nlut][256]
-    unsigned char* d_lut_skew = nullptr;     // SkewGeom::LUT_BYTES image (nlut == 72 only)
     unsigned char* d_lut_ring = nullptr;     // RingGeom::LUT_BYTES image (nlut == 72 only): fp64 or 32-bit entries
     unsigned char* d_lut_seg = nullptr;      // nseg x LUT_BYTES images, SEG_DEFAULT tables each (any geometry)
     int nseg = 0;
@@ -83,8 +80,6 @@ struct dsdgpu_ctx {
 
 namespace {
 
-using Skew512 = SkewGeom<72, 4, 512, 12>;
-using Skew1024 = SkewGeom<72, 4, 1024, 6>;
 using Ring16x2 = RingGeom<16, 2>;
 using Ring16x1 = RingGeom<16, 1>;               // the same kernel with one round per tile: half-size tiles for short launches
 static_assert(Ring16x1::LUT_BYTES == Ring16x2::LUT_BYTES, "both read the same table image");
@@ -179,22 +174,6 @@ int launch_dither(dsdgpu_ctx* ctx, dsdgpu_slot& s, unsigned long long first_samp
             seg, ctx->d_rand_lane, ctx->d_rand_jump, n, d_out + done);
         ctx->launches += 1;
     }
-    CUDA_TRY(ctx, cudaGetLastError());
-    return DSDGPU_OK;
-}
-
-template <class G>
-int launch_skew(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
-    const int smem = G::LUT_BYTES + 2 * G::TILE_BYTES;
-    static thread_local int configured_device = -1;
-    if (configured_device != ctx->device) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(decimate_skew_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_device = ctx->device;
-    }
-    const long long tiles = ((a.nframes + G::NT - 1) / G::NT) * a.nch;
-    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    decimate_skew_kernel<G><<<grid, G::NTHR, smem, st>>>(a);
-    ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return DSDGPU_OK;
 }
@@ -382,11 +361,10 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         if (rc) return rc;
         a.dither = scratch.d_dither;
     }
-    const bool skew_ok = (ctx->nlut == 72 && ctx->nstep == 4 && ctx->d_lut_skew != nullptr);
     const bool ring_ok = ctx->d_lut_ring != nullptr;
     int kernel = ctx->kernel;
     if (kernel == DSDGPU_KERNEL_AUTO)
-        kernel = ring_ok ? DSDGPU_KERNEL_RING : skew_ok ? DSDGPU_KERNEL_SKEW
+        kernel = ring_ok ? DSDGPU_KERNEL_RING
                : seg_samples_per_thread(ctx) > 0 ? DSDGPU_KERNEL_SEGMENTED : DSDGPU_KERNEL_DIRECT;
     if (kernel == DSDGPU_KERNEL_RING) {
         if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) or of the divide-by-64 extension (144/8), and tables without -0.0 entries");
@@ -401,12 +379,6 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         // (measured: configs[0] +2 %, configs[1] -1 %)
         if (ring_tile_count<Ring16x2>(a.nframes, a.nch) < 24LL * ctx->sm_count) return launch_ring<Ring16x1>(ctx, a, st);
         return launch_ring<Ring16x2>(ctx, a, st);
-    }
-    if (kernel == DSDGPU_KERNEL_SKEW) {
-        if (!skew_ok) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel needs nlut=72, nstep=4");
-        if (block_shift >= 0) return fail(ctx, DSDGPU_ERR_ARG, "skew kernel reads planar sources only");
-        a.lut = ctx->d_lut_skew;
-        return ctx->threads == 1024 ? launch_skew<Skew1024>(ctx, a, st) : launch_skew<Skew512>(ctx, a, st);
     }
     if (kernel == DSDGPU_KERNEL_SEGMENTED) return launch_seg(ctx, scratch, a, st);
     a.lut = ctx->d_lut_direct;
@@ -486,10 +458,6 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     for (double v : tab) plain = plain && std::isfinite(v) && !(v == 0.0 && std::signbit(v));
     std::vector<unsigned char> rimg;
     if (nlut == 72 && nstep == 4) {
-        std::vector<unsigned char> img(Skew512::LUT_BYTES);
-        skew_build_lut_image<Skew512>(tab.data(), img.data());
-        CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_skew), img.size()));
-        CREATE_TRY(cudaMemcpy(ctx->d_lut_skew, img.data(), img.size(), cudaMemcpyHostToDevice));
         if (lut_precision == 32) {
             rimg.resize(Ring16x2Q::LUT_BYTES);
             ring_build_lut_image<Ring16x2Q>(tab.data(), rimg.data(), ctx->lut_unit);
@@ -592,7 +560,6 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     for (int s = 0; s < DSDGPU_SLOTS; ++s) free_slot(ctx->slots[s]);
     free_slot(ctx->own);
     if (ctx->d_lut_direct) cudaFree(ctx->d_lut_direct);
-    if (ctx->d_lut_skew) cudaFree(ctx->d_lut_skew);
     if (ctx->d_lut_ring) cudaFree(ctx->d_lut_ring);
     if (ctx->d_lut_seg) cudaFree(ctx->d_lut_seg);
     if (ctx->d_rand_lane) cudaFree(ctx->d_rand_lane);
@@ -606,11 +573,9 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx) { return ctx ? ctx->err : g
 int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     if (!ctx || !key) return DSDGPU_ERR_ARG;
     if (!strcmp(key, "kernel")) {
-        if (value < DSDGPU_KERNEL_AUTO || value > DSDGPU_KERNEL_SEGMENTED) return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
+        if (value != DSDGPU_KERNEL_AUTO && value != DSDGPU_KERNEL_DIRECT && value != DSDGPU_KERNEL_RING && value != DSDGPU_KERNEL_SEGMENTED)
+            return fail(ctx, DSDGPU_ERR_ARG, "bad kernel %lld", value);
         ctx->kernel = (int)value;
-    } else if (!strcmp(key, "threads")) {
-        if (value != 512 && value != 1024) return fail(ctx, DSDGPU_ERR_ARG, "threads must be 512 or 1024");
-        ctx->threads = (int)value;
     } else if (!strcmp(key, "dither_stride")) {
         if (value != 0 && value < ctx->nch) return fail(ctx, DSDGPU_ERR_ARG, "dither_stride must be 0 or >= nch");
         ctx->dither_stride = (int)value;

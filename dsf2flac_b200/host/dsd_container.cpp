@@ -62,6 +62,9 @@ bool load_dsf(const File& f, DsdContainer& c) {
     at += fmtSz;
     if (!f.has(at, 12) || !is(b + at, "data")) return fail(c, "dsfFileReader::readHeaders:file ident error");
     c.dataOffset = (int64_t)at + 12;
+    // header fields of an untrusted file: a sample count that is negative as int64, or so large that rounding it up
+    // to bytes would overflow, would otherwise turn into a negative / wrapped payload size below
+    if (c.lengthSamples < 0 || c.lengthSamples > (int64_t)1 << 62) return fail(c, "dsfFileReader::readHeaders:implausible sample count");
     if (bits != 1) return fail(c, "Sorry, only one bit data is supported");          // dsf_file_reader.cpp:56-61
     if (c.channels < 1 || c.channels > 64) return fail(c, "unsupported channel count");
     if (block < 16 || (block & (block - 1)) != 0) return fail(c, "unsupported DSF block size (GPU path needs a power of two >= 16)");
@@ -103,6 +106,7 @@ bool load_dsdiff(const File& f, DsdContainer& c) {
     for (;;) {
         if (!f.has(at, 12)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
         uint64_t sz = be64(b + at + 4);
+        if (sz > (uint64_t)1 << 62) return fail(c, "dsdiffFileReader::readChunkHeader:implausible chunk size");   // size + 13 must not wrap (a chunk of 0 bytes would never advance)
         sz += (sz & 1) ? 13 : 12;
         if (is(b + at, "FRM8")) { frmSz = sz; break; }
         at += sz;
@@ -116,6 +120,7 @@ bool load_dsdiff(const File& f, DsdContainer& c) {
     for (uint64_t sub = at + 16; sub < frmStart + frmSz;) {
         if (!f.has(sub, 12)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
         uint64_t sz = be64(b + sub + 4);
+        if (sz > (uint64_t)1 << 62) return fail(c, "dsdiffFileReader::readChunkHeader:implausible chunk size");
         sz += (sz & 1) ? 13 : 12;
         if (!fver && is(b + sub, "FVER")) {
             fver = f.has(sub + 12, 4);
@@ -124,6 +129,7 @@ bool load_dsdiff(const File& f, DsdContainer& c) {
             for (uint64_t p = sub + 16; p < sub + sz;) {
                 if (!f.has(p, 12)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
                 uint64_t psz = be64(b + p + 4);
+                if (psz > (uint64_t)1 << 62) return fail(c, "dsdiffFileReader::readChunkHeader:implausible chunk size");
                 psz += (psz & 1) ? 13 : 12;
                 if (!fs && is(b + p, "FS  ") && f.has(p + 12, 4)) { c.samplingFreq = be32(b + p + 12); fs = true; }
                 else if (!chnl && is(b + p, "CHNL") && f.has(p + 12, 2)) { c.channels = be16(b + p + 12); chnl = true; }
@@ -151,7 +157,9 @@ bool load_dsdiff(const File& f, DsdContainer& c) {
     if (std::memcmp(compression, "DSD ", 4) != 0) return fail(c, "unknown DSDIFF compression type");
     if (c.channels < 1 || c.channels > 64) return fail(c, "unsupported channel count");
     const int64_t nch = c.channels;
-    const int64_t N = (int64_t)((dataChunkLen - 12) / (uint64_t)nch);                  // dsdiff_file_reader.cpp:1037
+    // dsdiff_file_reader.cpp:1037 divides the PADDED chunk length (readChunkHeader has already added the pad byte of an
+    // odd-sized chunk, :1160-1163), so an odd "DSD " chunk counts its pad byte as a sample byte; reproduced, not fixed
+    const int64_t N = (int64_t)((dataChunkLen - 12) / (uint64_t)nch);
     c.lengthSamples = N * 8;
     c.msbIsPlayedFirst = false;                                                        // dsdiff_file_reader.h:121
     c.blockBytes = 1;

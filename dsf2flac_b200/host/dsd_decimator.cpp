@@ -182,6 +182,13 @@ bool DsdDecimator::openGpu(int bits)
         return false;
     }
     dsdgpu_set_option(gpu, "slots", DSDGPU_SLOTS - 1);
+    // a bulk source set before this (re)creation keeps its layout on the new context
+    if (bulk && dsdgpu_set_option(gpu, "source_block_bytes", bulkBlock) != DSDGPU_OK) {
+        fail(std::string("DsdDecimator: ") + dsdgpu_last_error(gpu));
+        dsdgpu_destroy(gpu);
+        gpu = nullptr;
+        return false;
+    }
     lutBits = bits;
     blockFrames = 0;
     return true;
@@ -304,7 +311,6 @@ void DsdDecimator::harvest(dsf2flac_int64 lo, dsf2flac_int64 hi)
             if (keep) std::memmove(bytes + c * bytesStride, bytes + c * bytesStride + (keepFrom - bytesFirst), keep);
         bytesFirst = keepFrom; bytesCount = (dsf2flac_int64)keep;
     }
-    DsdByteRing* dummy = nullptr; (void)dummy;
     auto* rings = reader->getBuffer();
     while (harvested <= hi) {
         reader->step();                                  // pushes byte number `harvested` of every channel
@@ -397,11 +403,13 @@ void DsdDecimator::serve(T* buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 
         }
         if (idx < 0) {
             if (!refill(frames - done, scale, dither, clip, outKind)) {
-                // GPU path failed: there is deliberately no CPU fallback; hand back silence
-                for (dsf2flac_uint32 i = done * nch; i < frames * nch; ++i) buffer[i] = T(0);
-                pos += (dsf2flac_int64)(frames - done) * nStep;
-                samplesOut += (dsf2flac_uint64)(frames - done) * nch;
-                return;
+                // The GPU path failed and there is deliberately no CPU fallback.  main.cpp checks isValid() once,
+                // after construction (main.cpp:232-236); handing back made-up samples here would end in a FLAC
+                // file with silence in it and exit code 0.  The reference's convention for an unrecoverable error
+                // inside this function is message + exit (dsd_decimator.cpp:182-186): do the same.
+                fputs(errorMsg.empty() ? "DsdDecimator: GPU decimation failed" : errorMsg.c_str(), stderr);
+                fputs("\n", stderr);
+                exit(EXIT_FAILURE);
             }
             idx = 0;
         }

@@ -19,6 +19,17 @@ namespace {
 thread_local std::string g_error;
 }
 
+namespace {
+template <typename T>
+void raw_calls(DsdDecimator& dec, int nch, int64_t nframes, int64_t chunk_frames, double scale, double dither, double clip, void* out) {
+    T* dst = static_cast<T*>(out);
+    for (int64_t f = 0; f < nframes; f += chunk_frames) {
+        const int64_t n = nframes - f < chunk_frames ? nframes - f : chunk_frames;
+        dec.getSamples(dst + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
+    }
+}
+}  // namespace
+
 extern "C" {
 
 const char* dsdhost_last_error() { return g_error.c_str(); }
@@ -61,6 +72,32 @@ int dsdhost_run_raw(const uint8_t* planar, int nch, int64_t nbytes, int64_t leng
         const int64_t n = nframes - f < chunk_frames ? nframes - f : chunk_frames;
         if (out_i32) dec.getSamples(out_i32 + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
         else dec.getSamples(out_f64 + f * nch, (dsf2flac_uint32)(n * nch), scale, dither, clip);
+    }
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return 1; }
+    return 0;
+}
+
+// The same through any of the five getSamples<T> specialisations (reference dsd_decimator.cpp:153-172).
+// type: 0 int16, 1 int32, 2 int64, 3 float32, 4 float64; out is [nframes][nch] of that type.
+
+int dsdhost_run_raw_typed(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples, uint8_t idle,
+                          int msb_flag, uint32_t dsd_fs, uint32_t out_fs, int64_t pre_steps, int64_t nframes,
+                          int64_t chunk_frames, double scale, double dither, double clip, int lut_bits, uint32_t read_ahead,
+                          int type, void* out) {
+    MemorySampleReader rd(planar, (uint32_t)nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return 1; }
+    if (lut_bits != 64 && !dec.setLutPrecision(lut_bits)) { g_error = dec.getErrorMsg(); return 1; }
+    if (read_ahead) dec.setReadAheadFrames(read_ahead);
+    for (int64_t i = 0; i < pre_steps; ++i) dec.step();
+    if (chunk_frames <= 0) chunk_frames = nframes;
+    switch (type) {
+    case 0: raw_calls<dsf2flac_int16>(dec, nch, nframes, chunk_frames, scale, dither, clip, out); break;
+    case 1: raw_calls<dsf2flac_int32>(dec, nch, nframes, chunk_frames, scale, dither, clip, out); break;
+    case 2: raw_calls<dsf2flac_int64>(dec, nch, nframes, chunk_frames, scale, dither, clip, out); break;
+    case 3: raw_calls<dsf2flac_float32>(dec, nch, nframes, chunk_frames, scale, dither, clip, out); break;
+    case 4: raw_calls<dsf2flac_float64>(dec, nch, nframes, chunk_frames, scale, dither, clip, out); break;
+    default: g_error = "unknown sample type"; return 1;
     }
     if (!dec.isValid()) { g_error = dec.getErrorMsg(); return 1; }
     return 0;

@@ -55,7 +55,7 @@ enum { DSDGPU_OUT_INT32 = 0, DSDGPU_OUT_FLOAT64 = 1 };
 enum {
     DSDGPU_KERNEL_AUTO = 0,   /* ring kernel when the geometry supports it, else direct */
     DSDGPU_KERNEL_DIRECT = 1, /* one thread per output sample, tables [t][byte] in smem */
-    DSDGPU_KERNEL_SKEW = 2,   /* lane-skewed kernel, 80-step periods (divide-by-32 filters) */
+                              /* 2 was the ring kernel's predecessor (80-step periods); retired */
     DSDGPU_KERNEL_RING = 3,   /* lane-skewed kernel, 72-step periods, 4 frames per lane (divide-by-32) */
     DSDGPU_KERNEL_SEGMENTED = 4 /* lane-skewed kernel for any geometry, <= 72 tables per pass; filters with
                                    more tables (the /64, /128, /256 extension filters) run as a chain of
@@ -101,8 +101,7 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
  *      (dsf_file_reader.cpp:122-149): in[((o / B)*nch + c)*B + o % B]; in_first % B must be 0
  *   1  DSDIFF "DSD " chunk, byte-interleaved (dsdiff_file_reader.cpp:234): in[o*nch + c]
  *   in_stride is ignored for B != 0; the bytes are consumed where they lie, no host re-packing),
- * "threads"
- * (skew kernel CTA size, 512 or 1024), "dither_stride" (output samples per frame of the WHOLE
+ * "dither_stride" (output samples per frame of the WHOLE
  * stream when this context only holds a channel subset of it: sample m of frame i, local channel
  * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default), "trace" (1: every
  * dsdgpu_decimate_host call prints the timeline of its chunks -- upload, kernel, download, from events

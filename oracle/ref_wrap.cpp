@@ -21,47 +21,10 @@
 #include "dsdiff_file_reader.h"
 #include "dsf_file_reader.h"
 
-namespace {
+#include "app_driver.h"
+#include "ref_memory_reader.h"
 
-class MemoryReader : public DsdSampleReader {
-public:
-    MemoryReader(const uint8_t* planar, int nch, int64_t nbytes, int64_t lengthSamples,
-                 uint32_t fs, bool msbFirstFlag, uint8_t idle)
-        : data_(planar), nch_(nch), nbytes_(nbytes), len_(lengthSamples), fs_(fs),
-          msb_(msbFirstFlag), idle_(idle) {
-        samplesPerChar = 8;
-        valid = true;
-        posMarker = -1;
-        allocateBuffer();
-        rewind();
-    }
-    dsf2flac_uint32 getSamplingFreq() { return fs_; }
-    dsf2flac_uint32 getNumChannels() { return (dsf2flac_uint32)nch_; }
-    dsf2flac_int64 getLength() { return len_; }
-    bool msbIsPlayedFirst() { return msb_; }
-    dsf2flac_uint8 getIdleSample() { return idle_; }
-    void rewind() { posMarker = -1; clearBuffer(); }
-    // same shape as DsfFileReader::step(): availability is tested BEFORE the marker moves, so
-    // the byte at index L/8 is still fetched when L is a multiple of 8 (SURVEY 8a edge case).
-    bool step() {
-        bool ok = samplesAvailable();
-        const int64_t k = posMarker + 1;
-        for (int c = 0; c < nch_; ++c) {
-            uint8_t b = idle_;
-            if (ok && k >= 0 && k < nbytes_) b = data_[(int64_t)c * nbytes_ + k];
-            circularBuffers[c].push_front(b);
-        }
-        posMarker++;
-        return ok;
-    }
-private:
-    const uint8_t* data_;
-    int nch_;
-    int64_t nbytes_, len_;
-    uint32_t fs_;
-    bool msb_;
-    uint8_t idle_;
-};
+namespace {
 
 // EXTENSION filters.  The reference rejects every ratio but 8, 16 and 32
 // (dsd_decimator.cpp:57-68).  To run ITS arithmetic -- initLookupTable and getSamplesInternal, both
@@ -331,6 +294,42 @@ int64_t dsdref_file_run_dop(const char* path, int kind, int32_t* out, int64_t ou
     close_reader(dsr);
     return done;
 }
+
+// ---- all five getSamples<T> specialisations (dsd_decimator.cpp:153-172), driven by oracle/app_driver.h ----
+// type: 0 int16, 1 int32, 2 int64, 3 float32, 4 float64; out is [nframes][nch] of that type.
+int dsdref_run_raw_typed(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples, uint8_t idle,
+                         int msb_flag, uint32_t dsd_fs, uint32_t out_fs, int64_t pre_steps, int64_t nframes,
+                         int64_t chunk_frames, double scale, double dither, double clip, int reseed, int type, void* out) {
+    MemoryReader rd(planar, nch, nbytes, length_samples, dsd_fs, msb_flag != 0, idle);
+    RefDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) return 1;
+    if (reseed) srand(1);
+    return app_driver::raw_loop_typed(dec, nch, type, pre_steps, nframes, chunk_frames, scale, dither, clip, out);
+}
+
+// One file through the reference's own reader + decimator with main.cpp's loop, any sample type.
+// Returns frames written, -1 reader invalid, -3 decimator invalid, -2 out too small.  One call per process.
+int64_t dsdref_file_run_typed(const char* path, int kind, uint32_t out_fs, double scale, double dither, double clip,
+                              int reseed, int type, void* out, int64_t out_cap_frames, int32_t* info, int64_t* length) {
+    DsdSampleReader* rd = open_reader(path, kind);
+    if (!rd || !rd->isValid()) { close_reader(rd); return -1; }
+    if (info) {
+        info[0] = (int32_t)rd->getNumChannels();
+        info[1] = (int32_t)rd->getSamplingFreq();
+        info[2] = rd->msbIsPlayedFirst() ? 1 : 0;
+    }
+    if (length) *length = rd->getLength();
+    int64_t done;
+    {
+        DsdDecimator dec(rd, out_fs);
+        if (!dec.isValid()) { close_reader(rd); return -3; }
+        if (reseed) srand(1);
+        done = app_driver::app_loop_typed(dec, (int)rd->getNumChannels(), type, scale, dither, clip, out, out_cap_frames);
+    }
+    close_reader(rd);
+    return done;
+}
+
 
 // libc rand() as the reference sees it: srand(1) then n draws (pins the restated generator).
 void dsdref_libc_rand(int32_t* out, int64_t n) {

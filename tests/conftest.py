@@ -19,6 +19,14 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def oracle():
+    """The checker of the parity tests: the unmodified reference (oracle/_ref) where it is present, else the C restatement."""
+    from tests import oracle_lib
+    return oracle_lib.BestOracle()
+
+
+@pytest.fixture(scope="session")
+def port():
+    """The C restatement itself (oracle/dsd_oracle.c), for the tests that pin it to the reference and the golden vectors."""
     from tests import oracle_lib
     return oracle_lib.Oracle()
 

@@ -75,6 +75,13 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
                          int64_t in_count, uint8_t fill, int64_t p0, int64_t nframes, double scale,
                          double dither_amp, double clip, uint64_t dither_first_sample, int out_kind,
                          void* out) {
+    // failure injection for the "fail loudly" test: DSDGPU_STANDIN_FAIL_AFTER=n makes every call after the n-th fail
+    if (const char* env = getenv("DSDGPU_STANDIN_FAIL_AFTER")) {
+        if ((long long)ctx->launches >= atoll(env)) {
+            snprintf(ctx->err, sizeof ctx->err, "injected failure (stand-in)");
+            return DSDGPU_ERR_CUDA;
+        }
+    }
     std::vector<double> dith;
     const long long stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
     if (dither_amp > 0 && nframes > 0) dither_terms(dither_first_sample, (nframes - 1) * stride + ctx->nch, dith);

@@ -95,6 +95,29 @@ def test_container_rejects():
     assert file_info(lib, os.path.join(ROOT, "README.md"))[0] == 0
 
 
+def test_hostile_headers_are_refused(tmp_path):
+    """Header fields of untrusted files: a negative / overflowing DSF sample count, DSDIFF chunk sizes whose +12/+13
+    wraps (a top-level chunk of "size" 2^64-12 would never advance the walk).  Each must come back as an error."""
+    import struct
+    lib = cpu_host_lib()
+    data = seeded_bytes(2, 5000, 9)
+    for k, count in enumerate((-1, -8 * 4096, (1 << 63) - 1, (1 << 63) - 8)):
+        p = str(tmp_path / f"bad{k}.dsf")
+        write_dsf(p, data, DSD64, sample_count=count & 0xFFFFFFFFFFFFFFFF)
+        assert file_info(lib, p)[0] == 0 and b"sample count" in lib.dsdhost_last_error()
+    good = tmp_path / "good.dff"
+    write_dsdiff(str(good), data, DSD64)
+    raw = good.read_bytes()
+    assert file_info(lib, str(good))[0] == 1
+    for k, size in enumerate((0xFFFFFFFFFFFFFFF4, 0xFFFFFFFFFFFFFFF3, 1 << 63)):
+        p = tmp_path / f"bad{k}.dff"
+        p.write_bytes(b"JUNK" + struct.pack(">Q", size) + raw)          # a leading chunk whose size wraps
+        assert file_info(lib, str(p), 2)[0] == 0 and b"chunk size" in lib.dsdhost_last_error()
+        at = raw.index(b"PROP")
+        p.write_bytes(raw[:at + 4] + struct.pack(">Q", size) + raw[at + 12:])
+        assert file_info(lib, str(p))[0] == 0
+
+
 def test_dst_compressed_dsdiff_is_refused(tmp_path):
     import struct
     from tests.dsd_files import _chunk

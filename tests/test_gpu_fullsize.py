@@ -3,7 +3,7 @@
 config 1 (DSD64 stereo 60 s -> 24 bit / 88.2 kHz) is compared with the oracle in full.
 config 2 (DSD128 stereo 60 s -> 176.4 kHz, fp64 tables) is too long for that to stay in the
 seconds range, so it is checked through size-independent properties: two independent kernels
-(skewed and direct) agree bit for bit over the whole stream, time-segment shards with their
+(segmented and direct) agree bit for bit over the whole stream, time-segment shards with their
 halo stitch to the unsharded result, and windows sampled across the stream equal the oracle."""
 import numpy as np
 import pytest
@@ -50,11 +50,11 @@ def test_config2_full_properties(oracle):
     scale, amp, clip = filters.app_params(24, dither=False)
     lut = filters.build_lut(fir, 1)
     outs = {}
-    for name, k in (("ring", capi.KERNEL_RING), ("skew", capi.KERNEL_SKEW), ("direct", capi.KERNEL_DIRECT)):
+    for name, k in (("ring", capi.KERNEL_RING), ("seg", capi.KERNEL_SEGMENTED), ("direct", capi.KERNEL_DIRECT)):
         with capi.DsdGpu(lut, 2, fir.nstep) as g:
             g.set_option("kernel", k)
             outs[name] = g.decimate_host(data, fir.nlut, n, scale, amp, clip)
-    assert np.array_equal(outs["skew"], outs["direct"])
+    assert np.array_equal(outs["seg"], outs["direct"])
     assert np.array_equal(outs["ring"], outs["direct"])
     # 8-way time/channel shards with halos == unsharded
     job = batch.Job(data, fs, 176400, msb_flag=True, bits=24, dither=False)
@@ -63,7 +63,7 @@ def test_config2_full_properties(oracle):
     for r in range(8):
         parts += runner.run([job], r, 8)
     assert len(parts) == 8
-    assert np.array_equal(batch.stitch([job], parts)[0], outs["skew"])
+    assert np.array_equal(batch.stitch([job], parts)[0], outs["seg"])
     runner.close()
     # sampled windows against the oracle (start, middle, the very end)
     for f0 in (0, n // 3, n - 50000):
@@ -73,9 +73,9 @@ def test_config2_full_properties(oracle):
         pre = fir.nlut + f0 * fir.nstep - b0 + 1
         cnt = min(50000, n - f0)
         want = oracle.run_raw(sub, 1 << 40, 1, fs, 176400, pre, cnt, scale, amp, clip)
-        assert np.array_equal(outs["skew"][f0:f0 + cnt], want), f0
+        assert np.array_equal(outs["seg"][f0:f0 + cnt], want), f0
     # the signal is what went in: 1 kHz / 1.5 kHz sines at 0.5 * 4 dB
-    x = outs["skew"][:176400].astype(np.float64) / 2 ** 23
+    x = outs["seg"][:176400].astype(np.float64) / 2 ** 23
     assert abs(np.abs(x).max() - 0.5 * 10 ** 0.2) < 0.01
 
 

@@ -33,7 +33,7 @@ def test_random_case_equals_oracle(oracle, seed):
     scale, amp, clip = filters.app_params(bits, dither=dither)
     precision = 32 if rng.random() < 0.25 else 64
     fill = int(rng.choice([0x69, 0x96, 0x00]))
-    kernels = ["auto", "direct"] + (["skew"] if ratio == 32 and layout == 0 else [])
+    kernels = ["auto", "direct", "seg"]
     kernel = str(rng.choice(kernels))
     sample0 = int(rng.integers(0, 10_000_000)) if dither else 0
 
@@ -50,7 +50,7 @@ def test_random_case_equals_oracle(oracle, seed):
     else:
         src, stride = to_blocks(window, layout), 0
     g = capi.DsdGpu(filters.build_lut(fir, msb), nch, fir.nstep, lut_precision=precision)
-    g.set_option("kernel", {"auto": capi.KERNEL_AUTO, "direct": capi.KERNEL_DIRECT, "skew": capi.KERNEL_SKEW}[kernel])
+    g.set_option("kernel", {"auto": capi.KERNEL_AUTO, "direct": capi.KERNEL_DIRECT, "seg": capi.KERNEL_SEGMENTED}[kernel])
     g.set_option("source_block_bytes", layout)
     g.set_option("chunk_frames", int(rng.integers(1, 5000)))
     got = np.empty((nframes, nch), dtype=np.int32)

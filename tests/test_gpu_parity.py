@@ -14,19 +14,17 @@ pytestmark = pytest.mark.gpu
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
 RATES = {32: 88200, 16: 176400, 8: 352800}
-KERNELS = {"direct": capi.KERNEL_DIRECT, "skew": capi.KERNEL_SKEW, "ring": capi.KERNEL_RING, "auto": capi.KERNEL_AUTO}
+KERNELS = {"direct": capi.KERNEL_DIRECT, "seg": capi.KERNEL_SEGMENTED, "ring": capi.KERNEL_RING, "auto": capi.KERNEL_AUTO}
 
 
 def make(ratio, msb, nch, kernel="auto", precision=64):
     fir = filters.FILTERS[ratio]
-    if kernel == "skew" and ratio != 32:
-        pytest.skip("the 80-step skew kernel exists for the divide-by-32 filter only")
     g = capi.DsdGpu(filters.build_lut(fir, msb), nch, fir.nstep, lut_precision=precision)
     g.set_option("kernel", KERNELS[kernel])
     return fir, g
 
 
-@pytest.mark.parametrize("kernel", ["direct", "skew", "ring"])
+@pytest.mark.parametrize("kernel", ["direct", "seg", "ring"])
 @pytest.mark.parametrize("msb", [0, 1])
 @pytest.mark.parametrize("ratio", [32, 16, 8])
 def test_app_parity_all_depths(oracle, ratio, msb, kernel):
@@ -43,7 +41,7 @@ def test_app_parity_all_depths(oracle, ratio, msb, kernel):
     g.close()
 
 
-@pytest.mark.parametrize("kernel", ["direct", "skew", "ring"])
+@pytest.mark.parametrize("kernel", ["direct", "seg", "ring"])
 @pytest.mark.parametrize("ratio", [32, 16, 8])
 def test_fp64_sums_bit_exact_incl_idle_prefill(oracle, ratio, kernel):
     fir, g = make(ratio, 1, 3, kernel)
@@ -86,7 +84,7 @@ def test_golden_sigma_delta_both_packings():
         g.close()
 
 
-@pytest.mark.parametrize("kernel", ["direct", "skew", "ring"])
+@pytest.mark.parametrize("kernel", ["direct", "seg", "ring"])
 def test_ragged_windows_and_tiny_calls(oracle, kernel):
     fir, g = make(32, 0, 1, kernel)
     data = seeded_bytes(1, 30000, 3)
@@ -212,9 +210,8 @@ def test_option_errors():
     odd.set_option("kernel", capi.KERNEL_AUTO)                # ... the direct kernel takes any geometry
     assert odd.decimate_host(seeded_bytes(1, 1000, 1), 30, 10, 1.0).shape == (10, 1)
     odd.close()
-    g.set_option("kernel", capi.KERNEL_SKEW)
-    with pytest.raises(capi.DsdGpuError, match="skew kernel needs"):
-        g.decimate_host(seeded_bytes(2, 1000, 1), 30, 10, 1.0)
+    with pytest.raises(capi.DsdGpuError, match="bad kernel"):
+        g.set_option("kernel", 2)                             # the retired skew kernel's number
     g.close()
 
 
@@ -305,14 +302,14 @@ def test_32bit_tables_same_bits_from_every_kernel_and_sharding(oracle):
     n = filters.app_frames(nbytes * 8, fir)
     scale, amp, clip = filters.app_params(24, dither=True)
     outs = {}
-    for name in ("ring", "skew", "direct"):
+    for name in ("ring", "seg", "direct"):
         g = capi.DsdGpu(filters.build_lut(fir, 1), 2, fir.nstep, lut_precision=32)
         g.set_option("kernel", KERNELS[name])
         outs[name] = g.decimate_host(data, fir.nlut, n, scale, amp, clip)
         if name == "ring":
             f64 = g.decimate_host(data, fir.nlut, n, 1.0, out_kind=capi.OUT_FLOAT64)
         g.close()
-    assert np.array_equal(outs["ring"], outs["direct"]) and np.array_equal(outs["skew"], outs["direct"])
+    assert np.array_equal(outs["ring"], outs["direct"]) and np.array_equal(outs["seg"], outs["direct"])
     job = batch.Job(data, DSD64, 88200, msb_flag=True, bits=24, dither=True, lut_precision=32)
     runner = batch.BatchRunner()
     parts = []
@@ -347,4 +344,26 @@ def test_device_pointers_unaligned_everything(oracle, ratio):
                       out.data_ptr() + 4)
     assert np.array_equal(out[1:1 + n * 3].cpu().numpy().reshape(n, 3), want)
     assert int(out[0]) == 0 and int(out[1 + n * 3]) == 0          # nothing written outside
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nch", [2, 4, 6])
+def test_even_channels_output_base_only_4_byte_aligned(oracle, nch):
+    """Channel pairs are written with 8- / 16-byte stores; a caller's int32 pointer that is only 4-byte aligned (a slice
+    of a tensor) must fall back to scalar stores instead of faulting (a misaligned address is a sticky context error)."""
+    import torch
+    fir, g = make(32, 1, nch, "ring")
+    n_bytes = 20_000
+    data = seeded_bytes(nch, n_bytes, 40 + nch)
+    scale, amp, clip = filters.app_params(24, dither=True)
+    n = filters.app_frames(n_bytes * 8, fir)
+    want = oracle.run_app(data, n_bytes * 8, 1, DSD64, 88200, scale, amp, clip)
+    d_in = torch.from_numpy(data).cuda()
+    for off in (1, 2, 3):                                   # 4, 8 and 12 bytes past a 16-byte boundary
+        out = torch.zeros(n * nch + 8, dtype=torch.int32, device="cuda")
+        g.decimate_device(d_in, n_bytes, 0, n_bytes, 0x69, fir.nlut, n, scale, amp, clip, 0, capi.OUT_INT32,
+                          out.data_ptr() + 4 * off)
+        assert np.array_equal(out[off:off + n * nch].cpu().numpy().reshape(n, nch), want)
+        assert int(out[off - 1]) == 0 and int(out[off + n * nch]) == 0
     g.close()

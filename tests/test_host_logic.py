@@ -130,3 +130,28 @@ def test_read_ahead_of_bulk_sources_is_invisible(host, oracle, ratio):
     # and the plain part of it against the oracle directly
     first = oracle.run_raw(data, L, 1, DSD64, fs, fir.nlut + 1, 1725, sa, amp, clip)
     assert np.array_equal(got[:1725], first)
+
+
+def test_gpu_failure_mid_stream_exits_like_the_reference(tmp_path):
+    """A GPU error after construction must not turn into silence in the FLAC file: main.cpp checks isValid() once,
+    right after construction (main.cpp:232-236).  The drop-in follows the reference's convention for an unrecoverable
+    error inside getSamples (dsd_decimator.cpp:182-186): message on stderr, exit(EXIT_FAILURE)."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np\n"
+        "from dsf2flac_b200 import capi, filters\n"
+        "from tests.oracle_lib import DSD64, seeded_bytes\n"
+        f"host = capi.host_lib({CPU_HOST!r})\n"
+        "data = seeded_bytes(2, 6000, 5)\n"
+        "out = np.zeros((4096, 2), dtype=np.int32)\n"
+        "scale, amp, clip = filters.app_params(24)\n"
+        "n = host.dsdhost_run_app(data.ctypes.data, 2, 6000, 48000, 0x69, 1, DSD64, 88200, scale, amp, clip, 64, 200, out.ctypes.data, 4096)\n"
+        "print('returned', n)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ok = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert ok.returncode == 0 and "returned 1483" in ok.stdout, ok.stderr
+    bad = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True,
+                         env=dict(os.environ, DSDGPU_STANDIN_FAIL_AFTER="3"))
+    assert bad.returncode == 1, (bad.returncode, bad.stdout, bad.stderr)
+    assert "GPU decimation failed" in bad.stderr and "injected failure" in bad.stderr and "returned" not in bad.stdout
