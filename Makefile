@@ -27,10 +27,14 @@ $(PKG)/libdsdhost.so: $(HOSTSRC) $(HOSTHDR) $(PKG)/libdsdgpu.so
 oracle: gpu
 	$(MAKE) -C oracle all
 
-tests: tests/cpp/_build/emu_ring tests/cpp/_build/libdsdhost_cpu.so
+tests: tests/cpp/_build/emu_ring tests/cpp/_build/libdsdhost_cpu.so tests/cpp/_build/libdsdsynth.so
 tests/cpp/_build/emu_ring: tests/cpp/emu_ring.cpp $(PKG)/csrc/ring_core.h
 	mkdir -p tests/cpp/_build
 	$(CXX) -O2 -std=c++17 -I $(PKG)/csrc -o $@ tests/cpp/emu_ring.cpp
+# the synthetic-input generator on its own (bench.py's reference arm must not map the product libraries)
+tests/cpp/_build/libdsdsynth.so: $(PKG)/host/dsd_synth.cpp
+	mkdir -p tests/cpp/_build
+	$(CXX) -O2 -std=c++17 -fPIC -shared -o $@ $(PKG)/host/dsd_synth.cpp
 # the same host sources linked against a CPU stand-in of the C ABI (tests only, never shipped)
 tests/cpp/_build/libdsdhost_cpu.so: $(HOSTSRC) $(HOSTHDR) tests/cpp/standin_dsdgpu.cpp
 	mkdir -p tests/cpp/_build

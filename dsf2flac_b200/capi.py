@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 GPU_LIB = os.path.join(_HERE, "libdsdgpu.so")
 HOST_LIB = os.path.join(_HERE, "libdsdhost.so")
 
-OUT_INT32, OUT_FLOAT64 = 0, 1
+OUT_INT32, OUT_FLOAT64, OUT_PCM24, OUT_PCM16 = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RING, KERNEL_SEGMENTED = 0, 1, 3, 4
 ERR_NODEVICE = 3
 
@@ -194,7 +194,8 @@ class DsdGpu:
         planar = np.ascontiguousarray(planar, dtype=np.uint8)
         assert planar.ndim == 2 and planar.shape[0] == self.nch
         if out is None:
-            out = np.empty((nframes, self.nch), dtype=np.int32 if out_kind == OUT_INT32 else np.float64)
+            out = (np.empty((nframes, self.nch, 3), dtype=np.uint8) if out_kind == OUT_PCM24 else
+                   np.empty((nframes, self.nch), dtype={OUT_INT32: np.int32, OUT_FLOAT64: np.float64, OUT_PCM16: np.int16}[out_kind]))
         self._check(self.lib.dsdgpu_decimate_host(self.h, planar.ctypes.data, planar.shape[1], in_first,
                                                   planar.shape[1], fill, p0, nframes, scale, dither_amp, clip,
                                                   dither_first_sample, out_kind, out.ctypes.data),
@@ -234,6 +235,13 @@ class DsdGpu:
     def dither_fill_device(self, first_sample, count, d_out, stream=None):
         self._check(self.lib.dsdgpu_dither_fill_device(self.h, first_sample, count, _ptr(d_out), stream),
                     "dsdgpu_dither_fill_device")
+
+
+def unpack_pcm24(packed):
+    """uint8 [..., 3] little-endian two's-complement samples (DSDGPU_OUT_PCM24) -> int32 [...]."""
+    p = np.asarray(packed, dtype=np.uint8).astype(np.int32)
+    v = p[..., 0] | (p[..., 1] << 8) | (p[..., 2] << 16)
+    return np.where(v & 0x800000, v - (1 << 24), v).astype(np.int32)
 
 
 class PinnedBuffer:

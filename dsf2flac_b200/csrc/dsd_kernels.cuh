@@ -39,6 +39,7 @@ struct DecimateArgs {
     double unit;             // 32-bit tables: value of one table unit (2^-qbits); 1.0 otherwise
     void* out;
     int out_kind;
+    int pcm_bytes;           // DSDGPU_OUT_PCM24 / _PCM16: 3 / 2 bytes per sample (else 0)
     // multi-pass runs (filters longer than one shared-memory image): this launch adds
     // tables [seg_first, seg_first + seg_n) to the running sum of every sample
     int seg_first, seg_n;
@@ -74,16 +75,26 @@ __device__ __forceinline__ double quantise_tail(double sum, double scale, double
     return v;
 }
 
+// sample m of a packed PCM output: the low `bytes` bytes of the rounded integer, little endian
+__device__ __forceinline__ void store_pcm(unsigned char* out, long long m, int q, int bytes) {
+    unsigned char* p = out + m * bytes;
+    p[0] = (unsigned char)q;
+    p[1] = (unsigned char)(q >> 8);
+    if (bytes == 3) p[2] = (unsigned char)(q >> 16);
+}
+
 __device__ __forceinline__ void store_sample(const DecimateArgs& a, long long frame, int c, double sum) {
     const long long m = frame * a.nch + c;
     const double dith = (a.dither != nullptr) ? a.dither[frame * a.dither_stride + c] : 0.0;
     const double v = quantise_tail(sum, a.scale, a.dither_amp, dith, a.clip);
-    if (a.out_kind == DSDGPU_OUT_INT32) {
-        // C round(): half away from zero (dsd_decimator.cpp:213-214)
-        reinterpret_cast<int32_t*>(a.out)[m] = __double2int_rz(round(v));
-    } else {
+    if (a.out_kind == DSDGPU_OUT_FLOAT64) {
         reinterpret_cast<double*>(a.out)[m] = v;
+        return;
     }
+    // C round(): half away from zero (dsd_decimator.cpp:213-214)
+    const int q = __double2int_rz(round(v));
+    if (a.out_kind == DSDGPU_OUT_INT32) reinterpret_cast<int32_t*>(a.out)[m] = q;
+    else store_pcm(reinterpret_cast<unsigned char*>(a.out), m, q, a.pcm_bytes);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,12 +384,14 @@ struct RingDest {
 // straight-line code -- scale, dither, clip by selects, C round() as trunc + exact remainder test,
 // saturating double->int -- and frame-pair stores.  Called from inside the main steps.
 // OUT: 0 = int32 PCM, 1 = fp64 (scaled, dithered, clipped), 2 = the raw running sum into the planar plane
-// a.seg_raw (first pass of a two-pass filter).  INIT: sums start from the planar plane a.seg_init (second pass).
+// a.seg_raw (first pass of a two-pass filter), 3 = packed PCM of a.pcm_bytes (3 or 2) bytes per sample.
+// INIT: sums start from the planar plane a.seg_init (second pass).
 template <int OUT, bool DITHER, bool INIT>
 struct RingEmitter {
     const DecimateArgs& a;
     RingDest d, nx;              // the frames being finished / the frames the lane starts in the next period
     int h;
+    unsigned out_low_bits4;                // a.out & 3
     bool out_aligned16, out_aligned8;      // of a.out: the 16- and 8-byte stores below need them (a caller's device pointer may be a slice)
     int vi[4];
     double vd[4];
@@ -387,7 +400,8 @@ struct RingEmitter {
     static constexpr bool LATE = DITHER;
 
     __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, const RingDest& nx_, int h_, unsigned out_low_bits)
-        : a(a_), d(d_), nx(nx_), h(h_), out_aligned16((out_low_bits & 15u) == 0), out_aligned8((out_low_bits & 7u) == 0) {}
+        : a(a_), d(d_), nx(nx_), h(h_), out_low_bits4(out_low_bits & 3u), out_aligned16((out_low_bits & 15u) == 0),
+          out_aligned8((out_low_bits & 7u) == 0) {}
 
     // the dither terms of the four frames being finished, issued well ahead of quantise()
     // Pair tiles read them the way the stores go out: a lane loads the 16-byte pairs {D(f, c0), D(f, c0 + 1)}
@@ -469,6 +483,7 @@ struct RingEmitter {
                 if (fb + k < nf) out[(fb + k) * a.nch + d.c] = vd[k];
             return;
         }
+        if (OUT == 3) { store_packed(); return; }
         int32_t* out = reinterpret_cast<int32_t*>(a.out);
         if (d.pair && (a.nch & 1) == 0) {
             // trade halves: lane h=0 ends up with frames fb, fb+1 of both channels, lane h=1 with fb+2, fb+3
@@ -492,6 +507,44 @@ struct RingEmitter {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (fb + k < nf) out[(fb + k) * a.nch + d.c] = vi[k];
+        }
+    }
+
+    // Packed PCM (3 or 2 bytes per sample).  Stereo: after the same trade of halves a lane owns two whole frames =
+    // 12 (8) contiguous bytes, 4-byte aligned because fb is a multiple of 4; a warp instruction covers 768 (512)
+    // contiguous bytes.  Every other shape goes out byte by byte (the output side is 12x looser than the table loads).
+    __device__ __forceinline__ void store_packed() {
+        const long long fb = d.fb, nf = a.nframes;
+        unsigned char* out = reinterpret_cast<unsigned char*>(a.out);
+        const int B = a.pcm_bytes;
+        const bool aligned4 = out_aligned8 || (out_low_bits4 == 0);
+        if (d.pair && (a.nch & 1) == 0) {
+            const int s0 = __shfl_xor_sync(0xffffffffu, h ? vi[0] : vi[2], 16);
+            const int s1 = __shfl_xor_sync(0xffffffffu, h ? vi[1] : vi[3], 16);
+            const long long f = fb + 2 * h;
+            const int2 lo2 = h ? make_int2(s0, vi[2]) : make_int2(vi[0], s0);
+            const int2 hi2 = h ? make_int2(s1, vi[3]) : make_int2(vi[1], s1);
+            if (a.nch == 2 && aligned4 && f + 1 < nf) {
+                if (B == 3) {
+                    const uint32_t q0 = (uint32_t)lo2.x & 0xffffffu, q1 = (uint32_t)lo2.y & 0xffffffu;
+                    const uint32_t q2 = (uint32_t)hi2.x & 0xffffffu, q3 = (uint32_t)hi2.y & 0xffffffu;
+                    uint32_t* p = reinterpret_cast<uint32_t*>(out + f * 6);
+                    p[0] = q0 | (q1 << 24);
+                    p[1] = (q1 >> 8) | (q2 << 16);
+                    p[2] = (q2 >> 16) | (q3 << 8);
+                } else {
+                    uint32_t* p = reinterpret_cast<uint32_t*>(out + f * 4);
+                    p[0] = ((uint32_t)lo2.x & 0xffffu) | ((uint32_t)lo2.y << 16);
+                    p[1] = ((uint32_t)hi2.x & 0xffffu) | ((uint32_t)hi2.y << 16);
+                }
+            } else {
+                if (f < nf) { store_pcm(out, f * a.nch + d.c0, lo2.x, B); store_pcm(out, f * a.nch + d.c0 + 1, lo2.y, B); }
+                if (f + 1 < nf) { store_pcm(out, (f + 1) * a.nch + d.c0, hi2.x, B); store_pcm(out, (f + 1) * a.nch + d.c0 + 1, hi2.y, B); }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (fb + k < nf) store_pcm(out, (fb + k) * a.nch + d.c, vi[k], B);
         }
     }
 };

@@ -197,8 +197,9 @@ int launch_ring_variant(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st)
 
 template <class G, bool INIT = false>
 int launch_ring(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
-    const bool f64 = a.out_kind != DSDGPU_OUT_INT32, dith = a.dither != nullptr;
+    const bool f64 = a.out_kind == DSDGPU_OUT_FLOAT64, dith = a.dither != nullptr;
     if (f64) return dith ? launch_ring_variant<G, 1, true, INIT>(ctx, a, st) : launch_ring_variant<G, 1, false, INIT>(ctx, a, st);
+    if (a.pcm_bytes) return dith ? launch_ring_variant<G, 3, true, INIT>(ctx, a, st) : launch_ring_variant<G, 3, false, INIT>(ctx, a, st);
     return dith ? launch_ring_variant<G, 0, true, INIT>(ctx, a, st) : launch_ring_variant<G, 0, false, INIT>(ctx, a, st);
 }
 
@@ -314,8 +315,21 @@ int check_call(dsdgpu_ctx* ctx, const void* in, int64_t in_count, int64_t nframe
     if (nframes < 0 || in_count < 0) return fail(ctx, DSDGPU_ERR_ARG, "negative size");
     if (nframes > 0 && !out) return fail(ctx, DSDGPU_ERR_ARG, "null output buffer");
     if (in_count > 0 && !in) return fail(ctx, DSDGPU_ERR_ARG, "null input buffer");
-    if (out_kind != DSDGPU_OUT_INT32 && out_kind != DSDGPU_OUT_FLOAT64)
+    if (out_kind != DSDGPU_OUT_INT32 && out_kind != DSDGPU_OUT_FLOAT64 && out_kind != DSDGPU_OUT_PCM24 && out_kind != DSDGPU_OUT_PCM16)
         return fail(ctx, DSDGPU_ERR_ARG, "unknown output kind %d", out_kind);
+    return DSDGPU_OK;
+}
+
+// bytes per output sample; packed PCM only holds what the clip amplitude guarantees to fit
+size_t out_elem_bytes(int out_kind) {
+    return out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : out_kind == DSDGPU_OUT_FLOAT64 ? sizeof(double)
+         : out_kind == DSDGPU_OUT_PCM24 ? 3 : 2;
+}
+int check_packed(dsdgpu_ctx* ctx, int out_kind, double clip) {
+    if (out_kind == DSDGPU_OUT_PCM24 && !(clip > 0.0 && clip <= 8388607.0))
+        return fail(ctx, DSDGPU_ERR_ARG, "DSDGPU_OUT_PCM24 needs 0 < clip <= 2^23-1 (every sample must fit 24 bits)");
+    if (out_kind == DSDGPU_OUT_PCM16 && !(clip > 0.0 && clip <= 32767.0))
+        return fail(ctx, DSDGPU_ERR_ARG, "DSDGPU_OUT_PCM16 needs 0 < clip <= 2^15-1 (every sample must fit 16 bits)");
     return DSDGPU_OK;
 }
 
@@ -352,6 +366,8 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
     a.unit = ctx->lut_unit;
     a.out = d_out; a.out_kind = out_kind;
+    a.pcm_bytes = out_kind == DSDGPU_OUT_PCM24 ? 3 : out_kind == DSDGPU_OUT_PCM16 ? 2 : 0;
+    { int rc = check_packed(ctx, out_kind, clip); if (rc) return rc; }
     a.seg_first = 0; a.seg_n = ctx->nlut; a.seg_init = nullptr; a.seg_raw = nullptr; a.plane_stride = 0;
     if (dither_amp > 0.0) {
         const long long count = (nframes - 1) * a.dither_stride + ctx->nch;
@@ -738,9 +754,11 @@ int dsdgpu_submit(dsdgpu_ctx* ctx, int slot, const uint8_t* in, size_t in_stride
     if (s.busy) return fail(ctx, DSDGPU_ERR_STATE, "slot %d is still in flight", slot);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (nframes == 0) { s.busy = true; return DSDGPU_OK; }
-    const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
+    rc = check_packed(ctx, out_kind, clip);
+    if (rc) return rc;
+    const size_t elem = out_elem_bytes(out_kind);
     const size_t out_bytes = (size_t)nframes * ctx->nch * elem;
-    rc = ensure(ctx, reinterpret_cast<unsigned char**>(&s.d_out), &s.out_cap, out_bytes);
+    rc = ensure(ctx, reinterpret_cast<unsigned char**>(&s.d_out), &s.out_cap, out_bytes + 16);
     if (rc) return rc;
     // bytes this run of frames can touch, clipped to what the caller has
     int64_t lo, hi;
@@ -893,7 +911,7 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
                          void* out) {
     int rc = check_call(ctx, in, in_count, nframes, out_kind, out);
     if (rc) return rc;
-    const size_t elem = out_kind == DSDGPU_OUT_INT32 ? sizeof(int32_t) : sizeof(double);
+    const size_t elem = out_elem_bytes(out_kind);
     const long long chunk = ctx->chunk_frames;
     long long k = 0;
     const int nslots = ctx->pipeline_slots;

@@ -19,6 +19,9 @@
 #include <cstring>
 #include <mutex>
 #include <utility>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 #include "dsdgpu.h"
 
@@ -112,7 +115,7 @@ DsdDecimator::DsdDecimator(DsdSampleReader *r, dsf2flac_uint32 rate)
       gpu(nullptr), lutBits(64), pos(-1), harvested(0), samplesOut(0), bytes(nullptr), bytesStride(0),
       bytesCap(0), bytesFirst(0), bytesCount(0), block(nullptr), blockCap(0), blockKind(0), blockPos(0),
       blockFrames(0), blockSample0(0), blockScale(0), blockDither(0), blockClip(0),
-      readAhead(kDefaultReadAhead), bulk(nullptr), bulkBlock(0), bulkCount(0), bulkStride(0),
+      readAhead(kDefaultReadAhead), packedTransfer(true), bulk(nullptr), bulkBlock(0), bulkCount(0), bulkStride(0),
       ahead(nullptr), aheadCap(0), aheadBusy(false), aheadKind(0), aheadPos(0), aheadFrames(0), aheadSample0(0),
       aheadScale(0), aheadDither(0), aheadClip(0)
 {
@@ -166,7 +169,13 @@ void DsdDecimator::buildTables(int msbFlag)
     }
 }
 
-namespace { const int kAheadSlot = DSDGPU_SLOTS - 1; }   // the synchronous runs cycle through the slots below it
+namespace {
+const int kAheadSlot = DSDGPU_SLOTS - 1;    // the synchronous runs cycle through the slots below it
+size_t outElemBytes(int outKind) {
+    return outKind == DSDGPU_OUT_INT32 ? sizeof(dsf2flac_int32) : outKind == DSDGPU_OUT_FLOAT64 ? sizeof(double)
+         : outKind == DSDGPU_OUT_PCM24 ? 3 : 2;
+}
+}  // namespace
 
 bool DsdDecimator::openGpu(int bits)
 {
@@ -211,8 +220,7 @@ void DsdDecimator::prefetch(int outKind)
     dsf2flac_int64 frames = (lastDataByte + (dsf2flac_int64)nLookupTable - nextPos) / (dsf2flac_int64)nStep + 1;
     if (frames > (dsf2flac_int64)readAhead) frames = readAhead;
     if (frames < 1) return;                               // nothing but idle bytes from there on
-    const size_t elem = outKind == DSDGPU_OUT_INT32 ? sizeof(dsf2flac_int32) : sizeof(double);
-    const size_t need = (size_t)frames * nch * elem;
+    const size_t need = (size_t)frames * nch * outElemBytes(outKind);
     if (need > aheadCap) {
         g_pinned.give(ahead, aheadCap);
         ahead = g_pinned.take(need, aheadCap);
@@ -259,6 +267,8 @@ void DsdDecimator::step() { pos += 1; }
 void DsdDecimator::setExtensionFilters(bool on) { g_extensionFilters = on ? 1 : 0; }
 
 void DsdDecimator::setReadAheadFrames(dsf2flac_uint32 frames) { readAhead = frames ? frames : 1; }
+
+void DsdDecimator::setPackedTransfer(bool on) { packedTransfer = on; }
 
 bool DsdDecimator::setLutPrecision(int bits)
 {
@@ -358,8 +368,7 @@ bool DsdDecimator::refill(dsf2flac_uint32 wantFrames, dsf2flac_float64 scale, ds
         if (!valid) return false;
     }
 
-    const size_t elem = outKind == DSDGPU_OUT_INT32 ? sizeof(dsf2flac_int32) : sizeof(double);
-    const size_t needOut = (size_t)frames * nch * elem;
+    const size_t needOut = (size_t)frames * nch * outElemBytes(outKind);
     if (needOut > blockCap) {
         g_pinned.give(block, blockCap);
         block = g_pinned.take(needOut, blockCap);
@@ -442,6 +451,46 @@ struct CopyInt32 {                // rounded on the GPU already
         std::memcpy(dst, static_cast<const dsf2flac_int32*>(blk) + first, count * sizeof(dsf2flac_int32));
     }
 };
+
+// The block came over PCIe as packed 24-bit / 16-bit samples (include/dsdgpu.h, DSDGPU_OUT_PCM24 / _PCM16): the copy
+// into the caller's FLAC__int32 buffer (main.cpp:173-177) is the widening.  serve() copies every sample once anyway.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("ssse3"))) void widen24_ssse3(dsf2flac_int32* dst, const dsf2flac_uint8* src, size_t count) {
+    // 12 source bytes -> 4 samples: each sample's 3 bytes go to the top of a 32-bit lane, an arithmetic shift by 8
+    // brings them down sign-extended.  Loads are 16 bytes wide, so stop 4 bytes short of the end.
+    const __m128i pick = _mm_setr_epi8(-1, 0, 1, 2, -1, 3, 4, 5, -1, 6, 7, 8, -1, 9, 10, 11);
+    size_t i = 0;
+    for (; i + 4 <= count && 3 * i + 16 <= 3 * count; i += 4) {
+        const __m128i raw = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 3 * i));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm_srai_epi32(_mm_shuffle_epi8(raw, pick), 8));
+    }
+    for (; i < count; ++i) {
+        const dsf2flac_uint8* p = src + 3 * i;
+        dst[i] = (dsf2flac_int32)((dsf2flac_uint32)p[0] << 8 | (dsf2flac_uint32)p[1] << 16 | (dsf2flac_uint32)p[2] << 24) >> 8;
+    }
+}
+#endif
+void widen24(dsf2flac_int32* dst, const dsf2flac_uint8* src, size_t count) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool fast = __builtin_cpu_supports("ssse3");
+    if (fast) { widen24_ssse3(dst, src, count); return; }
+#endif
+    for (size_t i = 0; i < count; ++i) {
+        const dsf2flac_uint8* p = src + 3 * i;
+        dst[i] = (dsf2flac_int32)((dsf2flac_uint32)p[0] << 8 | (dsf2flac_uint32)p[1] << 16 | (dsf2flac_uint32)p[2] << 24) >> 8;
+    }
+}
+struct WidenPcm24 {
+    void operator()(dsf2flac_int32* dst, const void* blk, size_t first, size_t count) const {
+        widen24(dst, static_cast<const dsf2flac_uint8*>(blk) + 3 * first, count);
+    }
+};
+struct WidenPcm16 {
+    void operator()(dsf2flac_int32* dst, const void* blk, size_t first, size_t count) const {
+        const dsf2flac_int16* src = static_cast<const dsf2flac_int16*>(blk) + first;
+        for (size_t i = 0; i < count; ++i) dst[i] = src[i];           // vectorised by the compiler (pmovsxwd / unpack + shift)
+    }
+};
 }  // namespace
 
 template<> void DsdDecimator::getSamples(dsf2flac_int16 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
@@ -450,7 +499,13 @@ template<> void DsdDecimator::getSamples(dsf2flac_int16 *buffer, dsf2flac_uint32
 }
 template<> void DsdDecimator::getSamples(dsf2flac_int32 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
 {
-    serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_INT32, CopyInt32());
+    // main.cpp clips to 2^(bits-1)-1 (:245): the samples then fit 16 / 24 bits and cross PCIe that narrow
+    if (packedTransfer && clipAmplitude > 0 && clipAmplitude <= 32767.0)
+        serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_PCM16, WidenPcm16());
+    else if (packedTransfer && clipAmplitude > 0 && clipAmplitude <= 8388607.0)
+        serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_PCM24, WidenPcm24());
+    else
+        serve(buffer, bufferLen, scale, tpdfDitherPeakAmplitude, clipAmplitude, DSDGPU_OUT_INT32, CopyInt32());
 }
 template<> void DsdDecimator::getSamples(dsf2flac_int64 *buffer, dsf2flac_uint32 bufferLen, dsf2flac_float64 scale, dsf2flac_float64 tpdfDitherPeakAmplitude, dsf2flac_float64 clipAmplitude)
 {

@@ -46,7 +46,13 @@ enum {
     DSDGPU_ERR_STATE = 4     /* wait without submit, slot busy, ... */
 };
 
-enum { DSDGPU_OUT_INT32 = 0, DSDGPU_OUT_FLOAT64 = 1 };
+/* Output layouts.  INT32 is what the reference hands libFLAC (FLAC__int32 per sample whatever the bit depth,
+ * main.cpp:173-177); FLOAT64 is the value before rounding (getSamples<float64>, dsd_decimator.cpp:169-172).
+ * PCM24 / PCM16 (the output side) carry the SAME rounded integers as little-endian two's-complement
+ * samples of 3 / 2 bytes, interleaved [nframes][nch][3|2]: 25 % / 50 % fewer bytes over PCIe for the 20/24-bit and
+ * 16-bit conversions main.cpp runs (clip = 2^(bits-1)-1, main.cpp:245).  They need clip > 0 and clip <= 2^23-1 /
+ * 2^15-1, so that every sample fits; the drop-in class widens them back to FLAC__int32 as it hands blocks out. */
+enum { DSDGPU_OUT_INT32 = 0, DSDGPU_OUT_FLOAT64 = 1, DSDGPU_OUT_PCM24 = 2, DSDGPU_OUT_PCM16 = 3 };
 
 /* Independent upload/kernel/download pipelines ("slots") a context owns. */
 #define DSDGPU_SLOTS 4
@@ -129,7 +135,8 @@ int dsdgpu_host_unregister(void* p);
  *   scale, dither_amp, clip                     as main.cpp:239-245 computes them
  *   dither_first_sample                         m of the first output sample (frame-major)
  *   out_kind, d_out                             DSDGPU_OUT_INT32 -> int32[nframes][nch],
- *                                               DSDGPU_OUT_FLOAT64 -> double[nframes][nch]
+ *                                               DSDGPU_OUT_FLOAT64 -> double[nframes][nch],
+ *                                               DSDGPU_OUT_PCM24 / _PCM16 -> uint8[nframes][nch][3] / int16[nframes][nch]
  */
 int dsdgpu_decimate_device(dsdgpu_ctx* ctx, const uint8_t* d_in, size_t in_stride,
                            int64_t in_first, int64_t in_count, uint8_t fill, int64_t p0,

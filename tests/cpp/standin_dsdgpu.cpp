@@ -101,8 +101,12 @@ int dsdgpu_decimate_host(dsdgpu_ctx* ctx, const uint8_t* in, size_t in_stride, i
             sum = sum * scale;
             if (dither_amp > 0) sum = sum + dith[(size_t)(i * stride + c)] * dither_amp;
             if (clip > 0) { if (sum > clip) sum = clip; else if (sum < -clip) sum = -clip; }
-            if (out_kind == DSDGPU_OUT_INT32) static_cast<int32_t*>(out)[i * ctx->nch + c] = (int32_t)round(sum);
-            else static_cast<double*>(out)[i * ctx->nch + c] = sum;
+            const int64_t m = i * ctx->nch + c;
+            if (out_kind == DSDGPU_OUT_FLOAT64) { static_cast<double*>(out)[m] = sum; continue; }
+            const int32_t q = (int32_t)round(sum);
+            if (out_kind == DSDGPU_OUT_INT32) static_cast<int32_t*>(out)[m] = q;
+            else if (out_kind == DSDGPU_OUT_PCM16) static_cast<int16_t*>(out)[m] = (int16_t)q;
+            else { uint8_t* p = static_cast<uint8_t*>(out) + 3 * m; p[0] = (uint8_t)q; p[1] = (uint8_t)(q >> 8); p[2] = (uint8_t)(q >> 16); }
         }
     ctx->launches += 1;
     return DSDGPU_OK;

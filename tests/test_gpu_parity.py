@@ -367,3 +367,41 @@ def test_even_channels_output_base_only_4_byte_aligned(oracle, nch):
         assert np.array_equal(out[off:off + n * nch].cpu().numpy().reshape(n, nch), want)
         assert int(out[off - 1]) == 0 and int(out[off + n * nch]) == 0
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["ring", "seg", "direct"])
+@pytest.mark.parametrize("nch", [1, 2, 3, 6])
+def test_packed_pcm_outputs_carry_the_same_integers(oracle, kernel, nch):
+    """DSDGPU_OUT_PCM24 / _PCM16 are the int32 samples narrowed to 3 / 2 little-endian bytes (main.cpp clips to
+    2^(bits-1)-1, :245, so nothing is lost); host path (chunked) and device path (any output alignment)."""
+    import torch
+    for ratio in (32, 16, 8):
+        fir, g = make(ratio, 1, nch, kernel)
+        n_bytes = 30_011
+        data = seeded_bytes(nch, n_bytes, 900 + ratio + nch)
+        n = filters.app_frames(n_bytes * 8, fir)
+        g.set_option("chunk_frames", 1777)
+        for bits, kind in ((24, capi.OUT_PCM24), (20, capi.OUT_PCM24), (16, capi.OUT_PCM16)):
+            scale, amp, clip = filters.app_params(bits, dither=True)
+            want = oracle.run_app(data, n_bytes * 8, 1, DSD64, RATES[ratio], scale, amp, clip)
+            got = g.decimate_host(data, fir.nlut, n, scale, amp, clip, out_kind=kind)
+            got = capi.unpack_pcm24(got) if kind == capi.OUT_PCM24 else got.astype(np.int32)
+            assert np.array_equal(got, want), (ratio, bits)
+            d_in = torch.from_numpy(data).cuda()
+            elem = 3 if kind == capi.OUT_PCM24 else 2
+            for off in (0, 1, 2, 4):
+                raw = torch.full((n * nch * elem + 32,), 0x5A, dtype=torch.uint8, device="cuda")
+                g.decimate_device(d_in, n_bytes, 0, n_bytes, 0x69, fir.nlut, n, scale, amp, clip, 0, kind, raw.data_ptr() + off)
+                host = raw.cpu().numpy()
+                body = host[off:off + n * nch * elem]
+                got = capi.unpack_pcm24(body.reshape(n, nch, 3)) if elem == 3 else body.view(np.int16).reshape(n, nch).astype(np.int32) if off % 2 == 0 \
+                    else np.frombuffer(body.tobytes(), dtype=np.int16).reshape(n, nch).astype(np.int32)
+                assert np.array_equal(got, want), (ratio, bits, off)
+                assert (host[:off] == 0x5A).all() and (host[off + n * nch * elem:] == 0x5A).all()     # nothing written outside
+        # the packed kinds refuse a clip that does not guarantee the range
+        with pytest.raises(capi.DsdGpuError, match="needs 0 < clip"):
+            g.decimate_host(data, fir.nlut, 16, 1.0, 0.0, 0.0, out_kind=capi.OUT_PCM24)
+        with pytest.raises(capi.DsdGpuError, match="needs 0 < clip"):
+            g.decimate_host(data, fir.nlut, 16, 1.0, 0.0, 8388607.0, out_kind=capi.OUT_PCM16)
+        g.close()
