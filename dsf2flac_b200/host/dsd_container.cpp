@@ -15,6 +15,10 @@
 
 #include <cstdio>
 #include <cstring>
+#include <sys/types.h>
+
+#include "dsdgpu.h"
+#include "pinned_pool.h"
 
 namespace {
 
@@ -31,36 +35,45 @@ bool fail(DsdContainer& c, const std::string& why) {
     return false;
 }
 
+// The file, read where the parsers ask: a few header-sized pieces, then the sample bytes in one go.
 struct File {
-    std::vector<uint8_t> bytes;
-    bool load(const char* path) {
-        FILE* f = std::fopen(path, "rb");
+    FILE* f = nullptr;
+    uint64_t size = 0;
+    ~File() { if (f) std::fclose(f); }
+    bool open(const char* path) {
+        f = std::fopen(path, "rb");
         if (!f) return false;
-        std::fseek(f, 0, SEEK_END);
-        const long n = std::ftell(f);
-        std::fseek(f, 0, SEEK_SET);
-        bytes.resize(n > 0 ? (size_t)n : 0);
-        const size_t got = bytes.empty() ? 0 : std::fread(bytes.data(), 1, bytes.size(), f);
-        std::fclose(f);
-        return got == bytes.size();
+        if (fseeko(f, 0, SEEK_END) != 0) return false;
+        const off_t n = ftello(f);
+        size = n > 0 ? (uint64_t)n : 0;
+        return true;
     }
-    bool has(uint64_t off, uint64_t n) const { return off <= bytes.size() && n <= bytes.size() - off; }
+    bool has(uint64_t off, uint64_t n) const { return off <= size && n <= size - off; }
+    // n bytes at `off` (n <= 64: a chunk header and its first fields)
+    bool peek(uint64_t off, size_t n, uint8_t* dst) const {
+        if (!has(off, n)) return false;
+        return fseeko(f, (off_t)off, SEEK_SET) == 0 && std::fread(dst, 1, n, f) == n;
+    }
+    bool read(uint64_t off, size_t n, uint8_t* dst) const {
+        if (n == 0) return true;
+        return has(off, n) && fseeko(f, (off_t)off, SEEK_SET) == 0 && std::fread(dst, 1, n, f) == n;
+    }
 };
 
 bool load_dsf(const File& f, DsdContainer& c) {
-    const uint8_t* b = f.bytes.data();
+    uint8_t h[64];
     uint64_t at = 0;
-    if (!f.has(at, 28) || !is(b + at, "DSD ")) return fail(c, "dsfFileReader::readHeaders:DSD ident error");
-    at += le64(b + at + 4);
-    if (!f.has(at, 52) || !is(b + at, "fmt ")) return fail(c, "dsfFileReader::readHeaders:file ident error");
-    const uint64_t fmtSz = le64(b + at + 4);
-    c.channels = le32(b + at + 24);
-    c.samplingFreq = le32(b + at + 28);
-    const uint32_t bits = le32(b + at + 32);
-    c.lengthSamples = (int64_t)le64(b + at + 36);
-    const uint32_t block = le32(b + at + 44);
+    if (!f.peek(at, 28, h) || !is(h, "DSD ")) return fail(c, "dsfFileReader::readHeaders:DSD ident error");
+    at += le64(h + 4);
+    if (!f.peek(at, 52, h) || !is(h, "fmt ")) return fail(c, "dsfFileReader::readHeaders:file ident error");
+    const uint64_t fmtSz = le64(h + 4);
+    c.channels = le32(h + 24);
+    c.samplingFreq = le32(h + 28);
+    const uint32_t bits = le32(h + 32);
+    c.lengthSamples = (int64_t)le64(h + 36);
+    const uint32_t block = le32(h + 44);
     at += fmtSz;
-    if (!f.has(at, 12) || !is(b + at, "data")) return fail(c, "dsfFileReader::readHeaders:file ident error");
+    if (!f.peek(at, 12, h) || !is(h, "data")) return fail(c, "dsfFileReader::readHeaders:file ident error");
     c.dataOffset = (int64_t)at + 12;
     // header fields of an untrusted file: a sample count that is negative as int64, or so large that rounding it up
     // to bytes would overflow, would otherwise turn into a negative / wrapped payload size below
@@ -78,19 +91,22 @@ bool load_dsf(const File& f, DsdContainer& c) {
     // one byte is delivered, then idle.
     const int64_t B = block, nch = c.channels;
     const int64_t want = (c.lengthSamples + 7) / 8 + 1;
-    const int64_t fileData = (int64_t)f.bytes.size() - c.dataOffset;
+    const int64_t fileData = (int64_t)f.size - c.dataOffset;
     const int64_t fullBlocks = fileData > 0 ? fileData / (nch * B) : 0;
     const int64_t needBlocks = (want + B - 1) / B;
     const bool synth = needBlocks > fullBlocks;
     const int64_t haveBlocks = synth ? fullBlocks + 1 : needBlocks;
-    c.payload.assign((size_t)(haveBlocks * nch * B), 0);
+    if (!c.payload.allocate((size_t)(haveBlocks * nch * B))) return fail(c, "out of (page-locked) memory for the sample data");
     const int64_t copyBlocks = synth ? fullBlocks : needBlocks;
-    if (copyBlocks > 0) std::memcpy(c.payload.data(), b + c.dataOffset, (size_t)(copyBlocks * nch * B));
+    if (copyBlocks > 0 && !f.read((uint64_t)c.dataOffset, (size_t)(copyBlocks * nch * B), c.payload.data()))
+        return fail(c, "dsfFileReader::readNextBlock:File read error");
     if (synth) {
         uint8_t* last = c.payload.data() + fullBlocks * nch * B;
         if (fullBlocks > 0) std::memcpy(last, last - nch * B, (size_t)(nch * B));       // stale buffers
+        else std::memset(last, 0, (size_t)(nch * B));                                    // the reader's buffers start out zeroed
         const int64_t rest = fileData > 0 ? fileData - fullBlocks * nch * B : 0;        // short read fills from channel 0 on
-        if (rest > 0) std::memcpy(last, b + c.dataOffset + fullBlocks * nch * B, (size_t)rest);
+        if (rest > 0 && !f.read((uint64_t)(c.dataOffset + fullBlocks * nch * B), (size_t)rest, last))
+            return fail(c, "dsfFileReader::readNextBlock:File read error");
         c.deliveredBytes = want < fullBlocks * B + 1 ? want : fullBlocks * B + 1;
     } else {
         c.deliveredBytes = want;
@@ -100,51 +116,53 @@ bool load_dsf(const File& f, DsdContainer& c) {
 }
 
 bool load_dsdiff(const File& f, DsdContainer& c) {
-    const uint8_t* b = f.bytes.data();
+    uint8_t h[32];
     // top level: the first FRM8 chunk (dsdiff_file_reader.cpp:288-312)
     uint64_t at = 0, frmSz = 0;
     for (;;) {
-        if (!f.has(at, 12)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
-        uint64_t sz = be64(b + at + 4);
+        if (!f.peek(at, 12, h)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
+        uint64_t sz = be64(h + 4);
         if (sz > (uint64_t)1 << 62) return fail(c, "dsdiffFileReader::readChunkHeader:implausible chunk size");   // size + 13 must not wrap (a chunk of 0 bytes would never advance)
         sz += (sz & 1) ? 13 : 12;
-        if (is(b + at, "FRM8")) { frmSz = sz; break; }
+        if (is(h, "FRM8")) { frmSz = sz; break; }
         at += sz;
     }
     const uint64_t frmStart = at;
-    if (!f.has(at, 16) || !is(b + at + 12, "DSD ")) return fail(c, "dsdiffFileReader::readChunk_FRM8:chunk ident error");
+    if (!f.peek(at, 16, h) || !is(h + 12, "DSD ")) return fail(c, "dsdiffFileReader::readChunk_FRM8:chunk ident error");
     bool fver = false, prop = false, dsd = false, dst = false;
     bool fs = false, chnl = false, cmpr = false;
     char compression[5] = "    ";
     uint64_t dataChunkLen = 0;
     for (uint64_t sub = at + 16; sub < frmStart + frmSz;) {
-        if (!f.has(sub, 12)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
-        uint64_t sz = be64(b + sub + 4);
+        if (!f.peek(sub, 12, h)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
+        uint64_t sz = be64(h + 4);
         if (sz > (uint64_t)1 << 62) return fail(c, "dsdiffFileReader::readChunkHeader:implausible chunk size");
         sz += (sz & 1) ? 13 : 12;
-        if (!fver && is(b + sub, "FVER")) {
+        if (!fver && is(h, "FVER")) {
             fver = f.has(sub + 12, 4);
-        } else if (!prop && is(b + sub, "PROP")) {
-            if (!f.has(sub + 12, 4) || !is(b + sub + 12, "SND ")) return fail(c, "dsdiffFileReader::readChunk_PROP:PROP chunk format error");
+        } else if (!prop && is(h, "PROP")) {
+            uint8_t q[16];
+            if (!f.peek(sub + 12, 4, q) || !is(q, "SND ")) return fail(c, "dsdiffFileReader::readChunk_PROP:PROP chunk format error");
             for (uint64_t p = sub + 16; p < sub + sz;) {
-                if (!f.has(p, 12)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
-                uint64_t psz = be64(b + p + 4);
+                if (!f.peek(p, 12, q)) return fail(c, "dsdiffFileReader::readChunkHeader:File read error");
+                uint64_t psz = be64(q + 4);
                 if (psz > (uint64_t)1 << 62) return fail(c, "dsdiffFileReader::readChunkHeader:implausible chunk size");
                 psz += (psz & 1) ? 13 : 12;
-                if (!fs && is(b + p, "FS  ") && f.has(p + 12, 4)) { c.samplingFreq = be32(b + p + 12); fs = true; }
-                else if (!chnl && is(b + p, "CHNL") && f.has(p + 12, 2)) { c.channels = be16(b + p + 12); chnl = true; }
-                else if (!cmpr && is(b + p, "CMPR") && f.has(p + 12, 4)) { std::memcpy(compression, b + p + 12, 4); cmpr = true; }
+                uint8_t v[4];
+                if (!fs && is(q, "FS  ") && f.peek(p + 12, 4, v)) { c.samplingFreq = be32(v); fs = true; }
+                else if (!chnl && is(q, "CHNL") && f.peek(p + 12, 2, v)) { c.channels = be16(v); chnl = true; }
+                else if (!cmpr && is(q, "CMPR") && f.peek(p + 12, 4, v)) { std::memcpy(compression, v, 4); cmpr = true; }
                 p += psz;
             }
             if (!fs) return fail(c, "dsdiffFileReader::readChunk_PROP: no valid FS chunk");
             if (!chnl) return fail(c, "dsdiffFileReader::readChunk_PROP: no valid CHNL chunk");
             if (!cmpr) return fail(c, "dsdiffFileReader::readChunk_PROP: no valid CMPR chunk");
             prop = true;
-        } else if (!dsd && !dst && is(b + sub, "DSD ")) {
+        } else if (!dsd && !dst && is(h, "DSD ")) {
             c.dataOffset = (int64_t)sub + 12;
             dataChunkLen = sz;
             dsd = true;
-        } else if (!dsd && !dst && is(b + sub, "DST ")) {
+        } else if (!dsd && !dst && is(h, "DST ")) {
             dst = true;
         }
         sub += sz;
@@ -170,7 +188,7 @@ bool load_dsdiff(const File& f, DsdContainer& c) {
     // channel MORE than the chunk holds once it reaches the last buffer.  If the file goes on (a
     // chunk follows), those bytes are that chunk's; if the file ends there, the read comes back
     // short, eofbit sticks, and only the byte of that very step is still delivered.
-    const int64_t total = (int64_t)f.bytes.size() - c.dataOffset;                      // bytes from the first sample to EOF
+    const int64_t total = (int64_t)f.size - c.dataOffset;                              // bytes from the first sample to EOF
     int64_t delivered = N + 1;
     const int64_t first = (N < 1024 ? N : 1024) * nch;                                  // rewind(): position 0, nothing "behind"
     if (first > total) {
@@ -182,21 +200,41 @@ bool load_dsdiff(const File& f, DsdContainer& c) {
         }
     }
     if (delivered > total / nch) delivered = total / nch;
+    if (delivered < 0) delivered = 0;
     c.deliveredBytes = delivered;
-    c.payload.assign(b + c.dataOffset, b + c.dataOffset + (size_t)(delivered * nch));
+    if (!c.payload.allocate((size_t)(delivered * nch))) return fail(c, "out of (page-locked) memory for the sample data");
+    if (!f.read((uint64_t)c.dataOffset, (size_t)(delivered * nch), c.payload.data()))
+        return fail(c, "dsdiffFileReader::readNextBlock:File read error");
     c.valid = true;
     return true;
 }
 
 }  // namespace
 
+bool DsdContainer::Payload::allocate(size_t bytes) {
+    release();
+    if (bytes == 0) return true;
+    ptr_ = static_cast<uint8_t*>(pinnedPool().take(bytes, cap_));
+    if (!ptr_) { cap_ = 0; return false; }
+    size_ = bytes;
+    return true;
+}
+
+void DsdContainer::Payload::release() {
+    if (ptr_) pinnedPool().give(ptr_, cap_);
+    ptr_ = nullptr;
+    size_ = cap_ = 0;
+}
+
 bool dsd_container_load(const char* path, int kind_hint, DsdContainer& c) {
     c = DsdContainer();
     File f;
-    if (!f.load(path)) return fail(c, "could not open file");
-    if (f.bytes.size() < 12) return fail(c, "file too short");
+    if (!f.open(path)) return fail(c, "could not open file");
+    if (f.size < 12) return fail(c, "file too short");
     int kind = kind_hint;
-    if (kind == 0) kind = is(f.bytes.data(), "DSD ") ? 1 : is(f.bytes.data(), "FRM8") ? 2 : 0;
+    uint8_t magic[4];
+    if (!f.peek(0, 4, magic)) return fail(c, "file too short");
+    if (kind == 0) kind = is(magic, "DSD ") ? 1 : is(magic, "FRM8") ? 2 : 0;
     if (kind == 1) { c.kind = DsdContainer::DSF; return load_dsf(f, c); }
     if (kind == 2) { c.kind = DsdContainer::DSDIFF; return load_dsdiff(f, c); }
     return fail(c, "not a DSF or DSDIFF file");

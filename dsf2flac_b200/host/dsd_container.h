@@ -33,8 +33,30 @@ struct DsdContainer {
                                       // it turns to idle bytes (the operator's in_count)
     // the sample bytes in their file layout, ready for dsdgpu_decimate_host: payload.size() >=
     // what deliveredBytes needs; for DSF it may end with one block the file does not contain (the
-    // reference's stale-buffer read past the last block, reproduced)
-    std::vector<uint8_t> payload;
+    // reference's stale-buffer read past the last block, reproduced).  Read from the file straight into
+    // page-locked memory (dsdgpu_host_alloc): one copy between the page cache and the upload, no staging vector.
+    struct Payload {
+        Payload() = default;
+        Payload(const Payload&) = delete;
+        Payload& operator=(const Payload&) = delete;
+        Payload(Payload&& o) noexcept : ptr_(o.ptr_), size_(o.size_), cap_(o.cap_) { o.ptr_ = nullptr; o.size_ = o.cap_ = 0; }
+        Payload& operator=(Payload&& o) noexcept { release(); ptr_ = o.ptr_; size_ = o.size_; cap_ = o.cap_; o.ptr_ = nullptr; o.size_ = o.cap_ = 0; return *this; }
+        ~Payload() { release(); }
+        bool allocate(size_t bytes);          // page-locked (recycled through pinned_pool.h), NOT cleared; false if it fails
+        void release();
+        uint8_t* data() { return ptr_; }
+        const uint8_t* data() const { return ptr_; }
+        size_t size() const { return size_; }
+        bool empty() const { return size_ == 0; }
+        uint8_t operator[](size_t i) const { return ptr_[i]; }
+    private:
+        uint8_t* ptr_ = nullptr;
+        size_t size_ = 0, cap_ = 0;
+    } payload;
+
+    DsdContainer() = default;
+    DsdContainer(DsdContainer&&) = default;
+    DsdContainer& operator=(DsdContainer&&) = default;
 };
 
 // Parses `path` (DSF if it starts with "DSD ", DSDIFF if it starts with "FRM8") and loads the sample

@@ -24,6 +24,7 @@
 #endif
 
 #include "dsdgpu.h"
+#include "pinned_pool.h"
 
 namespace {
 
@@ -74,45 +75,61 @@ inline double tapValue(const FirSpec* f, int i) {
 
 const dsf2flac_uint32 kDefaultReadAhead = 1u << 20;
 
-// Page-locking memory costs about 0.45 ms per MB (measured: 3.5 ms for the 8 MB PCM block of a stereo stream),
-// more than the GPU needs for a minute of DSD128.  A process that converts several streams (tracks of one
-// file, a batch) therefore recycles the staging blocks of finished decimators instead of unpinning them.
-struct PinnedPool {
-    static const int kSlots = 6;
+PinnedPool& g_pinned = pinnedPool();
+
+// Creating a context costs about 3 ms (streams, table images, dither constants, their uploads) -- more than the GPU
+// needs for a minute of DSD128.  A process that converts several streams (tracks of one file, a batch of files)
+// gets the context of a finished decimator back when geometry, precision and tables are the same.
+struct ContextPool {
+    static const int kSlots = 4;
+    struct Entry { dsdgpu_ctx* ctx = nullptr; int device = 0, nch = 0, nlut = 0, nstep = 0, bits = 0; std::vector<double> tables; };
     std::mutex lock;
-    void* ptr[kSlots] = {nullptr};
-    size_t cap[kSlots] = {0};
-    void* take(size_t need, size_t& got) {
+    Entry slot[kSlots];
+    dsdgpu_ctx* take(int device, int nch, int nlut, int nstep, int bits, const std::vector<double>& tables) {
+        std::lock_guard<std::mutex> g(lock);
+        for (Entry& e : slot)
+            if (e.ctx && e.device == device && e.nch == nch && e.nlut == nlut && e.nstep == nstep && e.bits == bits &&
+                e.tables.size() == tables.size() && std::memcmp(e.tables.data(), tables.data(), tables.size() * sizeof(double)) == 0) {
+                dsdgpu_ctx* c = e.ctx;
+                e.ctx = nullptr;
+                return c;
+            }
+        return nullptr;
+    }
+    void give(dsdgpu_ctx* ctx, int device, int nch, int nlut, int nstep, int bits, const std::vector<double>& tables) {
+        if (!ctx) return;
+        dsdgpu_ctx* evicted = ctx;
         {
             std::lock_guard<std::mutex> g(lock);
-            int best = -1;
-            for (int i = 0; i < kSlots; ++i)
-                if (ptr[i] && cap[i] >= need && cap[i] <= 2 * need + (1u << 20) && (best < 0 || cap[i] < cap[best])) best = i;
-            if (best >= 0) { void* p = ptr[best]; got = cap[best]; ptr[best] = nullptr; cap[best] = 0; return p; }
+            for (Entry& e : slot)
+                if (!e.ctx) {
+                    e.ctx = ctx; e.device = device; e.nch = nch; e.nlut = nlut; e.nstep = nstep; e.bits = bits; e.tables = tables;
+                    evicted = nullptr;
+                    break;
+                }
+            if (evicted) {                                   // full: the oldest entry makes room
+                evicted = slot[0].ctx;
+                for (int i = 0; i + 1 < kSlots; ++i) slot[i] = std::move(slot[i + 1]);
+                Entry& e = slot[kSlots - 1];
+                e.ctx = ctx; e.device = device; e.nch = nch; e.nlut = nlut; e.nstep = nstep; e.bits = bits; e.tables = tables;
+            }
         }
-        void* p = dsdgpu_host_alloc(need);
-        got = p ? need : 0;
-        return p;
+        if (evicted) dsdgpu_destroy(evicted);
     }
-    void give(void* p, size_t n) {
-        if (!p) return;
-        {
-            std::lock_guard<std::mutex> g(lock);
-            for (int i = 0; i < kSlots; ++i)
-                if (!ptr[i]) { ptr[i] = p; cap[i] = n; return; }
-        }
-        dsdgpu_host_free(p);
-    }
-    // no destructor: at static-destruction time the CUDA runtime may already be gone; the process's pinned
-    // pages go back to the system with it
+    // no destructor, like PinnedPool: the CUDA runtime may be gone at static-destruction time
 };
-PinnedPool g_pinned;
+ContextPool g_contexts;
+
+int deviceFromEnv() {
+    const char* env = std::getenv("DSDGPU_DEVICE");
+    return env ? std::atoi(env) : 0;
+}
 
 }  // namespace
 
 DsdDecimator::DsdDecimator(DsdSampleReader *r, dsf2flac_uint32 rate)
     : reader(r), outputSampleRate(rate), nLookupTable(0), tzero(0), ratio(0), nStep(0), valid(true),
-      gpu(nullptr), lutBits(64), pos(-1), harvested(0), samplesOut(0), bytes(nullptr), bytesStride(0),
+      gpu(nullptr), gpuDevice(0), lutBits(64), pos(-1), harvested(0), samplesOut(0), bytes(nullptr), bytesStride(0),
       bytesCap(0), bytesFirst(0), bytesCount(0), block(nullptr), blockCap(0), blockKind(0), blockPos(0),
       blockFrames(0), blockSample0(0), blockScale(0), blockDither(0), blockClip(0),
       readAhead(kDefaultReadAhead), packedTransfer(true), bulk(nullptr), bulkBlock(0), bulkCount(0), bulkStride(0),
@@ -142,7 +159,7 @@ DsdDecimator::DsdDecimator(DsdSampleReader *r, dsf2flac_uint32 rate)
 DsdDecimator::~DsdDecimator()
 {
     dropAhead();
-    if (gpu) dsdgpu_destroy(gpu);
+    releaseGpu();
     if (bytes) dsdgpu_host_free(bytes);
     g_pinned.give(block, blockCap);
     g_pinned.give(ahead, aheadCap);
@@ -180,15 +197,21 @@ size_t outElemBytes(int outKind) {
 bool DsdDecimator::openGpu(int bits)
 {
     dropAhead();
-    if (gpu) { dsdgpu_destroy(gpu); gpu = nullptr; }
-    int device = 0;
-    if (const char* env = std::getenv("DSDGPU_DEVICE")) device = std::atoi(env);
-    const int rc = dsdgpu_create(&gpu, device, (int)reader->getNumChannels(), (int)nLookupTable, (int)nStep,
-                                 tables.data(), bits);
-    if (rc != DSDGPU_OK) {
-        fail(std::string("DsdDecimator: GPU path unavailable: ") + dsdgpu_last_error(nullptr));
-        gpu = nullptr;
-        return false;
+    releaseGpu();
+    gpuDevice = deviceFromEnv();
+    gpu = g_contexts.take(gpuDevice, (int)reader->getNumChannels(), (int)nLookupTable, (int)nStep, bits, tables);
+    if (gpu) {
+        // a recycled context: back to the defaults this class does not set itself
+        dsdgpu_set_option(gpu, "source_block_bytes", 0);
+        dsdgpu_set_option(gpu, "dither_stride", 0);
+    } else {
+        const int rc = dsdgpu_create(&gpu, gpuDevice, (int)reader->getNumChannels(), (int)nLookupTable, (int)nStep,
+                                     tables.data(), bits);
+        if (rc != DSDGPU_OK) {
+            fail(std::string("DsdDecimator: GPU path unavailable: ") + dsdgpu_last_error(nullptr));
+            gpu = nullptr;
+            return false;
+        }
     }
     dsdgpu_set_option(gpu, "slots", DSDGPU_SLOTS - 1);
     // a bulk source set before this (re)creation keeps its layout on the new context
@@ -201,6 +224,14 @@ bool DsdDecimator::openGpu(int bits)
     lutBits = bits;
     blockFrames = 0;
     return true;
+}
+
+// The context goes back to the pool (nothing of this decimator is in flight on it any more).
+void DsdDecimator::releaseGpu()
+{
+    if (!gpu) return;
+    g_contexts.give(gpu, gpuDevice, (int)reader->getNumChannels(), (int)nLookupTable, (int)nStep, lutBits, tables);
+    gpu = nullptr;
 }
 
 // A block in flight is waited for (its buffers must not be freed or reused under it) and forgotten.

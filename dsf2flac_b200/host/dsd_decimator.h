@@ -73,6 +73,7 @@ public:
 private:
     void buildTables(int msbFlag);
     bool openGpu(int lutBits);
+    void releaseGpu();
     void fail(const std::string& why);
     // make stream bytes [lo, hi] of every channel available in `bytes`
     void harvest(dsf2flac_int64 lo, dsf2flac_int64 hi);
@@ -95,6 +96,7 @@ private:
 
     std::vector<double> tables;          // [nLookupTable][256], built as the reference builds them
     dsdgpu_ctx* gpu;
+    int gpuDevice;
     int lutBits;
 
     dsf2flac_int64 pos;                  // logical reader marker: newest byte the consumer has reached

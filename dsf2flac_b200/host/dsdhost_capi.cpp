@@ -231,7 +231,6 @@ int64_t dsdhost_convert_file(const char* path, int kind, uint32_t out_fs, double
                              int lut_bits, uint32_t read_ahead, int32_t* out, int64_t out_cap_frames) {
     DsdContainer c;
     if (!dsd_container_load(path, kind, c)) { g_error = c.error; return -1; }
-    const bool pinned = !c.payload.empty() && dsdgpu_host_register(c.payload.data(), c.payload.size()) == DSDGPU_OK;
     int64_t done = -1;
     {
         ContainerSampleReader rd(c);
@@ -264,7 +263,6 @@ int64_t dsdhost_convert_file(const char* path, int kind, uint32_t out_fs, double
             if (!dec.isValid()) { g_error = dec.getErrorMsg(); done = -1; }
         }
     }
-    if (pinned) dsdgpu_host_unregister(c.payload.data());
     return done;
 }
 
@@ -316,10 +314,8 @@ int64_t dsdhost_dop_run_app(const uint8_t* planar, int nch, int64_t nbytes, int6
 int64_t dsdhost_dop_file(const char* path, int kind, int32_t* out, int64_t out_cap_frames) {
     DsdContainer c;
     if (!dsd_container_load(path, kind, c)) { g_error = c.error; return -1; }
-    const bool pinned = !c.payload.empty() && dsdgpu_host_register(c.payload.data(), c.payload.size()) == DSDGPU_OK;
     const int64_t n = dop_pack_all(c.payload.data(), 0, c.blockBytes, c.deliveredBytes, (int)c.channels, c.lengthSamples,
                                    c.idle, c.msbIsPlayedFirst ? 1 : 0, out, out_cap_frames);
-    if (pinned) dsdgpu_host_unregister(c.payload.data());
     return n;
 }
 

@@ -61,3 +61,13 @@ res["run_app_bulk_ms"] = t(lambda: host.dsdhost_run_app_bulk(pin_in.ptr, 2, nbyt
 res["run_app_bulk_readahead_all_ms"] = t(lambda: host.dsdhost_run_app_bulk(pin_in.ptr, 2, nbytes, nbytes * 8, 0x69, 1, DSD128, 176400, scale,
                                                                           amp, clip, 64, 1 << 24, out.ptr, cap))
 print(json.dumps(res))
+# the file path: a 60 s DSD128 stereo .dsf on local disk -> dsdhost_convert_file (parse, read into pinned memory, bulk source)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tests.dsd_files import write_dsf  # noqa: E402
+path = "/tmp/plugin_phases.dsf"
+write_dsf(path, np.ascontiguousarray(pin_in.array), DSD128)
+res2 = {"convert_file_ms": t(lambda: host.dsdhost_convert_file(path.encode(), 0, 176400, scale, amp, clip, 64, 0, out.ptr, cap), reps=4)}
+with open(path, "rb") as fh:
+    res2["plain_read_of_the_file_ms"] = t(lambda: (fh.seek(0), fh.readinto(memoryview(bytearray(os.path.getsize(path))))), reps=3)
+print(json.dumps(res2))
+os.remove(path)
