@@ -36,9 +36,9 @@ tests/cpp/_build/libdsdsynth.so: $(PKG)/host/dsd_synth.cpp
 	mkdir -p tests/cpp/_build
 	$(CXX) -O2 -std=c++17 -fPIC -shared -o $@ $(PKG)/host/dsd_synth.cpp
 # the same host sources linked against a CPU stand-in of the C ABI (tests only, never shipped)
-tests/cpp/_build/libdsdhost_cpu.so: $(HOSTSRC) $(HOSTHDR) tests/cpp/standin_dsdgpu.cpp
+tests/cpp/_build/libdsdhost_cpu.so: $(HOSTSRC) $(HOSTHDR) tests/cpp/standin_dsdgpu.cpp $(PKG)/csrc/shard_plan.cpp $(PKG)/csrc/batch_run.cpp
 	mkdir -p tests/cpp/_build
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) tests/cpp/standin_dsdgpu.cpp
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) tests/cpp/standin_dsdgpu.cpp $(PKG)/csrc/shard_plan.cpp $(PKG)/csrc/batch_run.cpp -lpthread
 
 clean:
 	rm -rf $(PKG)/*.so tests/cpp/_build

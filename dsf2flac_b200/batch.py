@@ -106,6 +106,28 @@ class BatchRunner:
         self.ctxs = {}
 
 
+def run_batch_c(jobs, devices=(0,), rank=0, world=1, align_frames=1024, lib=None, out_kind=capi.OUT_INT32):
+    """The same batch through the C entry point dsdgpu_run_batch (include/dsdgpu.h): one call, one host thread per device,
+    chunks pipelined across files.  -> list of [frames, nch] arrays, one per job (only this rank's shards are filled)."""
+    luts, outs, cjobs = {}, [], []
+    for j in jobs:
+        key = (j.fir.ratio, bool(j.msb_flag))
+        if key not in luts:
+            luts[key] = np.ascontiguousarray(filters.build_lut(j.fir, j.msb_flag))
+        scale, amp, clip = filters.app_params(j.bits, j.scale_db, j.dither)
+        if out_kind == capi.OUT_PCM24:
+            out = np.zeros((j.frames, j.nch, 3), dtype=np.uint8)
+        else:
+            out = np.zeros((j.frames, j.nch), dtype={capi.OUT_INT32: np.int32, capi.OUT_FLOAT64: np.float64, capi.OUT_PCM16: np.int16}[out_kind])
+        outs.append(out)
+        cjobs.append(dict(in_=j.planar, in_stride=j.planar.shape[1], in_first=j.first_byte, in_count=j.in_count, source_block_bytes=0,
+                          fill=j.idle, nch=j.nch, nlut=j.fir.nlut, nstep=j.fir.nstep, lut_precision=j.lut_precision, lut=luts[key],
+                          p0=j.fir.nlut, nframes=j.frames, scale=scale, dither_amp=amp, clip=clip, dither_first_sample=0,
+                          out_kind=out_kind, out=out))
+    capi.run_batch(cjobs, devices, rank, world, align_frames, lib=lib)
+    return outs
+
+
 def stitch(jobs, shard_results):
     """Host-side reassembly of shard outputs (from all ranks) into one [frames, nch] int32 array
     per job; raises if the shards do not tile the batch exactly once."""

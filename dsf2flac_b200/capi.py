@@ -48,6 +48,7 @@ GPU_PROTOTYPES = {
                                          _vp, _vp]),
     "dsdgpu_dop_pack_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64, C.c_int,
                                        _vp]),
+    "dsdgpu_run_batch": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_size_t]),
     "dsdgpu_plan_shards": (C.c_int64, [C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                        C.c_int, C.c_int, C.c_int64, _vp, C.c_int64]),
 }
@@ -266,6 +267,34 @@ class PinnedBuffer:
 class Shard(C.Structure):
     _fields_ = [("job", C.c_int32), ("ch_first", C.c_int32), ("ch_count", C.c_int32), ("reserved", C.c_int32),
                 ("frame_first", C.c_int64), ("frame_count", C.c_int64)]
+
+
+class JobStruct(C.Structure):
+    """dsdgpu_job of include/dsdgpu.h."""
+    _fields_ = [("in_", _vp), ("in_stride", C.c_size_t), ("in_first", C.c_int64), ("in_count", C.c_int64),
+                ("source_block_bytes", C.c_int32), ("fill", C.c_uint8), ("nch", C.c_int32), ("nlut", C.c_int32), ("nstep", C.c_int32),
+                ("lut_precision", C.c_int32), ("lut", _vp), ("p0", C.c_int64), ("nframes", C.c_int64), ("scale", C.c_double),
+                ("dither_amp", C.c_double), ("clip", C.c_double), ("dither_first_sample", C.c_uint64), ("out_kind", C.c_int32),
+                ("out", _vp)]
+
+
+def run_batch(jobs, devices=(0,), rank=0, world=1, align_frames=1024, lib=None):
+    """dsdgpu_run_batch: `jobs` is a list of dicts with the fields of dsdgpu_job (in_/lut/out as addresses or arrays)."""
+    lib = lib or gpu_lib()
+    arr = (JobStruct * len(jobs))()
+    keep = []
+    for a, j in zip(arr, jobs):
+        for name, _ in JobStruct._fields_:
+            v = j[name]
+            if name in ("in_", "lut", "out"):
+                keep.append(v)
+                v = _ptr(v)
+            setattr(a, name, v)
+    dev = (C.c_int * len(devices))(*devices)
+    err = C.create_string_buffer(512)
+    rc = lib.dsdgpu_run_batch(arr, len(jobs), dev, len(devices), rank, world, align_frames, err, 512)
+    if rc != 0:
+        raise DsdGpuError(f"dsdgpu_run_batch failed ({rc}): {err.value.decode()}")
 
 
 def plan_shards(job_frames, job_nch, job_cost, rank, world, align_frames=1024):

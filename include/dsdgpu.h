@@ -216,6 +216,36 @@ int64_t dsdgpu_plan_shards(const int64_t* job_frames, const int32_t* job_nch, co
                            int njobs, int rank, int world, int64_t align_frames, dsdgpu_shard* out,
                            int64_t cap);
 
+/*
+ * A whole batch from C, on the GPUs of this process (no reference counterpart beyond the serial shell loop of
+ * scripts/batch_dsf2flac.sh:16-19).  Every stream is described as what DsdDecimator::getSamples would be asked for it
+ * (reference src/dsd_decimator.cpp:173-222, driven by main.cpp:169-191): frames i = 0..nframes-1 at byte position
+ * p0 + i*nstep, the parameters of main.cpp:239-245, output [nframes][nch].  dsdgpu_plan_shards cuts the batch into
+ * world*ndevices equal-cost pieces; this process runs pieces rank*ndevices .. +ndevices-1, one host thread per device,
+ * chunks of neighbouring shards and files pipelined through the slots of their contexts (uploads, kernels and downloads
+ * overlap across files).  Contexts are kept across calls.  Host buffers should be page-locked (dsdgpu_host_alloc).
+ * A shard that holds only some channels of a job needs planar source rows (source_block_bytes = 0); its PCM is put
+ * into the job's interleaved output by the host.  Output is bit-identical for every world / ndevices (the dither stream
+ * is positional).  Returns 0, or an error code with the text in err.
+ */
+typedef struct {
+    const uint8_t* in;           /* source bytes, laid out as source_block_bytes says (see dsdgpu_set_option) */
+    size_t in_stride;            /* planar rows: bytes between channels */
+    int64_t in_first, in_count;  /* stream index of the first byte held, bytes per channel held */
+    int32_t source_block_bytes;  /* 0 planar, 1 interleaved, 2^k >= 16 block-planar */
+    uint8_t fill;                /* byte outside [in_first, in_first + in_count): the reader's idle byte */
+    int32_t nch, nlut, nstep, lut_precision;
+    const double* lut;           /* [nlut][256], built as initLookupTable builds it (dsd_decimator.cpp:117-151) */
+    int64_t p0, nframes;
+    double scale, dither_amp, clip;
+    uint64_t dither_first_sample; /* m of (frame 0, channel 0): sample (i, c) draws rand() number 2m', 2m'+1, m' = m + i*nch + c */
+    int32_t out_kind;            /* DSDGPU_OUT_* */
+    void* out;                   /* [nframes][nch] */
+} dsdgpu_job;
+
+int dsdgpu_run_batch(const dsdgpu_job* jobs, int njobs, const int* devices, int ndevices, int rank, int world,
+                     int64_t align_frames, char* err, size_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ from dsf2flac_b200 import capi
 
 CPU_HOST = os.path.join(os.path.dirname(__file__), "cpp", "_build", "libdsdhost_cpu.so")
 _NAMES = ["dsdgpu_create", "dsdgpu_destroy", "dsdgpu_last_error", "dsdgpu_set_option", "dsdgpu_kernel_launches",
-          "dsdgpu_decimate_host"]
+          "dsdgpu_decimate_host", "dsdgpu_run_batch", "dsdgpu_plan_shards"]
 
 
 @functools.lru_cache(None)

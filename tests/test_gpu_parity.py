@@ -405,3 +405,27 @@ def test_packed_pcm_outputs_carry_the_same_integers(oracle, kernel, nch):
         with pytest.raises(capi.DsdGpuError, match="needs 0 < clip"):
             g.decimate_host(data, fir.nlut, 16, 1.0, 0.0, 8388607.0, out_kind=capi.OUT_PCM16)
         g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 3])
+def test_c_batch_runner_on_gpu(oracle, world):
+    """dsdgpu_run_batch on the GPU: mixed files (three filters, 1-6 channels, dither on and off, both bit orders), every
+    split fills each job's interleaved output exactly once and the whole equals the oracle; int32 and packed 24-bit."""
+    from dsf2flac_b200 import batch
+    from tests.test_sharding import mixed_jobs
+    jobs = mixed_jobs(7)
+    want = []
+    for j in jobs:
+        scale, amp, clip = filters.app_params(j.bits, j.scale_db, j.dither)
+        want.append(oracle.run_app(j.planar, j.length_samples, j.msb_flag, j.dsd_fs, j.out_fs, scale, amp, clip))
+    for kind in (capi.OUT_INT32, capi.OUT_PCM24):
+        total = [np.zeros_like(w) for w in want]
+        for r in range(world):
+            outs = batch.run_batch_c(jobs, devices=(0,), rank=r, world=world, align_frames=64, out_kind=kind)
+            for t, o in zip(total, outs):
+                o = capi.unpack_pcm24(o) if kind == capi.OUT_PCM24 else o
+                assert not ((t != 0) & (o != 0)).any()
+                t += o
+        for t, w in zip(total, want):
+            assert np.array_equal(t, w)
