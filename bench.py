@@ -684,8 +684,12 @@ def sharded_case(dist, args, spec, steps, warmup):
     # files pipelined through the slots, contexts kept across calls).  Shards that hold only some channels of their job
     # (configs[2]) need the job's dither stride, which a job of their own cannot express: those go shard by shard.
     luts = {}
-    cjobs = []
-    for job, (j, c0, k, f0, nf), pin, out, ctx, d_in, d_out, job_nch in work:
+    cjobs, singles = [], []
+    for item in work:
+        job, (j, c0, k, f0, nf), pin, out, ctx, d_in, d_out, job_nch = item
+        if k != job_nch:
+            singles.append(item)
+            continue
         key = (job.fir.ratio, job.lut_precision)
         if key not in luts:
             luts[key] = np.ascontiguousarray(filters.build_lut(job.fir, job.msb_flag))
@@ -695,13 +699,11 @@ def sharded_case(dist, args, spec, steps, warmup):
                           lut_precision=job.lut_precision, lut=luts[key], p0=job.fir.nlut + f0 * job.fir.nstep, nframes=nf,
                           scale=scale, dither_amp=amp, clip=clip, dither_first_sample=f0 * job_nch + c0, out_kind=capi.OUT_INT32,
                           out=out.ptr))
-    one_call = all(k == job_nch for job, (j, c0, k, f0, nf), pin, out, ctx, d_in, d_out, job_nch in work)
 
     def host_step():
-        if one_call:
+        if cjobs:
             capi.run_batch(cjobs, devices=(local,))
-            return
-        for job, shard, pin, out, ctx, d_in, d_out, job_nch in work:
+        for job, shard, pin, out, ctx, d_in, d_out, job_nch in singles:
             j, c0, k, f0, nf = shard
             ctx.set_option("dither_stride", job_nch)
             scale, amp, clip = scale_of(job)
@@ -751,8 +753,8 @@ def sharded_case(dist, args, spec, steps, warmup):
                         "note": "whole job: LUT bytes of every output sample / device time of the slowest rank"},
            "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_s / steps * 1e3, "x_realtime": audio_s / (e2e_s / steps),
-                   "api": ("dsdgpu_run_batch: one call per step, this rank's shards pipelined across files (pinned host buffers)" if one_call
-                           else "dsdgpu_decimate_host per shard (pinned host buffers)"), "note": "bytes are rank 0's"},
+                   "api": (f"dsdgpu_run_batch: one call per step for {len(cjobs)} of this rank's {len(work)} shards, pipelined across files "
+                           f"(pinned host buffers); channel-subset shards through dsdgpu_decimate_host"), "note": "bytes and shard counts are rank 0's"},
            "gpu_launches": launches}
     for w in work:
         w[2].free()

@@ -429,3 +429,4 @@ def test_c_batch_runner_on_gpu(oracle, world):
                 t += o
         for t, w in zip(total, want):
             assert np.array_equal(t, w)
+

@@ -12,7 +12,7 @@ constexpr int ITER = 2048;
 
 // MODE 0: fixed conflict-free addresses, integer sink.   MODE 1: + one DADD per load (4 chains).
 // MODE 2: data-dependent row (byte from a register stream) + IMAD address + DADD, like the ring kernel.
-template <int MODE, int CHAINS>
+template <int MODE, int CHAINS, int SHFL = 0>
 __global__ void lds_kernel(unsigned long long* cycles, double* sink, uint32_t seed) {
     extern __shared__ __align__(128) unsigned char smem[];
     for (int i = threadIdx.x; i < LUT_BYTES / 8; i += blockDim.x) reinterpret_cast<double*>(smem)[i] = 1e-9 * i;
@@ -21,6 +21,7 @@ __global__ void lds_kernel(unsigned long long* cycles, double* sink, uint32_t se
     uint32_t x = seed * 2654435761u + threadIdx.x * 40503u;
     double acc[CHAINS];
     unsigned long long isink = 0;
+    uint32_t sh = x;
 #pragma unroll
     for (int c = 0; c < CHAINS; ++c) acc[c] = 0.0;
     const unsigned long long t0 = clock64();
@@ -28,6 +29,7 @@ __global__ void lds_kernel(unsigned long long* cycles, double* sink, uint32_t se
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
             if (MODE == 2 && (s & 3) == 0) x = x * 1664525u + 1013904223u;
+            if (SHFL && (s % SHFL) == 0) sh = __shfl_up_sync(0xffffffffu, sh, 3) + x;     // SHFL-th of the steps carries one warp shuffle
 #pragma unroll
             for (int c = 0; c < CHAINS; ++c) {
                 uint32_t addr;
@@ -44,19 +46,19 @@ __global__ void lds_kernel(unsigned long long* cycles, double* sink, uint32_t se
         }
     }
     const unsigned long long t1 = clock64();
-    double tot = (double)isink;
+    double tot = (double)isink + (double)sh;
 #pragma unroll
     for (int c = 0; c < CHAINS; ++c) tot += acc[c];
     if (tot == 1.2345) sink[0] = tot;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-template <int MODE, int CHAINS>
+template <int MODE, int CHAINS, int SHFL = 0>
 void run(const char* name, int threads) {
     unsigned long long* d_cyc; double* d_sink;
     cudaMalloc(&d_cyc, 148 * 8); cudaMalloc(&d_sink, 8);
-    cudaFuncSetAttribute(lds_kernel<MODE, CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES + 1024);
-    for (int rep = 0; rep < 2; ++rep) lds_kernel<MODE, CHAINS><<<148, threads, LUT_BYTES + 1024>>>(d_cyc, d_sink, 7);
+    cudaFuncSetAttribute(lds_kernel<MODE, CHAINS, SHFL>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES + 1024);
+    for (int rep = 0; rep < 2; ++rep) lds_kernel<MODE, CHAINS, SHFL><<<148, threads, LUT_BYTES + 1024>>>(d_cyc, d_sink, 7);
     cudaDeviceSynchronize();
     unsigned long long h[148];
     cudaMemcpy(h, d_cyc, sizeof h, cudaMemcpyDeviceToHost);
@@ -80,5 +82,9 @@ int main() {
     run<2, 1>("data-dependent rows + IMAD + 1 fp64 chain", 1024);
     run<2, 2>("data-dependent rows + IMAD + 2 fp64 chains", 512);
     run<2, 2>("data-dependent rows + IMAD + 2 fp64 chains", 1024);
+    // do warp shuffles take wavefronts of the same pipe?  4 loads per step; one SHFL every SHFL-th step
+    run<2, 4, 4>("data-dependent + 1 SHFL per 16 LDS.64", 512);
+    run<2, 4, 2>("data-dependent + 1 SHFL per 8 LDS.64", 512);
+    run<2, 4, 1>("data-dependent + 1 SHFL per 4 LDS.64", 512);
     return 0;
 }

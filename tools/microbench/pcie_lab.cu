@@ -48,6 +48,26 @@ __global__ void persistent(const uint4* in, uint4* out, size_t total16, size_t c
     }
 }
 
+// the same, storing straight into pinned host memory; keep = 4: every 16-byte piece, keep = 3: three of four (the
+// volume of packed 24-bit output)
+__global__ void persistent_host(const uint4* in, uint4* host_out, size_t total16, size_t chunk16, int spin,
+                                const volatile unsigned* ready, unsigned epoch, int keep) {
+    const size_t nchunks = (total16 + chunk16 - 1) / chunk16;
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (threadIdx.x == 0) {
+            unsigned long long t0 = clock64();
+            while (ready[c] != epoch) { if (clock64() - t0 > 4000000000ULL) __trap(); }
+        }
+        __syncthreads();
+        const size_t lo = c * chunk16, hi = lo + chunk16 < total16 ? lo + chunk16 : total16;
+        for (size_t i = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+            uint4 v = __ldcg(in + i);
+            for (int k = 0; k < spin; ++k) v.x = v.x * 1664525u + 1013904223u;
+            if ((i & 3) < (size_t)keep) host_out[i - (keep == 3 ? i / 4 : 0)] = v;
+        }
+    }
+}
+
 int main(int argc, char** argv) {
     const size_t total = 84672000;
     const int spin = argc > 1 ? atoi(argv[1]) : 3000;
@@ -207,6 +227,19 @@ int main(int argc, char** argv) {
             }
         });
     }
+    for (int keep : {4, 3})
+        for (int blocks : {148, 296, 592}) {
+            char name[64]; snprintf(name, sizeof name, "persist->host %s, %d blk", keep == 4 ? "int32" : "pcm24", blocks);
+            bench(name, [&](int) {
+                ++epoch;
+                persistent_host<<<blocks, 256, 0, st[1]>>>((const uint4*)d_in, (uint4*)h_out, total / 16, chunk / 16, spin, d_ready, epoch, keep);
+                for (int k = 0; k < nchunks; ++k) {
+                    size_t o, n; span(k, o, n);
+                    CK(cudaMemcpyAsync(d_in + o, h_in + o, n, cudaMemcpyHostToDevice, st[0]));
+                    CU(cuStreamWriteValue32(st[0], (CUdeviceptr)(d_ready + k), epoch, 0));
+                }
+            });
+        }
     // tapered schedules: few big pieces in the middle (fewer hand-offs), small ones at both ends (short fill and drain)
     {
         const double MB = 1048576.0;
