@@ -410,6 +410,14 @@ struct RingEmitter {
     // instead of four 8-byte loads at a stride that touches a different cache line per lane.
     __device__ __forceinline__ void fetch() {
         if (!DITHER) return;
+        // The plane comes from DRAM (it is larger than L2 for a whole file) and the loads below are issued only a
+        // quarter period before their use: ask L2 for the lines of the frames this lane STARTS next period -- they are
+        // emitted two periods from now -- so that the loads of that period find them there.  One hint per lane; the 32
+        // hints of a warp name 8 to 16 distinct lines.
+        if (nx.fb < a.nframes) {
+            const double* ahead = a.dither + nx.fb * a.dither_stride + nx.c;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
+        }
         const bool wide = d.pair && ((a.dither_stride | d.c0) & 1) == 0 &&
                           (reinterpret_cast<unsigned long long>(a.dither) & 15ULL) == 0;    // warp-uniform
         if (wide) {
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16);
             __threadfence_block();
             mbar_arrive_after_cp_async(&full[bn]);
-            if (INIT) {
+            if (INIT || DITHER) {
                 after.c = h ? tn.c[1] : tn.c[0];
                 after.fb = (h ? tn.f0[1] : tn.f0[0]) + 4LL * (16 * w + (l & 15));
             }

@@ -74,6 +74,15 @@ __device__ __forceinline__ void rand_apply_poly(const uint32_t* __restrict__ pol
 // (rand_anchor_segment below: a dozen 31x31 polynomial products) and passed by value.
 struct RandSegment { uint32_t w[64]; };
 
+// draw / RAND_MAX, correctly rounded, from the 31-bit draw a:  x = a * 2^-31 is exact (the draw becomes the low
+// mantissa bits of 2^21 + x, one subtraction away), and a / (2^31 - 1) = x * (1 + 2^-31 + 2^-62 + ...) rounds to
+// fma(x, 2^-31 + 2^-62, x) for EVERY one of the 2^31 possible draws (checked exhaustively against a / 2147483647.0 on
+// the CPU, tools/check_draw_quotient.c; tests/test_oracle.py samples it).  Two fp64 operations per draw.
+__device__ __forceinline__ double rand_draw_quotient(uint32_t r) {
+    const double x = __dsub_rn(__hiloint2double(0x41400000, (int)(r >> 1)), 2097152.0);
+    return __fma_rn(x, 4.6566128752457969e-10 /* 2^-31 + 2^-62 */, x);
+}
+
 __global__ void __launch_bounds__(32 * kRandFillWarps)
 glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ lane_polys,
                        const uint32_t* __restrict__ jump_polys, long long count, double* __restrict__ out) {
@@ -110,7 +119,6 @@ glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ l
                 if (d - i >= 0 && d - i < kRandDeg) ring[i] += c[d - i] * v;
         }
     }
-    const double rmax = 2147483647.0, rcp = 1.0 / 2147483647.0;
     const bool whole = s_warp + kRandWarpSamples <= count;         // every sample of this warp is wanted
     double* const row0 = out + s_warp + lane;                       // row r of a block: + r * kRandLaneSamples + blk * 31
 #pragma unroll 1
@@ -121,12 +129,7 @@ glibc_rand_fill_kernel(const RandSegment segment, const uint32_t* __restrict__ l
             const int slot = k % kRandDeg;
             const uint32_t v = ring[slot] + ring[(slot + 28) % kRandDeg];   // r[i-31] + r[i-3]
             ring[slot] = v;
-            // draw / RAND_MAX, correctly rounded: q0 = a*rcp, q0 + (a - q0*d)*rcp (checked against
-            // a/d for all 2^31 possible draws).  The draw becomes a double exactly as 2^52 + draw - 2^52
-            // (one add on the fp64 pipe instead of a conversion instruction).
-            const double a = __dsub_rn(__hiloint2double(0x43300000, (int)(v >> 1)), 4503599627370496.0);
-            const double q0 = __dmul_rn(a, rcp);
-            const double q = __fma_rn(__fma_rn(-q0, rmax, a), rcp, q0);
+            const double q = rand_draw_quotient(v);
             if (k & 1) stage_s[wl][lane][k >> 1] = __dsub_rn(r1, q);
             else r1 = q;
         }

@@ -342,3 +342,18 @@ void dsdoracle_rand(int32_t* out, int64_t n, int64_t skip) {
     for (int64_t k = 0; k < skip; ++k) (void)glibc_rand_next(&g);
     for (int64_t i = 0; i < n; ++i) out[i] = glibc_rand_next(&g);
 }
+
+/* The GPU dither generator's draw / RAND_MAX: fma(x, 2^-31 + 2^-62, x), x = a * 2^-31, against the quotient the
+ * reference computes (dsd_decimator.cpp:203-204) for a = first, first + stride, ... (count values).  Returns the
+ * number of mismatches (tools/check_draw_quotient.c runs all 2^31 values: 0). */
+long long dsdoracle_check_draw_quotient(long long first, long long stride, long long count) {
+    const double c = ldexp(1.0, -31) + ldexp(1.0, -62);
+    long long bad = 0;
+    for (long long k = 0; k < count; ++k) {
+        const long long a = first + k * stride;
+        if (a < 0 || a > 2147483647LL) continue;
+        const double x = ldexp((double)a, -31);
+        if (fma(x, c, x) != (double)a / 2147483647.0) ++bad;
+    }
+    return bad;
+}

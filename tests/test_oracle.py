@@ -107,3 +107,14 @@ def test_oracle_equals_reference(port, ref, ratio, msb):
 
 def test_oracle_rand_equals_libc(port, ref):
     assert np.array_equal(port.rand(100000), ref.rand(100000))
+
+
+def test_one_fma_draw_quotient_sampled(port):
+    """dsd_rand.cuh turns a draw into draw / RAND_MAX with one FMA; tools/check_draw_quotient.c compares all 2^31 values
+    with the reference's division (0 mismatches).  Here: both ends of the range and a stride through the middle."""
+    import ctypes as C
+    f = port.lib.dsdoracle_check_draw_quotient
+    f.restype, f.argtypes = C.c_longlong, [C.c_longlong] * 3
+    assert f(0, 1, 1 << 22) == 0
+    assert f((1 << 31) - (1 << 22), 1, 1 << 22) == 0
+    assert f(12345, 509, 1 << 22) == 0
