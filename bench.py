@@ -593,9 +593,12 @@ def run_gpu_arm(args, wl):
             sub[name] = {k: r[k] for k in ("dither", "value", "unit", "ms_per_step", "per_gpu_mbit_per_s", "x_realtime", "roofline", "e2e",
                                            "gpu_launches")}
         extra["configs0"] = {"workload": c1[5], **sub}
-        # ... and configs[1] itself with dither on
+        # ... and configs[1] itself with dither on, and with the PCM handed back as packed 24-bit samples (SURVEY 8f-4:
+        # the same integers, 3 bytes each over PCIe instead of the 4 of a FLAC__int32)
         r = stream_case(dist, args, wl, 1, args.lut, args.steps, args.warmup)
         extra["dither_on"] = {k: r[k] for k in ("dither", "value", "unit", "ms_per_step", "x_realtime", "roofline", "e2e", "gpu_launches")}
+        r = stream_case(dist, args, wl, args.dither, args.lut, args.steps, args.warmup, out_kind_name="pcm24")
+        extra["packed24"] = {k: r[k] for k in ("out", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
         if dist.world > 1:
             # the channel / time / file splits BASELINE names (strong scaling of one fixed job over the ranks)
             sh = {}

@@ -93,7 +93,9 @@ class BatchRunner:
         return out
 
     def run(self, jobs, rank, world, align_frames=1024):
-        """-> list of (shard, int32 array) for this rank."""
+        """-> list of (shard, int32 array) for this rank, one synchronous dsdgpu_decimate_host call per shard (each keeps its
+        own PCM array: what the tests stitch).  run_batch_c() below is the pipelined way: one dsdgpu_run_batch call, chunks
+        of neighbouring shards and files in flight together, PCM written into the jobs' interleaved outputs."""
         return [(s, self.run_shard(jobs[s[0]], s)) for s in plan(jobs, rank, world, align_frames)]
 
     @property

@@ -89,6 +89,7 @@ struct RingGeom {
     static constexpr int NWARP = NWARP_;
     static constexpr int NTHR = 32 * NWARP;
     static constexpr int ELEM = Q32 ? 4 : 8;          // bytes per table entry
+    static constexpr bool Q32_PAIRS = true;           // 32-bit tables: accumulate two lookups per IADD3 in the late steps
     static constexpr int SKEW_LANES = Q32 ? 32 : 16;  // lanes of one conflict-free load
     static constexpr int NSKEW = SKEW_LANES / COPIES; // distinct skew values
     static constexpr int EARLY_GROUPS = (NSKEW + 3) / 4;  // 4-step groups in which some lane is still wrapped
@@ -378,6 +379,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             for (int i = G::QH - 1; i > 0; --i) r.qo[i] = r.qo[i - 1];
             r.qo[0] = v;
         }
+        int32_t pend[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
@@ -407,6 +409,11 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                     if (s < G::EARLY_STEPS) {
                         r.n[k] = ring_imad(v, to_n, r.n[k]);
                         r.p[k] = ring_imad(v, to_p, r.p[k]);
+                    } else if (G::Q32_PAIRS) {
+                        // two table values per three-input add: 3.5 instead of 4 instructions per lookup (the sums are
+                        // exact integers, so the order does not matter)
+                        if ((u & 1) == 0) pend[k] = v;
+                        else r.n[k] = r.n[k] + pend[k] + v;
                     } else {
                         r.n[k] = ring_imad(v, r.one, r.n[k]);
                     }
