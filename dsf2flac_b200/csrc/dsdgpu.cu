@@ -364,6 +364,7 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     a.p0 = p0; a.nframes = nframes; a.nch = ctx->nch; a.fill = fill;
     a.dither = nullptr; a.dither_stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
     a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
+    a.clip_hi = clip > 0.0 ? clip : HUGE_VAL;
     a.unit = ctx->lut_unit;
     a.out = d_out; a.out_kind = out_kind;
     a.pcm_bytes = out_kind == DSDGPU_OUT_PCM24 ? 3 : out_kind == DSDGPU_OUT_PCM16 ? 2 : 0;
