@@ -86,6 +86,9 @@ static_assert(Ring16x1::LUT_BYTES == Ring16x2::LUT_BYTES, "both read the same ta
 using Ring16x2Q = RingGeom<16, 1, true>;   // 32-bit tables: two images (197 KB) leave room for one round per tile
 using Ring30 = RingGeom<16, 2, false, 30, 2>;   // divide-by-16 filter: 30 tables, 2 bytes per frame
 using Ring12 = RingGeom<16, 2, false, 12, 1>;   // divide-by-8 filter: 12 tables, 1 byte per frame
+using Ring12L = RingGeom<16, 16, false, 12, 1>; // the same with 16 rounds per tile: what a tile costs besides its table loads (geometry,
+                                                // staging, barriers: once per tile and thread) weighs on 12-step periods -- 0.58 -> 0.70 of roofline
+static_assert(Ring12L::LUT_BYTES == Ring12::LUT_BYTES, "both read the same table image");
 using Ring64 = RingGeom<16, 1, false, 72, 8>;   // one pass (72 of 144 tables) of the divide-by-64 extension filter
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
@@ -388,7 +391,8 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         a.lut = ctx->d_lut_ring;
         if (ctx->nlut == 144) return launch_ring_two_pass<Ring64>(ctx, scratch, a, st);
         if (ctx->nlut == 30) return launch_ring<Ring30>(ctx, a, st);
-        if (ctx->nlut == 12) return launch_ring<Ring12>(ctx, a, st);
+        if (ctx->nlut == 12)      // long tiles where there are enough of them to keep every SM busy, short ones for short launches
+            return ring_tile_count<Ring12L>(a.nframes, a.nch) >= 6LL * ctx->sm_count ? launch_ring<Ring12L>(ctx, a, st) : launch_ring<Ring12>(ctx, a, st);
         // (a 1024-thread instance of the 32-bit kernel fits in 64 registers but runs 13 % slower)
         if (ctx->lut_precision == 32) return launch_ring<Ring16x2Q>(ctx, a, st);
         // Tiles of 2 x 2048 frames run 1 % faster on a long stream; a short launch (a 60 s DSD64 file, a chunk of

@@ -507,7 +507,9 @@ RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
     const int npair = nch / 2;
     RingTile t;
     if (tile < nr * npair) {
-        const long long rr = tile / npair;
+        // (mono and stereo -- one channel pair at most -- skip the 64-bit division: it runs once per tile and thread, which
+        // the 12-step periods of the shortest filter feel)
+        const long long rr = npair == 1 ? tile : tile / npair;
         const int u = (int)(tile - rr * npair);
         t.c[0] = 2 * u; t.c[1] = 2 * u + 1;
         t.f0[0] = t.f0[1] = rr * G::NTP;

@@ -240,6 +240,7 @@ int main(int argc, char** argv) {
     if (nwarp == 8 && kr == 6) return run<RingGeom<8, 6>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 30 && kr == 2) return run<RingGeom<16, 2, false, 30, 2>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "30": /16 filter
     if (nwarp == 12 && kr == 2) return run<RingGeom<16, 2, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "12": /8 filter
+    if (nwarp == 12 && kr == 16) return run<RingGeom<16, 16, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);  // its long-tile instance
     if (nwarp == 64 && kr == 1) return run<RingGeom<16, 1, false, 72, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "64": one pass of the /64 extension
     if (nwarp == 32 && kr == 1) return run<RingGeom<16, 1, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // the product's 32-bit geometry
     if (nwarp == 32 && kr == 2) return run<RingGeom<16, 2, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "32": 32-bit tables

@@ -33,6 +33,8 @@ EMU = os.path.join(os.path.dirname(__file__), "cpp", "_build", "emu_ring")
     (12, 2, 30000, 2, 15, 0, 31000, 8, 3),       # nwarp "12" = the divide-by-8 filter (12 tables, 16-step periods)
     (12, 2, 9000, 6, -1, 0, 9500, 3, 2),
     (12, 2, 5000, 1, 12, 1, 5200, 4, 1),
+    (12, 16, 70000, 2, 15, 0, 71000, 8, 2),      # the divide-by-8 filter's long tiles (16 rounds per tile), 2-3 tiles per CTA
+    (12, 16, 40000, 3, -1, 0, 40500, 3, 1),
     (64, 1, 9000, 2, 75, 0, 73000, 4, 2),        # nwarp "64" = one pass of the divide-by-64 extension: 8-byte frame hop,
     (64, 1, 5000, 3, -1, 0, 41000, 3, 3),        #   six history words, sums start from a plane of initial values
     (64, 1, 3000, 1, 72, 5, 24000, 2, 1),
