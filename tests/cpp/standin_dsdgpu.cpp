@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "dsdgpu.h"
@@ -32,7 +33,9 @@ struct dsdgpu_ctx {
 
 namespace {
 // glibc rand() draws by position: srand(1), skip, draw (tests are small, so the skip is cheap)
+std::mutex g_rand_lock;      // libc's generator is process-global; dsdgpu_run_batch drives this stand-in from several threads
 void dither_terms(uint64_t first_sample, int64_t count, std::vector<double>& out) {
+    std::lock_guard<std::mutex> guard(g_rand_lock);
     out.resize((size_t)count);
     srand(1);
     for (uint64_t k = 0; k < 2 * first_sample; ++k) (void)rand();
