@@ -106,6 +106,8 @@ def host_lib(path=None):
     lib.dsdhost_run_script.restype = i64
     lib.dsdhost_run_script.argtypes = [_vp, C.c_int, i64, i64, C.c_uint8, C.c_int, u32, u32, C.c_int, C.POINTER(i64), C.c_int,
                                        dbl, dbl, dbl, dbl, _vp, i64]
+    lib.dsdhost_run_precision_after_bulk.restype = i64
+    lib.dsdhost_run_precision_after_bulk.argtypes = [_vp, C.c_int, i64, i64, i64, C.c_int, u32, u32, C.c_int, dbl, dbl, dbl, i64, _vp]
     lib.dsdhost_file_info.restype = C.c_int
     lib.dsdhost_file_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(i64), C.POINTER(i64)]
     lib.dsdhost_file_channel_bytes.restype = i64

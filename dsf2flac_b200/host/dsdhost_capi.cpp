@@ -198,6 +198,27 @@ int64_t dsdhost_run_script(const uint8_t* planar, int nch, int64_t nbytes, int64
     return done;
 }
 
+// setLutPrecision() AFTER setBulkSource() on a block-planar (DSF-style) source: the context is recreated and must keep
+// the source layout (DsdDecimator::openGpu).  `blocks` holds the stream in blocks of block_bytes per channel, channel after
+// channel; precision goes 64 -> 32 -> 64 before the first sample is asked for.  int32 frames to `out`; returns frames or -1.
+int64_t dsdhost_run_precision_after_bulk(const uint8_t* blocks, int nch, int64_t nbytes, int64_t block_bytes, int64_t length_samples,
+                                         int msb_flag, uint32_t dsd_fs, uint32_t out_fs, int final_bits, double scale, double dither,
+                                         double clip, int64_t nframes, int32_t* out) {
+    const uint8_t dummy = 0;
+    MemorySampleReader rd(&dummy, (uint32_t)nch, 0, length_samples, dsd_fs, msb_flag != 0, 0x69);     // geometry only
+    DsdDecimator dec(&rd, out_fs);
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    if (!dec.setBulkSource(blocks, block_bytes, nbytes)) { g_error = dec.getErrorMsg(); return -1; }
+    if (!dec.setLutPrecision(32) || !dec.setLutPrecision(64) || (final_bits != 64 && !dec.setLutPrecision(final_bits))) {
+        g_error = dec.getErrorMsg();
+        return -1;
+    }
+    while (dec.getPosition() < dec.getFirstValidSample()) dec.step();
+    dec.getSamples(out, (dsf2flac_uint32)(nframes * nch), scale, dither, clip);
+    if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
+    return nframes;
+}
+
 // Header facts of a DSF / DSDIFF file as the reference's readers report them, plus what the bulk
 // path derives: info = {channels, sampling frequency, msbIsPlayedFirst, kind (1 DSF, 2 DSDIFF),
 // source_block_bytes}; *length_samples = getLength(); *delivered_bytes = stream bytes per channel

@@ -27,6 +27,10 @@ def check_reference_line(d, n_gpus):
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the default workload also carries the config the metric's x realtime is quoted on, dither off and on
+    if "configs0" in d:
+        for k in ("dither_off", "dither_on"):
+            assert d["configs0"][k]["value"] > 0 and d["configs0"][k]["x_realtime"] > 1 and d["configs0"][k]["kind"] in ("reference", "port")
 
 
 def test_reference_arm_line():

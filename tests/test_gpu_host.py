@@ -83,3 +83,11 @@ def test_read_ahead_of_bulk_sources_on_gpu(oracle):
     assert np.array_equal(got, want)
     first = oracle.run_raw(data, L, 1, DSD64, 88200, fir.nlut + 1, 31025, sa, amp, clip)
     assert np.array_equal(got[:31025], first)
+
+
+@pytest.mark.gpu
+def test_gpu_precision_change_after_bulk_source_keeps_the_layout(oracle):
+    """The same on the GPU (tests/test_host_logic.py has the stand-in version): 64 -> 32 -> 64 bit tables after a DSF
+    block-planar bulk source has been set; the recreated context must address the blocks, not planar rows."""
+    from tests.test_host_logic import test_precision_change_after_bulk_source_keeps_the_layout as check
+    check(capi.host_lib(), oracle)

@@ -155,3 +155,23 @@ def test_gpu_failure_mid_stream_exits_like_the_reference(tmp_path):
                          env=dict(os.environ, DSDGPU_STANDIN_FAIL_AFTER="3"))
     assert bad.returncode == 1, (bad.returncode, bad.stdout, bad.stderr)
     assert "GPU decimation failed" in bad.stderr and "injected failure" in bad.stderr and "returned" not in bad.stdout
+
+
+def test_precision_change_after_bulk_source_keeps_the_layout(host, oracle):
+    """setLutPrecision() recreates the GPU context; a DSF block-planar bulk source set before must keep its layout on the
+    new one (else every channel reads the wrong bytes, silently)."""
+    nch, block, nblocks = 2, 256, 40
+    data = seeded_bytes(nch, block * nblocks, 99)
+    blocks = np.ascontiguousarray(data.reshape(nch, nblocks, block).transpose(1, 0, 2)).reshape(-1)
+    L = data.shape[1] * 8
+    scale, amp, clip = filters.app_params(24, dither=True)
+    n = 2000
+    want = oracle.run_app(data, L, 1, DSD64, 88200, scale, amp, clip)[:n]
+    out = np.zeros((n, nch), dtype=np.int32)
+    got = host.dsdhost_run_precision_after_bulk(blocks.ctypes.data, nch, data.shape[1], block, L, 1, DSD64, 88200, 64, scale, amp, clip,
+                                                n, out.ctypes.data)
+    assert got == n, host.dsdhost_last_error()
+    assert np.array_equal(out, want)
+    got = host.dsdhost_run_precision_after_bulk(blocks.ctypes.data, nch, data.shape[1], block, L, 1, DSD64, 88200, 32, scale, amp, clip,
+                                                n, out.ctypes.data)
+    assert got == n and np.abs(out.astype(np.int64) - want).max() <= 1          # 32-bit tables: within one LSB
