@@ -430,3 +430,19 @@ def test_c_batch_runner_on_gpu(oracle, world):
         for t, w in zip(total, want):
             assert np.array_equal(t, w)
 
+
+
+@pytest.mark.gpu
+def test_c_batch_runner_all_devices_of_one_process(oracle):
+    """dsdgpu_run_batch with every visible GPU in ONE process (one host thread per device): the shape a C++ caller uses on
+    a multi-GPU box.  With one GPU this is the single-device path again; on the 2/4/8-GPU boxes it is the real thing."""
+    import torch
+    from dsf2flac_b200 import batch
+    from tests.test_sharding import mixed_jobs
+    ndev = torch.cuda.device_count()
+    jobs = mixed_jobs(11)
+    outs = batch.run_batch_c(jobs, devices=tuple(range(ndev)), rank=0, world=1, align_frames=64)
+    for j, got in zip(jobs, outs):
+        scale, amp, clip = filters.app_params(j.bits, j.scale_db, j.dither)
+        want = oracle.run_app(j.planar, j.length_samples, j.msb_flag, j.dsd_fs, j.out_fs, scale, amp, clip)
+        assert np.array_equal(got, want)
