@@ -355,11 +355,43 @@ __global__ void __launch_bounds__(SegLayout::NTHR, 1) decimate_seg_kernel(Decima
 // ---------------------------------------------------------------------------------------------
 // ring kernel
 // ---------------------------------------------------------------------------------------------
-// Stage both halves of a tile: bytes [t0_h, t0_h + HALF_BYTES) of channel c_h.
+// Bulk copy (TMA, cp.async.bulk: SASS UBLKCP) of `bytes` contiguous bytes into shared memory, completion counted in bytes
+// on an mbarrier of this CTA; source, destination and size multiples of 16.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// one arrival of this thread + `bytes` more transaction bytes to wait for
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Stage both halves of a tile: bytes [t0_h, t0_h + HALF_BYTES) of channel c_h, and arrive on the tile's `full` barrier.
+// A tile whose halves lie inside a planar, 16-byte aligned source -- every tile but those at the ends of the stream, for
+// every buffer the host entry points build -- is ONE thread's work: two bulk copies (TMA) that report to the barrier in
+// bytes; the other 511 threads just arrive.  (What a tile costs a thread besides its table loads -- the staging loop,
+// its 64-bit geometry -- is per period for the instances with one round per tile.)  Other tiles: every thread copies its
+// 16-byte chunks (cp.async; edges byte by byte with the fill value) and arrives when they have landed.
 template <class G>
 __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const RingTile& tl, unsigned char* dst,
-                                                bool aligned16) {
+                                                bool aligned16, uint64_t* full_bar) {
     constexpr int CHUNKS = G::HALF_BYTES / 16;
+    if (aligned16 && a.block_shift < 0) {
+        long long t0[2]; int a_tile;
+        ring_half_origin<G>(a.p0, a.in_first, tl.f0[0], t0[0], a_tile);
+        ring_half_origin<G>(a.p0, a.in_first, tl.f0[1], t0[1], a_tile);
+        const long long o0 = t0[0] - a.in_first, o1 = t0[1] - a.in_first;
+        if (o0 >= 0 && o1 >= 0 && o0 + G::HALF_BYTES <= a.in_count && o1 + G::HALF_BYTES <= a.in_count) {   // CTA-uniform
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(full_bar, 2u * G::HALF_BYTES);
+                bulk_copy_g2s(dst, a.in + (long long)tl.c[0] * a.in_stride + o0, G::HALF_BYTES, full_bar);
+                bulk_copy_g2s(dst + G::HALF_BYTES, a.in + (long long)tl.c[1] * a.in_stride + o1, G::HALF_BYTES, full_bar);
+            } else {
+                mbar_arrive(full_bar);
+            }
+            return;
+        }
+    }
     for (int k = threadIdx.x; k < 2 * CHUNKS; k += G::NTHR) {
         const int h = k >= CHUNKS ? 1 : 0;
         const int kk = k - h * CHUNKS;
@@ -370,6 +402,8 @@ __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const Rin
         unsigned char* d = dst + h * G::HALF_BYTES + 16 * kk;
         stage_chunk16(a, c, o, d, aligned16);
     }
+    __threadfence_block();           // plain stores of edge chunks are ordered before the arrival
+    mbar_arrive_after_cp_async(full_bar);
 }
 
 // Where a lane's four frames of one period go: frames fb..fb+3 of channel c.  Its partner
@@ -597,9 +631,8 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
 
     long long tile = blockIdx.x;     // grid <= ntiles
     RingTile tl = ring_tile_at<G>(tile, a.nframes, a.nch);
-    ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16);
-    __threadfence_block();           // plain stores of edge chunks are ordered before the arrival
-    mbar_arrive_after_cp_async(&full[0]);                       // covers the table image too
+    cp_async_wait<0>();              // the table image of this thread (the tile's barrier may be a bulk-copy one)
+    ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16, &full[0]);
 
     RingDest prev;                   // nothing to emit in the very first period: every store is off
     prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
@@ -620,9 +653,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             // buffer bn last held tile i-2; its use count is `use` when bn > b, else use + 1, minus one
             if (i + 1 >= NBUF) mbar_wait(&empty[bn], (unsigned)(((i + 1) / NBUF - 1) & 1));
             const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
-            ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16);
-            __threadfence_block();
-            mbar_arrive_after_cp_async(&full[bn]);
+            ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16, &full[bn]);
             if (INIT || DITHER) {
                 after.c = h ? tn.c[1] : tn.c[0];
                 after.fb = (h ? tn.f0[1] : tn.f0[0]) + 4LL * (16 * w + (l & 15));
