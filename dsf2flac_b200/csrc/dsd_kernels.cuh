@@ -592,6 +592,25 @@ struct RingEmitter {
     }
 };
 
+// The pair geometry (ring_core.h, "Frame pairs") finishes eight frames per lane and period: two emitters, the second four
+// frames further on, driven as two staggered sequences.
+template <int OUT, bool DITHER>
+struct RingEmitterPair {
+    RingEmitter<OUT, DITHER, false> e0, e1;
+    static constexpr bool LATE = DITHER;
+    static __device__ __forceinline__ RingDest further(RingDest d) { d.fb += 4; return d; }
+    __device__ __forceinline__ RingEmitterPair(const DecimateArgs& a, const RingDest& d, const RingDest& nx, int h, unsigned out_low_bits)
+        : e0(a, d, nx, h, out_low_bits), e1(a, further(d), further(nx), h, out_low_bits) {}
+    __device__ __forceinline__ void fetch(int q) { if (q) e1.fetch(); else e0.fetch(); }
+    __device__ __forceinline__ void quantise(int q, int k, double sum) { if (q) e1.quantise(k, sum); else e0.quantise(k, sum); }
+    __device__ __forceinline__ void store(int q) { if (q) e1.store(); else e0.store(); }
+    __device__ __forceinline__ void prefetch() {}
+    __device__ __forceinline__ double init(int) const { return 0.0; }
+};
+template <class G, int OUT, bool DITHER, bool INIT> struct RingEmitterOf { typedef RingEmitter<OUT, DITHER, INIT> type; };
+template <int NW, int KR, int NL, int OUT, bool DITHER, bool INIT>
+struct RingEmitterOf<RingGeom<NW, KR, true, NL, 8>, OUT, DITHER, INIT> { typedef RingEmitterPair<OUT, DITHER> type; };
+
 // Tile pipeline.  Three tile buffers and two mbarriers per buffer; nothing in the steady state
 // makes one warp wait for another:
 //   full[b]   expects one arrival per thread; a thread arrives when the cp.async chunks it staged
@@ -636,13 +655,15 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
 
     RingDest prev;                   // nothing to emit in the very first period: every store is off
     prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
-    if (INIT) {                      // second pass: the sums of the first tile's frames start from the plane
+    if constexpr (INIT && !G::PAIR) {   // second pass: the sums of the first tile's frames start from the plane
         const int c = h ? tl.c[1] : tl.c[0];
         const long long fb = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             lane.n[k] = fb + k < a.nframes ? (typename RingLane<G>::acc_t)a.seg_init[(long long)c * a.plane_stride + fb + k] : 0;
     }
+    typedef typename RingEmitterOf<G, OUT, DITHER, INIT>::type Emitter;
+    constexpr long long FPL = G::FPL;   // output frames per lane and period
     int b = 0, use = 0;              // buffer of the current tile, how often it has been used before
     for (long long i = 0; tile < ntiles; ++i) {
         const long long next = tile + gridDim.x;
@@ -656,7 +677,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16, &full[bn]);
             if (INIT || DITHER) {
                 after.c = h ? tn.c[1] : tn.c[0];
-                after.fb = (h ? tn.f0[1] : tn.f0[0]) + 4LL * (16 * w + (l & 15));
+                after.fb = (h ? tn.f0[1] : tn.f0[0]) + FPL * (16 * w + (l & 15));
             }
         }
         mbar_wait(&full[b], (unsigned)(use & 1));
@@ -664,32 +685,42 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
         cur.c = h ? tl.c[1] : tl.c[0];
         cur.c0 = tl.c[0];
         cur.pair = tl.c[1] != tl.c[0];
-        cur.fb = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
+        cur.fb = (h ? tl.f0[1] : tl.f0[0]) + FPL * (16 * w + (l & 15));
 #pragma unroll 1
         for (int n = 0; n < G::KR; ++n) {
             const uint32_t wnew = w0 + (uint32_t)(b * G::TILE_BYTES + n * G::HOP);
             ring_head<G>(lane, smem, wnew, loff, tid, n, RingNoTrace());
             if (n == 0 && i > 0) mbar_arrive(&empty[b == 0 ? NBUF - 1 : b - 1]);   // done with the previous tile's bytes
             RingDest nx = cur;           // the frames this lane starts in the next period
-            nx.fb += 4LL * G::BLK_PER_ROUND;
+            nx.fb += FPL * G::BLK_PER_ROUND;
             if (n + 1 == G::KR) nx = after;
-            RingEmitter<OUT, DITHER, INIT> emit(a, prev, nx, h, out_low_bits);
+            Emitter emit(a, prev, nx, h, out_low_bits);
             ring_tail<G>(lane, smem, wnew, loff, tid, n, emit, RingNoTrace());
             prev = cur;
-            cur.fb += 4LL * G::BLK_PER_ROUND;
+            cur.fb += FPL * G::BLK_PER_ROUND;
         }
         tile = next;
         if (bn == 0) ++use;
         b = bn;
         if (tile < ntiles) tl = ring_tile_at<G>(tile, a.nframes, a.nch);
     }
-    // the one drain of this CTA: 16 more steps finish the last frames
-    ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
-    RingEmitter<OUT, DITHER, INIT> emit(a, prev, prev, h, out_low_bits);
-    emit.fetch();
+    // the one drain of this CTA: 16 more steps finish the last frames (ROTATE: they are finished, only the emitter is left)
+    if constexpr (!G::ROTATE) ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());
+    Emitter emit(a, prev, prev, h, out_low_bits);
+    if constexpr (G::PAIR) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));
-    emit.store();
+        for (int q = 0; q < 2; ++q) {
+            emit.fetch(q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) emit.quantise(q, k, lane.value(4 * q + k));
+            emit.store(q);
+        }
+    } else {
+        emit.fetch();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));
+        emit.store();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

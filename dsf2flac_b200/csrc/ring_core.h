@@ -57,6 +57,15 @@ namespace dsdgpu {
 //              bank nobody else can be on.  Two images of the (half-size) tables, the second shifted by 16
 //              slots: 16 distinct skews instead of 32 (see "short filters" below), so 16 early steps of 72.
 //
+// Frame pairs (Q32 = true, NLUT = 76, NSTEP = 8: the product's 32-bit geometry).  Frame A + 1 of the divide-by-32 filter
+//              reads at its tap t + 4 the byte frame A reads at tap t, so ONE 8-byte entry
+//              P[tau][e] = (LUT[tau - 4][e], LUT[tau][e])  (tau = 0..75, entries outside 0..71 are 0) serves both:
+//              a "chain" = the frames (A, A + 1) at the position of A + 1, 8 bytes from the next chain, 76 pair
+//              tables, two int32 sums per chain.  That is the geometry of the divide-by-64 pass below -- LDS.64,
+//              80-step periods (4 pad slots of zeros), identity skew, 16-lane groups -- with a lane carrying
+//              4 chains = 8 output frames: half the table loads, byte extractions and address computations per
+//              frame of the one-entry-per-load layout, for 320 instead of 288 bytes of table reads.
+//
 // Other filters (NLUT = 30 tables, 2 bytes per frame; NLUT = 12, 1 byte per frame): the period is
 // NLUT rounded up to a multiple of 16 steps, the extra slots hold -0.0 (the identity of fp64
 // addition), so a wrapped lane needs no second copy: slot PERIOD + s - j is bank pair (s - j) mod 16.
@@ -80,21 +89,31 @@ struct RingGeom {
     static constexpr bool Q32 = Q32_;
     static constexpr int NLUT = NLUT_;                // tables
     static constexpr int NSTEP = NSTEP_;              // bytes between successive frames
+    static constexpr bool PAIR = Q32 && NSTEP_ == 8;   // 32-bit tables, two frames per 8-byte entry (see "Frame pairs" above)
+    static constexpr int FPC = PAIR ? 2 : 1;          // output frames per chain (per sum a lane carries)
+    // Exact integer sums do not care about the order of their terms: a lane that is j taps behind spends its first j
+    // steps on the LAST j taps of the frames it is starting (bytes further back in its own window) instead of finishing
+    // the frames of the previous period.  Same table slots, same banks, but one set of sums, nothing to route in the
+    // early steps, no window shared between neighbouring tiles and no drain.
+    static constexpr bool ROTATE = PAIR;
     static constexpr bool DUP = (NLUT == 72);         // 72-step periods with tail copies (see above)
-    static constexpr int COPIES = NLUT == 12 ? 4 : (NLUT == 30 || Q32) ? 2 : 1;   // images of the tables (whatever fits shared memory)
+    static constexpr int COPIES = NLUT == 12 ? 4 : (NLUT == 30 || (Q32 && !PAIR)) ? 2 : 1;   // images of the tables (whatever fits shared memory)
     static constexpr int PERIOD = DUP ? 72 : COPIES == 4 ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
     static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
-    static constexpr int KF = 4;                      // consecutive frames per lane
+    static constexpr int KF = 4;                      // consecutive chains (sums) per lane
+    static constexpr int FPL = KF * FPC;              // consecutive output frames per lane
+    static constexpr int FBYTES = NSTEP / FPC;        // stream bytes between successive output frames
+    static constexpr int P_SHIFT = PAIR ? FBYTES : 0; // a chain sits at the position of the LATER of its two frames
     static constexpr int KR = KR_;                    // rounds (periods) per tile
     static constexpr int NWARP = NWARP_;
     static constexpr int NTHR = 32 * NWARP;
-    static constexpr int ELEM = Q32 ? 4 : 8;          // bytes per table entry
+    static constexpr int ELEM = (Q32 && !PAIR) ? 4 : 8;   // bytes per table entry
     static constexpr bool Q32_PAIRS = true;           // 32-bit tables: accumulate two lookups per IADD3 in the late steps
-    static constexpr int SKEW_LANES = Q32 ? 32 : 16;  // lanes of one conflict-free load
+    static constexpr int SKEW_LANES = (Q32 && !PAIR) ? 32 : 16;  // lanes of one conflict-free load
     static constexpr int NSKEW = SKEW_LANES / COPIES; // distinct skew values
     static constexpr int EARLY_GROUPS = (NSKEW + 3) / 4;  // 4-step groups in which some lane is still wrapped
     static constexpr int EARLY_STEPS = NSKEW;
-    static constexpr int ROW = Q32 ? 96 : (DUP ? 80 : (PERIOD + 15) / 16 * 16);   // slots per table row
+    static constexpr int ROW = (Q32 && !PAIR) ? 96 : (DUP ? 80 : (PERIOD + 15) / 16 * 16);   // slots per table row
     static constexpr int ROW_BYTES = ROW * ELEM;      // a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
     static constexpr int COPY_STRIDE = 256 * ROW_BYTES + (COPIES > 1 ? 128 : 0);   // image a: + a * (COPY_STRIDE + ELEM * NSKEW)
@@ -103,7 +122,8 @@ struct RingGeom {
     static constexpr int LANE_BYTES = KF * NSTEP;     // bytes between the windows of neighbouring lanes
     static constexpr int BLK_PER_ROUND = 16 * NWARP;  // 4-frame blocks per half per round
     static constexpr int FR_PER_ROUND = KF * BLK_PER_ROUND;
-    static constexpr int NTP = KR * FR_PER_ROUND;     // frames per half per tile
+    static constexpr int NTP = KR * FR_PER_ROUND;     // chains per half per tile
+    static constexpr int NTPF = NTP * FPC;            // output frames per half per tile
     static constexpr int HOP = NSTEP * FR_PER_ROUND;  // bytes between a lane's rounds
     static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
     static constexpr int QH = NSTEP == 8 ? 6 : 3;     // window words of history: frame k reads NSTEP*k bytes further on
@@ -117,9 +137,10 @@ struct RingGeom {
     static constexpr int LATE_GROUPS = GROUPS - EARLY_GROUPS;
     static constexpr bool EMIT_SHORT = !EMIT_SPREAD && LATE_GROUPS >= 1;     // quantise calls shared out over the late groups
     static constexpr int EMIT_PER_GROUP = EMIT_SHORT ? (4 + LATE_GROUPS - 1) / LATE_GROUPS : 0;
-    static_assert(!Q32 || DUP, "32-bit tables exist for the 72-table filter");
+    static_assert(!Q32 || DUP || (PAIR && NLUT == 76), "32-bit tables exist for the 72-table filter (as 76 pair tables with an 8-byte hop)");
     static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8, "frame hop of 8, 16, 32 or 64 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
+    static_assert(!PAIR || GROUPS >= EARLY_GROUPS + 15, "two emitter sequences fit the late groups");
     static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == HALF_SHIFT && ROW_BYTES % 128 == 0 && PERIOD % 4 == 0, "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
     static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
@@ -209,6 +230,10 @@ struct RingNoEmit {
     RING_HD void store() {}
     RING_HD void prefetch() {}
     RING_HD double init(int) const { return 0.0; }
+    // pair geometry: two sequences (frames 0..3 / 4..7 of the lane)
+    RING_HD void fetch(int) {}
+    RING_HD void quantise(int, int, double) {}
+    RING_HD void store(int) {}
 };
 
 // Skew of lane l (0..31) of a warp.
@@ -224,6 +249,7 @@ struct RingNoEmit {
 template <class G>
 RING_HD int ring_lane_skew(int l) {
     const int h = (l >> 4) & 1, i = l & 15;
+    if (G::PAIR) return i;                              // lane stride of eight words, like the divide-by-64 pass
     if (G::Q32 && G::COPIES > 1) {
         // 16 skews, each used by one lane of either image (ring_lane_image); the window word of lane (h, i) is
         // 4*i + (j >> 2): the four lanes that share 4*i mod 32 -- (h, i), (h, i ^ 8) for h = 0, 1 -- get the four values of j >> 2
@@ -255,14 +281,31 @@ RING_HD int ring_lane_image(int l) {
     return G::Q32 ? (i >> 2) & 1 : i % G::COPIES;
 }
 
-template <bool Q32> struct RingAcc { typedef double type; };
-template <> struct RingAcc<true> { typedef int32_t type; };
+struct RingI2 { int32_t x, y; };                      // the two sums of a chain of the pair geometry: frames A, A + 1
+template <bool Q32, bool PAIR> struct RingAcc { typedef double type; };
+template <> struct RingAcc<true, false> { typedef int32_t type; };
+template <> struct RingAcc<true, true> { typedef RingI2 type; };
+RING_HD void ring_acc_clear(double& a) { a = 0.0; }
+RING_HD void ring_acc_clear(int32_t& a) { a = 0; }
+RING_HD void ring_acc_clear(RingI2& a) { a.x = 0; a.y = 0; }
+RING_HD RingI2 ring_lds_i2(const unsigned char* smem, uint32_t off) {
+#if defined(__CUDACC__)
+    const int2 v = *reinterpret_cast<const int2*>(smem + off);
+    RingI2 r; r.x = v.x; r.y = v.y;
+    return r;
+#else
+    RingI2 r;
+    r.x = *reinterpret_cast<const int32_t*>(smem + off);
+    r.y = *reinterpret_cast<const int32_t*>(smem + off + 4);
+    return r;
+#endif
+}
 
 // Per-lane state.  It lives across periods AND across tiles: the pipeline never drains between
 // tiles, a lane finishes the last frames of one tile during the first steps of the next.
 template <class G>
 struct RingLane {
-    typedef typename RingAcc<G::Q32>::type acc_t;
+    typedef typename RingAcc<G::Q32, G::PAIR>::type acc_t;
     acc_t n[4];                 // sums of the frames started in the current period
     acc_t p[4];                 // sums of the frames started in the previous period (final after EARLY_STEPS)
     uint32_t qn[G::QH], qo[G::QH];   // previous window words of the current / the previous frame set
@@ -276,7 +319,11 @@ struct RingLane {
     double unit;                // value of one unit of acc_t (1.0, or 2^-qbits for 32-bit tables)
     int one;                    // 1, in a register the compiler cannot see through: x * one + acc issues on
                                 // the multiply-add pipe instead of the integer ALU the byte extraction keeps busy
-    RING_HD double value(int k) const { return (double)p[k] * unit; }   // exact: |p| < 2^31
+    // finished sum of output frame k of the lane (k < FPL), exact: |p| < 2^31
+    RING_HD double value(int k) const {
+        if constexpr (G::PAIR) return (double)((k & 1) ? p[k >> 1].y : p[k >> 1].x) * unit;
+        else return (double)p[k] * unit;
+    }
 };
 
 // a0 = a_tile + LANE_BYTES*(16*warp + (lane & 15)) + j: offset inside the half's buffer of the byte the
@@ -305,7 +352,7 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
         r.sel[g] = v;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { r.n[k] = 0; r.p[k] = 0; }
+    for (int k = 0; k < 4; ++k) { ring_acc_clear(r.n[k]); ring_acc_clear(r.p[k]); }
 #pragma unroll
     for (int i = 0; i < G::QH; ++i) { r.qo[i] = 0u; r.qn[i] = 0u; }
     r.lo = r.ln = 0u;
@@ -335,7 +382,18 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                          int tid, int period, Emit& emit, const Trace& tr) {
 #pragma unroll
     for (int g = G0; g < G1; ++g) {
-        if (G::EMIT_SPREAD) {
+        if constexpr (G::PAIR) {
+            // eight finished frames per lane: two emitter sequences (frames 0..3, then 4..7), each fetch -> four quantise
+            // calls -> store, staggered over the late groups (Emit is a RingEmitterPair-like object)
+            constexpr int E = G::EARLY_GROUPS;
+            if (g == E + 1) emit.fetch(0);
+            if (g >= E + 4 && g < E + 8) emit.quantise(0, g - (E + 4), r.value(g - (E + 4)));
+            if (g == E + 8) emit.store(0);
+            if (g == E + 6) emit.fetch(1);
+            if (g >= E + 9 && g < E + 13) emit.quantise(1, g - (E + 9), r.value(4 + g - (E + 9)));
+            if (g == E + 13) emit.store(1);
+            if (g == E + 14) emit.prefetch();
+        } else if (G::EMIT_SPREAD) {
             constexpr bool late = Emit::LATE && G::GROUPS >= G::EARLY_GROUPS + 12;
             constexpr int q0 = G::EARLY_GROUPS + (late ? 6 : 1);       // group of the first quantise call
             if (late && g == G::EARLY_GROUPS + 1) emit.fetch();
@@ -380,6 +438,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             r.qo[0] = v;
         }
         int32_t pend[4] = {0, 0, 0, 0};
+        RingI2 pend2[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
@@ -404,7 +463,18 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 else e = ring_byte<0>(x[k]);
                 const uint32_t addr = e * (uint32_t)G::ROW_BYTES + loff + (uint32_t)(G::ELEM * s);
                 tr.lut(tid, period, s, k, addr);
-                if constexpr (G::Q32) {
+                if constexpr (G::PAIR) {
+                    const RingI2 v = ring_lds_i2(smem, addr);
+                    if (s < G::EARLY_STEPS && !G::ROTATE) {
+                        r.n[k].x = ring_imad(v.x, to_n, r.n[k].x); r.n[k].y = ring_imad(v.y, to_n, r.n[k].y);
+                        r.p[k].x = ring_imad(v.x, to_p, r.p[k].x); r.p[k].y = ring_imad(v.y, to_p, r.p[k].y);
+                    } else if ((u & 1) == 0) {
+                        pend2[k] = v;            // two entries per three-input add (exact integer sums: any order)
+                    } else {
+                        r.n[k].x = r.n[k].x + pend2[k].x + v.x;
+                        r.n[k].y = r.n[k].y + pend2[k].y + v.y;
+                    }
+                } else if constexpr (G::Q32) {
                     const int32_t v = ring_lds_i32(smem, addr);
                     if (s < G::EARLY_STEPS) {
                         r.n[k] = ring_imad(v, to_n, r.n[k]);
@@ -448,6 +518,22 @@ RING_HD void ring_head(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
     r.ln = l[0];
     loff = r.lwrap;
     RingNoEmit none;
+    if constexpr (G::ROTATE) {
+        // the wrapped steps read on in this window, behind its last group: raw words w(g) = word L(0) - g,
+        // V(g) = funnel(w(g), w(g - 1)); history V(GROUPS-1 .. GROUPS-QH), last raw word w(GROUPS-1)
+        uint32_t w[G::QH + 1];
+#pragma unroll
+        for (int i = 0; i <= G::QH; ++i) {
+            const uint32_t a = wnew - 4u * (uint32_t)(G::GROUPS - 1 - i);
+            w[i] = ring_lds_u32(smem, a);
+            tr.word(tid, period, 110 + i, a);
+        }
+#pragma unroll
+        for (int i = 0; i < G::QH; ++i) r.qo[i] = ring_funnel_r(w[i], w[i + 1], r.shift);
+        r.lo = w[0];
+        ring_groups<G, 0, G::EARLY_GROUPS>(r, smem, wnew, wnew, loff, tid, period, none, tr);
+        return;
+    }
     ring_groups<G, 0, G::EARLY_GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, none, tr);
 }
 
@@ -456,7 +542,7 @@ RING_HD void ring_head(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
 template <class G, class Emit, class Trace>
 RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew, uint32_t& loff, int tid, int period,
                        Emit& emit, const Trace& tr) {
-    if (!G::EMIT_SPREAD && !G::EMIT_SHORT) {   // shortest periods: the whole emitter before the remaining steps
+    if constexpr (!G::EMIT_SPREAD && !G::EMIT_SHORT) {   // shortest periods: the whole emitter before the remaining steps
         emit.fetch();
 #pragma unroll
         for (int k = 0; k < 4; ++k) emit.quantise(k, r.value(k));
@@ -464,12 +550,16 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
         emit.prefetch();
     }
     ring_groups<G, G::EARLY_GROUPS, G::GROUPS>(r, smem, wnew, r.wlast, loff, tid, period, emit, tr);
-    if (G::EMIT_SHORT) {
+    if constexpr (G::EMIT_SHORT) {
         emit.store();
         emit.prefetch();
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { r.p[k] = r.n[k]; r.n[k] = (typename RingLane<G>::acc_t)emit.init(k); }
+    for (int k = 0; k < 4; ++k) {
+        r.p[k] = r.n[k];
+        if constexpr (G::PAIR) ring_acc_clear(r.n[k]);
+        else r.n[k] = (typename RingLane<G>::acc_t)emit.init(k);
+    }
 #pragma unroll
     for (int i = 0; i < G::QH; ++i) r.qo[i] = r.qn[i];   // this window's last words = next period's history
     r.lo = r.ln;
@@ -483,7 +573,7 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
 //   a_tile pmin - t0 (the same for every tile of a launch: NTP*NSTEP is a multiple of 16)
 template <class G>
 RING_HD void ring_half_origin(long long p0, long long in_first, long long f0, long long& t0, int& a_tile) {
-    const long long pmin = p0 + f0 * G::NSTEP;
+    const long long pmin = p0 + f0 * G::FBYTES + G::P_SHIFT;
     long long rel = pmin - G::FRONT - in_first;
     rel = (rel >= 0) ? (rel & ~15LL) : -((-rel + 15) & ~15LL);
     t0 = in_first + rel;
@@ -497,13 +587,13 @@ struct RingTile { int c[2]; long long f0[2]; };
 
 template <class G>
 RING_HD long long ring_tile_count(long long nframes, int nch) {
-    const long long nr = (nframes + G::NTP - 1) / G::NTP, nr2 = (nframes + 2 * G::NTP - 1) / (2 * G::NTP);
+    const long long nr = (nframes + G::NTPF - 1) / G::NTPF, nr2 = (nframes + 2 * G::NTPF - 1) / (2 * G::NTPF);
     return nr * (nch / 2) + nr2 * (nch & 1);
 }
 
 template <class G>
 RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
-    const long long nr = (nframes + G::NTP - 1) / G::NTP;
+    const long long nr = (nframes + G::NTPF - 1) / G::NTPF;
     const int npair = nch / 2;
     RingTile t;
     if (tile < nr * npair) {
@@ -512,11 +602,11 @@ RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
         const long long rr = npair == 1 ? tile : tile / npair;
         const int u = (int)(tile - rr * npair);
         t.c[0] = 2 * u; t.c[1] = 2 * u + 1;
-        t.f0[0] = t.f0[1] = rr * G::NTP;
+        t.f0[0] = t.f0[1] = rr * G::NTPF;
     } else {
         const long long rr = tile - nr * npair;
         t.c[0] = t.c[1] = nch - 1;
-        t.f0[0] = 2 * rr * G::NTP; t.f0[1] = t.f0[0] + G::NTP;
+        t.f0[0] = 2 * rr * G::NTPF; t.f0[1] = t.f0[0] + G::NTPF;
     }
     return t;
 }
@@ -529,6 +619,16 @@ inline void ring_build_lut_image(const double* lut, unsigned char* image, double
     for (int i = 0; i < G::LUT_BYTES; ++i) image[i] = 0;
     if (!G::Q32)                                        // pad slots: -0.0, the identity of fp64 addition
         for (int i = 0; i < G::LUT_BYTES / 8; ++i) reinterpret_cast<double*>(image)[i] = -0.0;
+    if constexpr (G::PAIR) {
+        // lut is the filter's own [72][256]; slot tau of row e = (LUT[tau - 4][e], LUT[tau][e]), zero outside the filter
+        for (int e = 0; e < 256; ++e)
+            for (int tau = 0; tau < G::NLUT; ++tau) {
+                int32_t* at = reinterpret_cast<int32_t*>(image + G::GUARD_BYTES + e * G::ROW_BYTES + tau * G::ELEM);
+                at[0] = tau >= G::FBYTES ? (int32_t)(lut[(tau - G::FBYTES) * 256 + e] / unit) : 0;
+                at[1] = tau < G::NLUT - G::FBYTES ? (int32_t)(lut[tau * 256 + e] / unit) : 0;
+            }
+        return;
+    }
     auto put = [&](int image_no, int e, int slot, double v) {
         unsigned char* at = image + G::GUARD_BYTES + image_no * (G::COPY_STRIDE + G::ELEM * G::NSKEW) + e * G::ROW_BYTES + slot * G::ELEM;
         if (G::Q32) *reinterpret_cast<int32_t*>(at) = (int32_t)(v / unit);

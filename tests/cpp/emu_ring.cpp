@@ -64,7 +64,9 @@ static int wavefronts(const std::vector<uint32_t>& addrs, int bytes_per_lane) {
 template <class G>
 static int run(long long nframes, int nch, long long p0, long long in_first, long long in_count, unsigned seed, int grid) {
     srand(seed);
-    std::vector<double> lut((size_t)G::NLUT * 256);
+    constexpr int NTAB = G::PAIR ? 72 : G::NLUT;       // the filter's own tables (the pair geometry stores them as 76 pair tables)
+    constexpr int FPL = G::FPL;                        // output frames per lane and period
+    std::vector<double> lut((size_t)NTAB * 256);
     g_elem = G::ELEM;
     // random tables reach |sum| ~ 12, the reference's stay below 1.33: 2^-27 here, 2^-30 in the product
     const double unit = G::Q32 ? 1.0 / (double)(1 << 27) : 1.0;
@@ -105,29 +107,33 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
     struct Dest { long long fb; int c; };
     struct Collect {                      // the emulator's emitter: just keeps what the lane hands over
         enum { LATE = 1 };                    // the later call sites: what the dither variants of the kernel run
-        double sums[4]; int got = 0, stored = 0, fetched = 0, early = 0;
+        double sums[8]; int got = 0, stored = 0, fetched = 0, early = 0;
         double iv[4] = {0, 0, 0, 0};
         void fetch() { if (!got) ++early; }
         void quantise(int k, double v) { sums[k] = v; got |= 1 << k; }
         void store() { ++stored; }
         void prefetch() { ++fetched; }
         double init(int k) const { return iv[k]; }
+        // pair geometry: sequence q finishes frames 4q .. 4q+3 of the lane
+        void fetch(int q) { if (!(got & (15 << (4 * q)))) ++early; }
+        void quantise(int q, int k, double v) { sums[4 * q + k] = v; got |= 1 << (4 * q + k); }
+        void store(int q) { if ((got >> (4 * q) & 15) == 15) ++stored; }
     };
     // multi-pass geometry (NSTEP = 8): every frame's sum starts from a value left by "the previous pass"
-    const bool use_init = (G::NSTEP == 8);
+    const bool use_init = (G::NSTEP == 8) && !G::PAIR;
     auto init_of = [&](int c, long long f) -> double {
         if (!use_init || f >= nframes) return 0.0;
         unsigned x = (unsigned)(c * 2654435761u) ^ (unsigned)(f * 40503u + 17u);
         x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15;
         return ((double)(x & 0xffffff) / (double)0x1000000 - 0.5) * 1.7;
     };
-    auto check = [&](const Dest& d, const double (&sums)[4], int tid) {
-        for (int k = 0; k < 4; ++k) {
+    auto check = [&](const Dest& d, const double (&sums)[8], int tid) {
+        for (int k = 0; k < FPL; ++k) {
             const long long f = d.fb + k;
             if (f >= nframes) continue;
-            const long long p = p0 + f * G::NSTEP;
+            const long long p = p0 + f * G::FBYTES;
             double ref = init_of(d.c, f);
-            for (int t = 0; t < G::NLUT; ++t) ref += lut[(size_t)t * 256 + stream_byte(d.c, p - t)];
+            for (int t = 0; t < NTAB; ++t) ref += lut[(size_t)t * 256 + stream_byte(d.c, p - t)];
             ++checked;
             if (seen[d.c][(size_t)f]++) ++dup;
             if (memcmp(&ref, &sums[k], 8) != 0) {
@@ -153,7 +159,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         long long tile = cta;
         int buf = 0, period = 0;
         if (stage(tile, 0)) return 2;
-        if (use_init) {                   // the kernel loads these right after ring_lane_init
+        if constexpr (!G::PAIR) if (use_init) {   // the kernel loads these right after ring_lane_init
             const RingTile t0 = ring_tile_at<G>(tile, nframes, nch);
             for (int tid = 0; tid < G::NTHR; ++tid) {
                 const int l = tid & 31, w = tid >> 5, h = l >> 4;
@@ -181,14 +187,14 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                     Collect col;
                     {   // frames this lane starts in the NEXT period: next round of this tile, or the next tile
                         long long fbn = nframes; int cn = 0;
-                        if (n + 1 < G::KR) { fbn = tl.f0[h] + 4LL * ((long long)(n + 1) * G::BLK_PER_ROUND + 16 * w + (l & 15)); cn = tl.c[h]; }
-                        else if (next < ntiles) { const RingTile tn = ring_tile_at<G>(next, nframes, nch); fbn = tn.f0[h] + 4LL * (16 * w + (l & 15)); cn = tn.c[h]; }
+                        if (n + 1 < G::KR) { fbn = tl.f0[h] + (long long)FPL * ((long long)(n + 1) * G::BLK_PER_ROUND + 16 * w + (l & 15)); cn = tl.c[h]; }
+                        else if (next < ntiles) { const RingTile tn = ring_tile_at<G>(next, nframes, nch); fbn = tn.f0[h] + (long long)FPL * (16 * w + (l & 15)); cn = tn.c[h]; }
                         for (int k = 0; k < 4; ++k) col.iv[k] = init_of(cn, fbn + k);
                     }
                     ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, col, rec);
-                    if (col.got != 15 || col.stored != 1 || col.fetched != 1 || col.early != 1) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
+                    if (col.got != (1 << FPL) - 1 || col.stored != G::FPC || col.fetched != 1 || col.early != G::FPC) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
                     if (have_prev) check(prev[tid], col.sums, tid);
-                    prev[tid] = {tl.f0[h] + 4LL * ((long long)n * G::BLK_PER_ROUND + 16 * w + (l & 15)), tl.c[h]};
+                    prev[tid] = {tl.f0[h] + (long long)FPL * ((long long)n * G::BLK_PER_ROUND + 16 * w + (l & 15)), tl.c[h]};
                 }
                 have_prev = true;
                 if (trace) {
@@ -205,8 +211,9 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         }
         if (have_prev)
             for (int tid = 0; tid < G::NTHR; ++tid) {
-                ring_head<G>(lanes[tid], smem.data(), lanes[tid].wlast, loff[tid], tid, period, Recorder{nullptr, nullptr});
-                const double last[4] = {lanes[tid].value(0), lanes[tid].value(1), lanes[tid].value(2), lanes[tid].value(3)};
+                if constexpr (!G::ROTATE) ring_head<G>(lanes[tid], smem.data(), lanes[tid].wlast, loff[tid], tid, period, Recorder{nullptr, nullptr});
+                double last[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int k = 0; k < FPL; ++k) last[k] = lanes[tid].value(k);
                 check(prev[tid], last, tid);
             }
     }
@@ -242,6 +249,8 @@ int main(int argc, char** argv) {
     if (nwarp == 12 && kr == 2) return run<RingGeom<16, 2, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "12": /8 filter
     if (nwarp == 12 && kr == 16) return run<RingGeom<16, 16, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);  // its long-tile instance
     if (nwarp == 64 && kr == 1) return run<RingGeom<16, 1, false, 72, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "64": one pass of the /64 extension
+    if (nwarp == 76 && kr == 1) return run<RingGeom<16, 1, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "76": the product's 32-bit geometry (frame pairs)
+    if (nwarp == 76 && kr == 2) return run<RingGeom<16, 2, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 32 && kr == 1) return run<RingGeom<16, 1, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // the product's 32-bit geometry
     if (nwarp == 32 && kr == 2) return run<RingGeom<16, 2, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "32": 32-bit tables
     if (nwarp == 32 && kr == 3) return run<RingGeom<16, 3, true>>(nframes, nch, p0, in_first, in_count, seed, grid);
