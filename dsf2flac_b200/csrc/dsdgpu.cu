@@ -66,6 +66,16 @@ struct dsdgpu_ctx {
     std::vector<uint32_t> rand_base;         // host: seed words r[3..94]
     uint32_t* d_rand_lane = nullptr;         // x^(kRandLaneValues*l), l < 32, stored [k][l]
     uint32_t* d_rand_jump = nullptr;         // x^(kRandWarpValues * 128^level * u), [level][u][k]
+    // Dither plane cache ("dither_cache" option).  The reference draws from the UNSEEDED process-global rand()
+    // (dsd_decimator.cpp:203-204), and dsf2flac converts one file per process: the (r1 - r2) term of output sample m
+    // is a constant of the reference, the same for every file -- like the filter tables.  A context therefore keeps
+    // the prefix [0, dither_len) of that plane once generated; calls whose samples lie inside the limit read it in
+    // place and only ever generate what is not there yet.  Grow-only; a region is never rewritten once valid.
+    long long dither_cache_limit = 1LL << 27;   // samples (8 bytes each); 0 = off: every call generates its own plane
+    double* d_dither_cache = nullptr;
+    long long dither_cap = 0, dither_len = 0;   // allocated / valid samples
+    cudaEvent_t dither_ready = nullptr;         // recorded after the last generation; readers on other streams wait for it
+    std::vector<double*> dither_retired;        // outgrown planes: possibly still read by launches in flight, freed at destroy
     cudaStream_t stream = nullptr;           // for dsdgpu_decimate_device(stream == NULL)
     dsdgpu_slot slots[DSDGPU_SLOTS];
     int pipeline_slots = DSDGPU_SLOTS;       // slots dsdgpu_decimate_host cycles through
@@ -178,6 +188,31 @@ int launch_dither(dsdgpu_ctx* ctx, dsdgpu_slot& s, unsigned long long first_samp
         ctx->launches += 1;
     }
     CUDA_TRY(ctx, cudaGetLastError());
+    return DSDGPU_OK;
+}
+
+// Make samples [0, end) of the cached dither plane valid for work enqueued on `st` afterwards.
+int dither_cache_cover(dsdgpu_ctx* ctx, dsdgpu_slot& s, long long end, cudaStream_t st) {
+    if (!ctx->dither_ready) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->dither_ready, cudaEventDisableTiming));
+    if (ctx->dither_len > 0) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->dither_ready, 0));   // earlier generations, on whatever stream
+    if (end <= ctx->dither_len) return DSDGPU_OK;
+    if (end > ctx->dither_cap) {
+        long long cap = 1LL << 22;
+        while (cap < end) cap <<= 1;
+        if (cap > ctx->dither_cache_limit) cap = ctx->dither_cache_limit;
+        double* fresh = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&fresh), (size_t)cap * sizeof(double)));
+        if (ctx->dither_len > 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(fresh, ctx->d_dither_cache, (size_t)ctx->dither_len * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (ctx->d_dither_cache) ctx->dither_retired.push_back(ctx->d_dither_cache);
+        ctx->d_dither_cache = fresh;
+        ctx->dither_cap = cap;
+    }
+    // whole generator warps: the new part starts where the valid part ends
+    int rc = launch_dither(ctx, s, (unsigned long long)ctx->dither_len, end - ctx->dither_len, ctx->d_dither_cache + ctx->dither_len, st);
+    if (rc) return rc;
+    ctx->dither_len = end;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->dither_ready, st));
     return DSDGPU_OK;
 }
 
@@ -375,11 +410,20 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     a.seg_first = 0; a.seg_n = ctx->nlut; a.seg_init = nullptr; a.seg_raw = nullptr; a.plane_stride = 0;
     if (dither_amp > 0.0) {
         const long long count = (nframes - 1) * a.dither_stride + ctx->nch;
-        int rc = ensure(ctx, &scratch.d_dither, &scratch.dither_cap, (size_t)count * sizeof(double));
-        if (rc) return rc;
-        rc = launch_dither(ctx, scratch, dither_first_sample, count, scratch.d_dither, st);
-        if (rc) return rc;
-        a.dither = scratch.d_dither;
+        // the cached plane serves calls that start inside (or right at the end of) what is already valid -- a file converted
+        // from its first sample, whole or chunk after chunk; a call far into the stream (a time shard) makes its own plane
+        if (dither_first_sample <= (uint64_t)ctx->dither_len &&
+            dither_first_sample + (uint64_t)count <= (uint64_t)ctx->dither_cache_limit) {
+            int rc = dither_cache_cover(ctx, scratch, (long long)dither_first_sample + count, st);
+            if (rc) return rc;
+            a.dither = ctx->d_dither_cache + dither_first_sample;
+        } else {
+            int rc = ensure(ctx, &scratch.d_dither, &scratch.dither_cap, (size_t)count * sizeof(double));
+            if (rc) return rc;
+            rc = launch_dither(ctx, scratch, dither_first_sample, count, scratch.d_dither, st);
+            if (rc) return rc;
+            a.dither = scratch.d_dither;
+        }
     }
     const bool ring_ok = ctx->d_lut_ring != nullptr;
     int kernel = ctx->kernel;
@@ -585,6 +629,9 @@ void dsdgpu_destroy(dsdgpu_ctx* ctx) {
     if (ctx->d_lut_seg) cudaFree(ctx->d_lut_seg);
     if (ctx->d_rand_lane) cudaFree(ctx->d_rand_lane);
     if (ctx->d_rand_jump) cudaFree(ctx->d_rand_jump);
+    if (ctx->d_dither_cache) cudaFree(ctx->d_dither_cache);
+    for (double* p : ctx->dither_retired) cudaFree(p);
+    if (ctx->dither_ready) cudaEventDestroy(ctx->dither_ready);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -608,6 +655,13 @@ int dsdgpu_set_option(dsdgpu_ctx* ctx, const char* key, long long value) {
     } else if (!strcmp(key, "slots")) {
         if (value < 1 || value > DSDGPU_SLOTS) return fail(ctx, DSDGPU_ERR_ARG, "slots must be 1..%d", DSDGPU_SLOTS);
         ctx->pipeline_slots = (int)value;
+    } else if (!strcmp(key, "dither_cache")) {
+        if (value < 0) return fail(ctx, DSDGPU_ERR_ARG, "dither_cache must be >= 0 (samples)");
+        if (value < ctx->dither_len) {              // shrinking below what is valid: drop the plane (launches in flight keep reading it)
+            if (ctx->d_dither_cache) ctx->dither_retired.push_back(ctx->d_dither_cache);
+            ctx->d_dither_cache = nullptr; ctx->dither_cap = 0; ctx->dither_len = 0;
+        }
+        ctx->dither_cache_limit = value;
     } else if (!strcmp(key, "trace")) {
         ctx->trace = value != 0;
     } else if (!strcmp(key, "chunk_frames")) {

@@ -386,13 +386,15 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             // eight finished frames per lane: two emitter sequences (frames 0..3, then 4..7), each fetch -> four quantise
             // calls -> store, staggered over the late groups (Emit is a RingEmitterPair-like object)
             constexpr int E = G::EARLY_GROUPS;
-            if (g == E + 1) emit.fetch(0);
-            if (g >= E + 4 && g < E + 8) emit.quantise(0, g - (E + 4), r.value(g - (E + 4)));
-            if (g == E + 8) emit.store(0);
-            if (g == E + 6) emit.fetch(1);
-            if (g >= E + 9 && g < E + 13) emit.quantise(1, g - (E + 9), r.value(4 + g - (E + 9)));
-            if (g == E + 13) emit.store(1);
-            if (g == E + 14) emit.prefetch();
+            constexpr int LEAD = Emit::LATE ? 5 : 1;   // groups between a sequence's fetch (dither loads) and its first quantise
+            constexpr int F0 = E + 1, Q0 = F0 + LEAD, F1 = Q0 + 4 - LEAD + 1, Q1 = Q0 + 5;
+            static_assert(Q1 + 5 <= G::GROUPS, "both sequences end inside the period");
+            if (g == F0) emit.fetch(0);
+            if (g >= Q0 && g < Q0 + 4) emit.quantise(0, g - Q0, r.value(g - Q0));
+            if (g == Q0 + 4) emit.store(0);
+            if (g == F1) emit.fetch(1);
+            if (g >= Q1 && g < Q1 + 4) emit.quantise(1, g - Q1, r.value(4 + g - Q1));
+            if (g == Q1 + 4) emit.store(1);
         } else if (G::EMIT_SPREAD) {
             constexpr bool late = Emit::LATE && G::GROUPS >= G::EARLY_GROUPS + 12;
             constexpr int q0 = G::EARLY_GROUPS + (late ? 6 : 1);       // group of the first quantise call

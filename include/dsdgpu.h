@@ -109,7 +109,11 @@ const char* dsdgpu_last_error(const dsdgpu_ctx* ctx);
  *   in_stride is ignored for B != 0; the bytes are consumed where they lie, no host re-packing),
  * "dither_stride" (output samples per frame of the WHOLE
  * stream when this context only holds a channel subset of it: sample m of frame i, local channel
- * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default), "trace" (1: every
+ * c is dither_first_sample + i*dither_stride + c; 0 = nch, the default), "dither_cache" (samples, default 2^27 = 1 GiB
+ * of device memory at most, allocated as needed; 0 = off: the reference's dither stream comes from the unseeded
+ * process-global rand() and dsf2flac converts one file per process (dsd_decimator.cpp:203-204, main.cpp), so the dither
+ * term of output sample m is the same constant for every file; a context keeps the part of that plane it has generated
+ * and calls whose samples lie below the limit read it in place, generating only what is not there yet), "trace" (1: every
  * dsdgpu_decimate_host call prints the timeline of its chunks -- upload, kernel, download, from events
  * on the slot streams -- to stderr; for looking at the PCIe pipeline, off by default). Unknown keys are
  * an error. */

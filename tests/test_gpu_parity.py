@@ -138,6 +138,60 @@ def test_dither_stream_by_position(oracle):
     g.close()
 
 
+def test_dither_plane_cache(oracle):
+    """The context keeps the dither plane it has generated (dsdgpu_set_option "dither_cache"): calls that start inside it
+    read it in place, calls that reach past it generate the rest, a plane that is outgrown is copied, a call far into
+    the stream makes its own -- and every one of them draws what the reference draws at that position."""
+    fir, g = make(32, 1, 2)
+    data = seeded_bytes(2, 60000, 31)
+    scale, amp, clip = filters.app_params(24, dither=True)
+    nbits = 60000 * 8
+
+    def want(p0, n, first):
+        return oracle.run_raw(data, nbits, 1, DSD64, 88200, p0 + 1, n, scale, amp, clip, rand_skip=2 * first)   # p0 = pre_steps - 1
+
+    def got(p0, n, first, kind=capi.OUT_INT32):
+        return g.decimate_host(data, p0, n, scale, amp, clip, dither_first_sample=first, out_kind=kind)
+
+    launches = []
+    for p0, n, first in ((72, 3000, 0),              # fills samples [0, 6000)
+                         (72, 3000, 0),              # read in place: one launch less
+                         (72 + 4 * 1000, 2000, 2000),   # starts inside, ends inside
+                         (72 + 4 * 3000, 4000, 6000),   # starts at the end of the valid part: generates [6000, 14000)
+                         (72 + 4 * 500, 9000, 1001),    # odd first sample (the 16-byte dither loads fall back to 8-byte ones)
+                         (72, 14000, 0),                # reaches past the valid part again
+                         (72, 14000, 0)):               # ... and now lies inside it
+        before = g.launches
+        assert np.array_equal(got(p0, n, first), want(p0, n, first)), (p0, n, first)
+        launches.append(g.launches - before)
+    assert launches[1] == launches[0] - 1 and launches[2] == launches[1] and launches[3] == launches[0]
+    assert launches[4] == launches[0] and launches[5] == launches[0] and launches[6] == launches[1]
+    # a call far into the stream (a time shard) does not extend the plane
+    before = g.launches
+    assert np.array_equal(got(72, 3000, 5_000_000), want(72, 3000, 5_000_000))
+    assert g.launches - before == launches[0]
+    # a small limit: calls beyond it make their own plane; shrinking below the valid part drops the plane
+    g.set_option("dither_cache", 4096)
+    assert np.array_equal(got(72, 3000, 0), want(72, 3000, 0))
+    assert np.array_equal(got(72, 1000, 100), want(72, 1000, 100))
+    g.set_option("dither_cache", 0)
+    assert np.array_equal(got(72, 3000, 0), want(72, 3000, 0))
+    g.close()
+    # growth past the first allocation (2^22 samples): the valid part is carried over
+    fir, g = make(32, 1, 2)
+    n1 = 3000
+    assert np.array_equal(got(72, n1, 0), want(72, n1, 0))
+    d = seeded_bytes(2, 4 * 2_200_000 + 400, 32)
+    big = g.decimate_host(d, 72, 2_200_000, scale, amp, clip, dither_first_sample=0)       # 4.4 M samples > 2^22
+    head = oracle.run_raw(d, d.shape[1] * 8, 1, DSD64, 88200, 73, 5000, scale, amp, clip, rand_skip=0)
+    assert np.array_equal(big[:5000], head)
+    tail0 = 2_195_000
+    tail = oracle.run_raw(d, d.shape[1] * 8, 1, DSD64, 88200, 73 + 4 * tail0, 5000, scale, amp, clip, rand_skip=2 * 2 * tail0)
+    assert np.array_equal(big[tail0:], tail)
+    assert np.array_equal(got(72, n1, 0), want(72, n1, 0))
+    g.close()
+
+
 def test_device_pointers_and_stream(oracle):
     import torch
     fir, g = make(32, 1, 2)
