@@ -37,6 +37,7 @@ struct DecimateArgs {
     long long dither_stride; // samples per frame of the whole stream (>= nch)
     double scale, dither_amp, clip;
     double clip_hi;          // clip, or +infinity when clip <= 0 (no clipping): min / max instead of compare-and-select
+    int clip_lo_i, clip_hi_i;   // the same bounds after rounding: -round(clip), round(clip) saturated to int32; INT_MIN, INT_MAX without clipping
     double unit;             // 32-bit tables: value of one table unit (2^-qbits); 1.0 otherwise
     void* out;
     int out_kind;
@@ -432,6 +433,8 @@ struct RingEmitter {
     double vd[4];
     double iv[4];
     double dv[4];
+    double2 du, dw;              // dither terms as loaded (pair tiles), traded with the partner lane in settle()
+    bool wide;
     static constexpr bool LATE = DITHER;
 
     __device__ __forceinline__ RingEmitter(const DecimateArgs& a_, const RingDest& d_, const RingDest& nx_, int h_, unsigned out_low_bits)
@@ -453,16 +456,14 @@ struct RingEmitter {
             const double* ahead = a.dither + nx.fb * a.dither_stride + nx.c;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
         }
-        const bool wide = d.pair && ((a.dither_stride | d.c0) & 1) == 0 &&
-                          (reinterpret_cast<unsigned long long>(a.dither) & 15ULL) == 0;    // warp-uniform
+        wide = d.pair && ((a.dither_stride | d.c0) & 1) == 0 &&
+               (reinterpret_cast<unsigned long long>(a.dither) & 15ULL) == 0;    // warp-uniform
         if (wide) {
+            // loads only: the trade with the partner lane waits until the values are used (settle), so that the warp does
+            // not sit on the load latency here
             const long long f0 = d.fb + 2 * h, f1 = f0 + 1;
-            const double2 u = __ldg(reinterpret_cast<const double2*>(a.dither + (f0 < a.nframes ? f0 : 0) * a.dither_stride + d.c0));
-            const double2 v = __ldg(reinterpret_cast<const double2*>(a.dither + (f1 < a.nframes ? f1 : 0) * a.dither_stride + d.c0));
-            const double r0 = __shfl_xor_sync(0xffffffffu, h ? u.x : u.y, 16);
-            const double r1 = __shfl_xor_sync(0xffffffffu, h ? v.x : v.y, 16);
-            dv[0] = h ? r0 : u.x; dv[1] = h ? r1 : v.x;
-            dv[2] = h ? u.y : r0; dv[3] = h ? v.y : r1;
+            du = __ldg(reinterpret_cast<const double2*>(a.dither + (f0 < a.nframes ? f0 : 0) * a.dither_stride + d.c0));
+            dw = __ldg(reinterpret_cast<const double2*>(a.dither + (f1 < a.nframes ? f1 : 0) * a.dither_stride + d.c0));
             return;
         }
 #pragma unroll
@@ -471,22 +472,34 @@ struct RingEmitter {
             dv[k] = __ldg(a.dither + f * a.dither_stride + d.c);
         }
     }
+    // called once, right before the first quantise of the period
+    __device__ __forceinline__ void settle() {
+        if (!DITHER || !wide) return;
+        const double r0 = __shfl_xor_sync(0xffffffffu, h ? du.x : du.y, 16);
+        const double r1 = __shfl_xor_sync(0xffffffffu, h ? dw.x : dw.y, 16);
+        dv[0] = h ? r0 : du.x; dv[1] = h ? r1 : dw.x;
+        dv[2] = h ? du.y : r0; dv[3] = h ? dw.y : r1;
+    }
 
     __device__ __forceinline__ void quantise(int k, double sum) {
         if (OUT == 2) { vd[k] = sum; return; }
+        if (k == 0) settle();
         double x = __dmul_rn(sum, a.scale);
         if (DITHER) x = __dadd_rn(x, __dmul_rn(dv[k], a.dither_amp));
-        // clip (dsd_decimator.cpp:207-212): a.clip_hi is the clip amplitude, or +infinity when the caller passed none
-        x = fmin(fmax(x, -a.clip_hi), a.clip_hi);
         if (OUT == 1) {
-            vd[k] = x;
+            // clip (dsd_decimator.cpp:207-212): a.clip_hi is the clip amplitude, or +infinity when the caller passed none
+            vd[k] = fmin(fmax(x, -a.clip_hi), a.clip_hi);
         } else {
             // C round() -- half away from zero (dsd_decimator.cpp:213-214) -- as trunc(x + copysign(0.5 - 2^-54, x)): the
             // largest double below one half pushes every tie and nothing but the ties over the next integer.  Checked
             // against round() around every integer and every tie below 2^25, around all powers of two, and on 4e8
             // random doubles up to 2^52 (tools/check_round.c); the direct and segmented kernels keep libdevice's round(),
             // so every parity test that compares kernels compares the two.
-            vi[k] = __double2int_rz(__dadd_rn(x, copysign(0.49999999999999994, x)));
+            // The clip (dsd_decimator.cpp:207-212) comes AFTER the rounding, on the integer: round() is monotone, so
+            // round(min(max(x, -c), c)) = min(max(round(x), round(-c)), round(c)) for every x and c -- two integer
+            // min / max instead of two fp64 compare-and-select sequences per sample.
+            const int q = __double2int_rz(__dadd_rn(x, copysign(0.49999999999999994, x)));
+            vi[k] = min(max(q, a.clip_lo_i), a.clip_hi_i);
         }
     }
 

@@ -403,6 +403,11 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
     a.dither = nullptr; a.dither_stride = ctx->dither_stride > 0 ? ctx->dither_stride : ctx->nch;
     a.scale = scale; a.dither_amp = dither_amp; a.clip = clip;
     a.clip_hi = clip > 0.0 ? clip : HUGE_VAL;
+    {   // round(clip) as C round() does it, saturated like the kernels' double -> int conversion
+        const double rc = std::round(clip);
+        a.clip_hi_i = !(clip > 0.0) || rc >= 2147483647.0 ? INT32_MAX : (int)rc;
+        a.clip_lo_i = !(clip > 0.0) || rc > 2147483647.0 ? INT32_MIN : -(int)rc;
+    }
     a.unit = ctx->lut_unit;
     a.out = d_out; a.out_kind = out_kind;
     a.pcm_bytes = out_kind == DSDGPU_OUT_PCM24 ? 3 : out_kind == DSDGPU_OUT_PCM16 ? 2 : 0;

@@ -59,6 +59,46 @@ def test_fp64_sums_bit_exact_incl_idle_prefill(oracle, ratio, kernel):
     g.close()
 
 
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("ratio", [32, 8])
+def test_clip_amplitudes_of_every_kind(oracle, ratio, precision):
+    """The ring kernels clip AFTER rounding, on the integer (round() is monotone: round(clamp(x, -c, c)) =
+    clamp(round(x), round(-c), round(c))); the reference clips the double and rounds then (dsd_decimator.cpp:207-214).
+    Same integers for whole, fractional, half-way, tiny and beyond-int32 clip amplitudes, with and without dither,
+    int32 and packed output; the fp64 output keeps the clipped double itself."""
+    if precision == 32 and ratio != 32:
+        pytest.skip("32-bit tables exist for the divide-by-32 filter")
+    fir, g = make(ratio, 1, 2, "ring", precision)
+    data = seeded_bytes(2, 6000, 77 + ratio)
+    n = 5000 // fir.nstep
+    tol = precision == 32
+    for scale, clip, amp in ((9e7, 8388607.0, 0.0), (9e7, 8388607.0, 1.0), (3e3, 1000.5, 0.0), (3e3, 1000.49, 1.0),
+                             (3e3, 1001.7, 0.0), (40.0, 0.4, 0.0), (40.0, 0.5, 0.0), (40.0, 2.5, 1.0),
+                             # clip amplitudes at and beyond int32 (samples stay inside: the reference's cast of a larger
+                             # double is undefined behaviour in C++, the kernels saturate)
+                             (1e9, 3e9, 0.0), (1e9, 2147483647.2, 0.0), (1.5e9, 2147483646.5, 0.0), (1e9, 0.0, 0.0),
+                             (1e9, 2147483648.0, 2.0), (1.5e9, 1.9e9, 0.0)):
+        want = oracle.run_raw(data, 6000 * 8, 1, DSD64, RATES[ratio], fir.nlut + 1, n, scale, amp, clip)
+        got = g.decimate_host(data, fir.nlut, n, scale, amp, clip)
+        if tol:                 # 32-bit tables: a sum may differ in its last bits, a rounded sample by one
+            assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= max(1, scale * 4e-8), (scale, clip, amp)
+            if clip > 0:
+                assert np.abs(got.astype(np.int64)).max() <= np.abs(want.astype(np.int64)).max()
+        else:
+            assert np.array_equal(got, want), (scale, clip, amp)
+        if clip > 0:
+            wf = oracle.run_raw(data, 6000 * 8, 1, DSD64, RATES[ratio], fir.nlut + 1, n, scale, amp, clip, want="f64")
+            gf = g.decimate_host(data, fir.nlut, n, scale, amp, clip, out_kind=capi.OUT_FLOAT64)
+            if not tol:
+                assert gf.tobytes() == wf.tobytes(), (scale, clip, amp)
+    want = oracle.run_raw(data, 6000 * 8, 1, DSD64, RATES[ratio], fir.nlut + 1, n, 9e7, 1.0, 8388607.0)
+    got = g.decimate_host(data, fir.nlut, n, 9e7, 1.0, 8388607.0, out_kind=capi.OUT_PCM24)
+    q = got[..., 0].astype(np.int32) | (got[..., 1].astype(np.int32) << 8) | (got[..., 2].astype(np.int8).astype(np.int32) << 16)
+    if not tol:
+        assert np.array_equal(q, want)
+    g.close()
+
+
 @pytest.mark.parametrize("ratio,msb", [(r, m) for r in RATES for m in (0, 1)])
 def test_golden_vectors(ratio, msb):
     tag = f"r{ratio}_m{msb}"
