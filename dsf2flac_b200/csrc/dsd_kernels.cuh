@@ -422,17 +422,17 @@ struct RingDest {
 // OUT: 0 = int32 PCM, 1 = fp64 (scaled, dithered, clipped), 2 = the raw running sum into the planar plane
 // a.seg_raw (first pass of a two-pass filter), 3 = packed PCM of a.pcm_bytes (3 or 2) bytes per sample.
 // INIT: sums start from the planar plane a.seg_init (second pass).
-template <int OUT, bool DITHER, bool INIT>
+template <int OUT, bool DITHER, bool INIT, int KF = 4>
 struct RingEmitter {
     const DecimateArgs& a;
     RingDest d, nx;              // the frames being finished / the frames the lane starts in the next period
     int h;
     unsigned out_low_bits4;                // a.out & 3
     bool out_aligned16, out_aligned8;      // of a.out: the 16- and 8-byte stores below need them (a caller's device pointer may be a slice)
-    int vi[4];
-    double vd[4];
-    double iv[4];
-    double dv[4];
+    int vi[KF];
+    double vd[KF];
+    double iv[KF];
+    double dv[KF];
     double2 du, dw;              // dither terms as loaded (pair tiles), traded with the partner lane in settle()
     bool wide;
     static constexpr bool LATE = DITHER;
@@ -456,7 +456,7 @@ struct RingEmitter {
             const double* ahead = a.dither + nx.fb * a.dither_stride + nx.c;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
         }
-        wide = d.pair && ((a.dither_stride | d.c0) & 1) == 0 &&
+        wide = KF == 4 && d.pair && ((a.dither_stride | d.c0) & 1) == 0 &&
                (reinterpret_cast<unsigned long long>(a.dither) & 15ULL) == 0;    // warp-uniform
         if (wide) {
             // loads only: the trade with the partner lane waits until the values are used (settle), so that the warp does
@@ -467,18 +467,18 @@ struct RingEmitter {
             return;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < KF; ++k) {
             const long long f = d.fb + k < a.nframes ? d.fb + k : 0;     // keep the load in bounds
             dv[k] = __ldg(a.dither + f * a.dither_stride + d.c);
         }
     }
     // called once, right before the first quantise of the period
     __device__ __forceinline__ void settle() {
-        if (!DITHER || !wide) return;
+        if (!DITHER || KF != 4 || !wide) return;
         const double r0 = __shfl_xor_sync(0xffffffffu, h ? du.x : du.y, 16);
         const double r1 = __shfl_xor_sync(0xffffffffu, h ? dw.x : dw.y, 16);
-        dv[0] = h ? r0 : du.x; dv[1] = h ? r1 : dw.x;
-        dv[2] = h ? du.y : r0; dv[3] = h ? dw.y : r1;
+        dv[0] = h ? r0 : du.x; dv[1 % KF] = h ? r1 : dw.x;
+        dv[2 % KF] = h ? du.y : r0; dv[3 % KF] = h ? dw.y : r1;
     }
 
     __device__ __forceinline__ void quantise(int k, double sum) {
@@ -507,13 +507,16 @@ struct RingEmitter {
     __device__ __forceinline__ void prefetch() {
         if (!INIT) return;
         const double* src = a.seg_init + (long long)nx.c * a.plane_stride + nx.fb;
-        if (nx.fb + 3 < a.nframes) {
+        if (KF == 4 && nx.fb + 3 < a.nframes) {
             const double2 u = __ldg(reinterpret_cast<const double2*>(src));
             const double2 v = __ldg(reinterpret_cast<const double2*>(src) + 1);
-            iv[0] = u.x; iv[1] = u.y; iv[2] = v.x; iv[3] = v.y;
+            iv[0] = u.x; iv[1 % KF] = u.y; iv[2 % KF] = v.x; iv[3 % KF] = v.y;
+        } else if (KF == 2 && nx.fb + 1 < a.nframes) {
+            const double2 u = __ldg(reinterpret_cast<const double2*>(src));
+            iv[0] = u.x; iv[1 % KF] = u.y;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) iv[k] = nx.fb + k < a.nframes ? __ldg(src + k) : 0.0;
+            for (int k = 0; k < KF; ++k) iv[k] = nx.fb + k < a.nframes ? __ldg(src + k) : 0.0;
         }
     }
     __device__ __forceinline__ double init(int k) const { return INIT ? iv[k] : 0.0; }
@@ -522,12 +525,14 @@ struct RingEmitter {
         const long long fb = d.fb, nf = a.nframes;
         if (OUT == 2) {
             double* dst = a.seg_raw + (long long)d.c * a.plane_stride + fb;
-            if (fb + 3 < nf) {
-                reinterpret_cast<double2*>(dst)[0] = make_double2(vd[0], vd[1]);
-                reinterpret_cast<double2*>(dst)[1] = make_double2(vd[2], vd[3]);
+            if (KF == 4 && fb + 3 < nf) {
+                reinterpret_cast<double2*>(dst)[0] = make_double2(vd[0], vd[1 % KF]);
+                reinterpret_cast<double2*>(dst)[1] = make_double2(vd[2 % KF], vd[3 % KF]);
+            } else if (KF == 2 && fb + 1 < nf) {
+                reinterpret_cast<double2*>(dst)[0] = make_double2(vd[0], vd[1 % KF]);
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < KF; ++k)
                     if (fb + k < nf) dst[k] = vd[k];
             }
             return;
@@ -535,19 +540,19 @@ struct RingEmitter {
         if (OUT == 1) {
             double* out = reinterpret_cast<double*>(a.out);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < KF; ++k)
                 if (fb + k < nf) out[(fb + k) * a.nch + d.c] = vd[k];
             return;
         }
         if (OUT == 3) { store_packed(); return; }
         int32_t* out = reinterpret_cast<int32_t*>(a.out);
-        if (d.pair && (a.nch & 1) == 0) {
+        if (KF == 4 && d.pair && (a.nch & 1) == 0) {
             // trade halves: lane h=0 ends up with frames fb, fb+1 of both channels, lane h=1 with fb+2, fb+3
-            const int s0 = __shfl_xor_sync(0xffffffffu, h ? vi[0] : vi[2], 16);
-            const int s1 = __shfl_xor_sync(0xffffffffu, h ? vi[1] : vi[3], 16);
+            const int s0 = __shfl_xor_sync(0xffffffffu, h ? vi[0] : vi[2 % KF], 16);
+            const int s1 = __shfl_xor_sync(0xffffffffu, h ? vi[1 % KF] : vi[3 % KF], 16);
             const long long f = fb + 2 * h;
-            const int2 lo2 = h ? make_int2(s0, vi[2]) : make_int2(vi[0], s0);
-            const int2 hi2 = h ? make_int2(s1, vi[3]) : make_int2(vi[1], s1);
+            const int2 lo2 = h ? make_int2(s0, vi[2 % KF]) : make_int2(vi[0], s0);
+            const int2 hi2 = h ? make_int2(s1, vi[3 % KF]) : make_int2(vi[1 % KF], s1);
             if (a.nch == 2 && out_aligned16 && f + 1 < nf) {
                 *reinterpret_cast<int4*>(out + f * 2) = make_int4(lo2.x, lo2.y, hi2.x, hi2.y);
             } else if (out_aligned8) {
@@ -557,11 +562,11 @@ struct RingEmitter {
                 if (f < nf) { out[f * a.nch + d.c0] = lo2.x; out[f * a.nch + d.c0 + 1] = lo2.y; }
                 if (f + 1 < nf) { out[(f + 1) * a.nch + d.c0] = hi2.x; out[(f + 1) * a.nch + d.c0 + 1] = hi2.y; }
             }
-        } else if (a.nch == 1 && out_aligned16 && fb + 3 < nf) {
-            *reinterpret_cast<int4*>(out + fb) = make_int4(vi[0], vi[1], vi[2], vi[3]);
+        } else if (KF == 4 && a.nch == 1 && out_aligned16 && fb + 3 < nf) {
+            *reinterpret_cast<int4*>(out + fb) = make_int4(vi[0], vi[1 % KF], vi[2 % KF], vi[3 % KF]);
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < KF; ++k)
                 if (fb + k < nf) out[(fb + k) * a.nch + d.c] = vi[k];
         }
     }
@@ -574,12 +579,12 @@ struct RingEmitter {
         unsigned char* out = reinterpret_cast<unsigned char*>(a.out);
         const int B = a.pcm_bytes;
         const bool aligned4 = out_aligned8 || (out_low_bits4 == 0);
-        if (d.pair && (a.nch & 1) == 0) {
-            const int s0 = __shfl_xor_sync(0xffffffffu, h ? vi[0] : vi[2], 16);
-            const int s1 = __shfl_xor_sync(0xffffffffu, h ? vi[1] : vi[3], 16);
+        if (KF == 4 && d.pair && (a.nch & 1) == 0) {
+            const int s0 = __shfl_xor_sync(0xffffffffu, h ? vi[0] : vi[2 % KF], 16);
+            const int s1 = __shfl_xor_sync(0xffffffffu, h ? vi[1 % KF] : vi[3 % KF], 16);
             const long long f = fb + 2 * h;
-            const int2 lo2 = h ? make_int2(s0, vi[2]) : make_int2(vi[0], s0);
-            const int2 hi2 = h ? make_int2(s1, vi[3]) : make_int2(vi[1], s1);
+            const int2 lo2 = h ? make_int2(s0, vi[2 % KF]) : make_int2(vi[0], s0);
+            const int2 hi2 = h ? make_int2(s1, vi[3 % KF]) : make_int2(vi[1 % KF], s1);
             if (a.nch == 2 && aligned4 && f + 1 < nf) {
                 if (B == 3) {
                     const uint32_t q0 = (uint32_t)lo2.x & 0xffffffu, q1 = (uint32_t)lo2.y & 0xffffffu;
@@ -599,7 +604,7 @@ struct RingEmitter {
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < KF; ++k)
                 if (fb + k < nf) store_pcm(out, (fb + k) * a.nch + d.c, vi[k], B);
         }
     }
@@ -609,7 +614,7 @@ struct RingEmitter {
 // frames further on, driven as two staggered sequences.
 template <int OUT, bool DITHER>
 struct RingEmitterPair {
-    RingEmitter<OUT, DITHER, false> e0, e1;
+    RingEmitter<OUT, DITHER, false, 4> e0, e1;
     static constexpr bool LATE = DITHER;
     static __device__ __forceinline__ RingDest further(RingDest d) { d.fb += 4; return d; }
     __device__ __forceinline__ RingEmitterPair(const DecimateArgs& a, const RingDest& d, const RingDest& nx, int h, unsigned out_low_bits)
@@ -620,7 +625,7 @@ struct RingEmitterPair {
     __device__ __forceinline__ void prefetch() {}
     __device__ __forceinline__ double init(int) const { return 0.0; }
 };
-template <class G, int OUT, bool DITHER, bool INIT> struct RingEmitterOf { typedef RingEmitter<OUT, DITHER, INIT> type; };
+template <class G, int OUT, bool DITHER, bool INIT> struct RingEmitterOf { typedef RingEmitter<OUT, DITHER, INIT, G::KF> type; };
 template <int NW, int KR, int NL, int OUT, bool DITHER, bool INIT>
 struct RingEmitterOf<RingGeom<NW, KR, true, NL, 8>, OUT, DITHER, INIT> { typedef RingEmitterPair<OUT, DITHER> type; };
 
@@ -670,9 +675,9 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
     if constexpr (INIT && !G::PAIR) {   // second pass: the sums of the first tile's frames start from the plane
         const int c = h ? tl.c[1] : tl.c[0];
-        const long long fb = (h ? tl.f0[1] : tl.f0[0]) + 4LL * (16 * w + (l & 15));
+        const long long fb = (h ? tl.f0[1] : tl.f0[0]) + (long long)G::FPL * (16 * w + (l & 15));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < G::KF; ++k)
             lane.n[k] = fb + k < a.nframes ? (typename RingLane<G>::acc_t)a.seg_init[(long long)c * a.plane_stride + fb + k] : 0;
     }
     typedef typename RingEmitterOf<G, OUT, DITHER, INIT>::type Emitter;
@@ -731,7 +736,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     } else {
         emit.fetch();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) emit.quantise(k, lane.value(k));
+        for (int k = 0; k < G::KF; ++k) emit.quantise(k, lane.value(k));
         emit.store();
     }
 }

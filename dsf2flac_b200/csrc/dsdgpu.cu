@@ -100,6 +100,9 @@ using Ring12L = RingGeom<16, 16, false, 12, 1>; // the same with 16 rounds per t
                                                 // staging, barriers: once per tile and thread) weighs on 12-step periods -- 0.58 -> 0.70 of roofline
 static_assert(Ring12L::LUT_BYTES == Ring12::LUT_BYTES, "both read the same table image");
 using Ring64 = RingGeom<16, 1, false, 72, 8>;   // one pass (72 of 144 tables) of the divide-by-64 extension filter
+using Ring128 = RingGeom<16, 1, false, 72, 16>; // ... of the divide-by-128 filter (288 tables, four passes): two frames per lane, 16 bytes apart
+using Ring256 = RingGeom<16, 1, false, 72, 32>; // ... of the divide-by-256 filter (576 tables, eight passes): one frame per lane
+static_assert(Ring64::LUT_BYTES == Ring128::LUT_BYTES && Ring64::LUT_BYTES == Ring256::LUT_BYTES, "one image layout for all passes");
 
 int fail(dsdgpu_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_error;
@@ -241,23 +244,30 @@ int launch_ring(dsdgpu_ctx* ctx, const DecimateArgs& a, cudaStream_t st) {
     return dith ? launch_ring_variant<G, 0, true, INIT>(ctx, a, st) : launch_ring_variant<G, 0, false, INIT>(ctx, a, st);
 }
 
-// Decimation by 64 (EXTENSION filter, 144 tables): two passes of the ring kernel with 8-byte frame hop.
-// Pass 1 adds tables 0..71 and leaves the running sums in a planar fp64 plane; pass 2 starts from them,
-// adds tables 72..143 -- the byte of table 72 + t at frame position p is the byte of table t at p - 72 --
-// and finishes the samples.  The reference's sequential sum over all tables, cut once, bit for bit.
+// Decimation by 64 / 128 / 256 (EXTENSION filters, 144 / 288 / 576 tables): passes of the ring kernel over 72 tables each,
+// frames 8 / 16 / 32 bytes apart.  Pass 0 adds tables 0..71 and leaves the running sums in a planar fp64 plane; pass s
+// starts from them and adds tables 72s .. 72s+71 -- the byte of table 72s + t at frame position p is the byte of table t
+// at p - 72s -- in place (a lane reads the sums of its next frames a period before it writes those of its last ones,
+// and every sample belongs to one lane); the last pass finishes the samples.  The reference's sequential sum over all
+// tables, cut at table boundaries, bit for bit.
 template <class G>
-int launch_ring_two_pass(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+int launch_ring_passes(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, DecimateArgs a, cudaStream_t st) {
+    const int npass = ctx->nlut / G::NLUT;
     a.plane_stride = (a.nframes + 3) & ~3LL;
     int rc = ensure(ctx, &scratch.d_partial, &scratch.partial_cap, (size_t)a.plane_stride * a.nch * sizeof(double));
     if (rc) return rc;
-    DecimateArgs first = a;
-    first.lut = ctx->d_lut_ring;
-    first.seg_raw = scratch.d_partial;
-    first.dither = nullptr;
-    rc = launch_ring_variant<G, 2, false, false>(ctx, first, st);
-    if (rc) return rc;
-    a.lut = ctx->d_lut_ring + G::LUT_BYTES;
-    a.p0 -= G::NLUT;
+    DecimateArgs pass = a;
+    pass.seg_raw = scratch.d_partial;
+    pass.dither = nullptr;
+    for (int s = 0; s + 1 < npass; ++s) {
+        pass.lut = ctx->d_lut_ring + (size_t)s * G::LUT_BYTES;
+        pass.p0 = a.p0 - (long long)s * G::NLUT;
+        pass.seg_init = s > 0 ? scratch.d_partial : nullptr;
+        rc = s > 0 ? launch_ring_variant<G, 2, false, true>(ctx, pass, st) : launch_ring_variant<G, 2, false, false>(ctx, pass, st);
+        if (rc) return rc;
+    }
+    a.lut = ctx->d_lut_ring + (size_t)(npass - 1) * G::LUT_BYTES;
+    a.p0 -= (long long)(npass - 1) * G::NLUT;
     a.seg_init = scratch.d_partial;
     return launch_ring<G, true>(ctx, a, st);
 }
@@ -436,9 +446,11 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         kernel = ring_ok ? DSDGPU_KERNEL_RING
                : seg_samples_per_thread(ctx) > 0 ? DSDGPU_KERNEL_SEGMENTED : DSDGPU_KERNEL_DIRECT;
     if (kernel == DSDGPU_KERNEL_RING) {
-        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) or of the divide-by-64 extension (144/8), and tables without -0.0 entries");
+        if (!ring_ok) return fail(ctx, DSDGPU_ERR_ARG, "ring kernel needs the geometry of one of the reference's filters (72/4, 30/2, 12/1) or of the extension filters (144/8, 288/16, 576/32), and tables without -0.0 entries");
         a.lut = ctx->d_lut_ring;
-        if (ctx->nlut == 144) return launch_ring_two_pass<Ring64>(ctx, scratch, a, st);
+        if (ctx->nlut == 144) return launch_ring_passes<Ring64>(ctx, scratch, a, st);
+        if (ctx->nlut == 288) return launch_ring_passes<Ring128>(ctx, scratch, a, st);
+        if (ctx->nlut == 576) return launch_ring_passes<Ring256>(ctx, scratch, a, st);
         if (ctx->nlut == 30) return launch_ring<Ring30>(ctx, a, st);
         if (ctx->nlut == 12)      // long tiles where there are enough of them to keep every SM busy, short ones for short launches
             return ring_tile_count<Ring12L>(a.nframes, a.nch) >= 6LL * ctx->sm_count ? launch_ring<Ring12L>(ctx, a, st) : launch_ring<Ring12>(ctx, a, st);
@@ -541,11 +553,12 @@ int dsdgpu_create(dsdgpu_ctx** out, int device, int nch, int nlut, int nstep, co
     } else if (nlut == 12 && nstep == 1 && plain) {
         rimg.resize(Ring12::LUT_BYTES);
         ring_build_lut_image<Ring12>(tab.data(), rimg.data());
-    } else if (nlut == 144 && nstep == 8 && plain && lut_precision == 64) {
-        // divide-by-64 extension filter: one image per pass of 72 tables
-        rimg.resize(2 * (size_t)Ring64::LUT_BYTES);
-        ring_build_lut_image<Ring64>(tab.data(), rimg.data());
-        ring_build_lut_image<Ring64>(tab.data() + (size_t)72 * 256, rimg.data() + Ring64::LUT_BYTES);
+    } else if (((nlut == 144 && nstep == 8) || (nlut == 288 && nstep == 16) || (nlut == 576 && nstep == 32)) && plain && lut_precision == 64) {
+        // divide-by-64 / -128 / -256 extension filters: one image per pass of 72 tables (the same layout for all three)
+        const int npass = nlut / 72;
+        rimg.resize((size_t)npass * Ring64::LUT_BYTES);
+        for (int sidx = 0; sidx < npass; ++sidx)
+            ring_build_lut_image<Ring64>(tab.data() + (size_t)sidx * 72 * 256, rimg.data() + (size_t)sidx * Ring64::LUT_BYTES);
     }
     if (!rimg.empty()) {
         CREATE_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut_ring), rimg.size()));

@@ -100,7 +100,8 @@ struct RingGeom {
     static constexpr int COPIES = NLUT == 12 ? 4 : (NLUT == 30 || (Q32 && !PAIR)) ? 2 : 1;   // images of the tables (whatever fits shared memory)
     static constexpr int PERIOD = DUP ? 72 : COPIES == 4 ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
     static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
-    static constexpr int KF = 4;                      // consecutive chains (sums) per lane
+    // consecutive chains (sums) per lane: four, or as many as keep neighbouring lanes 32 bytes apart (frame hops of 16 / 32 bytes)
+    static constexpr int KF = NSTEP_ == 16 ? 2 : NSTEP_ == 32 ? 1 : 4;
     static constexpr int FPL = KF * FPC;              // consecutive output frames per lane
     static constexpr int FBYTES = NSTEP / FPC;        // stream bytes between successive output frames
     static constexpr int P_SHIFT = PAIR ? FBYTES : 0; // a chain sits at the position of the LATER of its two frames
@@ -126,8 +127,9 @@ struct RingGeom {
     static constexpr int NTPF = NTP * FPC;            // output frames per half per tile
     static constexpr int HOP = NSTEP * FR_PER_ROUND;  // bytes between a lane's rounds
     static constexpr int FRONT = 127;                 // buffer starts FRONT..FRONT+15 bytes before pmin
-    static constexpr int QH = NSTEP == 8 ? 6 : 3;     // window words of history: frame k reads NSTEP*k bytes further on
-    static constexpr int HALF_SHIFT = NSTEP == 8 ? 16 : COPIES > 1 ? 64 : 0;   // bank offset of the upper half-warp's buffer
+    static constexpr int QH = NSTEP >= 8 ? NSTEP * (KF - 1) / 4 : 3;   // window words of history: frame k reads NSTEP*k bytes further on
+    static constexpr int QHA = QH > 0 ? QH : 1;       // (array size)
+    static constexpr int HALF_SHIFT = LANE_BYTES == 32 ? 16 : COPIES > 1 ? 64 : 0;   // bank offset of the upper half-warp's buffer
     static constexpr int HALF_BYTES = NSTEP * NTP + 256 + HALF_SHIFT;
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
     static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
@@ -138,7 +140,7 @@ struct RingGeom {
     static constexpr bool EMIT_SHORT = !EMIT_SPREAD && LATE_GROUPS >= 1;     // quantise calls shared out over the late groups
     static constexpr int EMIT_PER_GROUP = EMIT_SHORT ? (4 + LATE_GROUPS - 1) / LATE_GROUPS : 0;
     static_assert(!Q32 || DUP || (PAIR && NLUT == 76), "32-bit tables exist for the 72-table filter (as 76 pair tables with an 8-byte hop)");
-    static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8, "frame hop of 8, 16, 32 or 64 DSD samples");
+    static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8 || NSTEP == 16 || NSTEP == 32, "frame hop of 8 ... 256 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
     static_assert(!PAIR || GROUPS >= EARLY_GROUPS + 15, "two emitter sequences fit the late groups");
     static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == HALF_SHIFT && ROW_BYTES % 128 == 0 && PERIOD % 4 == 0, "staging chunks / bank pattern");
@@ -306,9 +308,9 @@ RING_HD RingI2 ring_lds_i2(const unsigned char* smem, uint32_t off) {
 template <class G>
 struct RingLane {
     typedef typename RingAcc<G::Q32, G::PAIR>::type acc_t;
-    acc_t n[4];                 // sums of the frames started in the current period
-    acc_t p[4];                 // sums of the frames started in the previous period (final after EARLY_STEPS)
-    uint32_t qn[G::QH], qo[G::QH];   // previous window words of the current / the previous frame set
+    acc_t n[G::KF];             // sums of the frames started in the current period
+    acc_t p[G::KF];             // sums of the frames started in the previous period (final after EARLY_STEPS)
+    uint32_t qn[G::QHA], qo[G::QHA];   // previous window words of the current / the previous frame set
     uint32_t ln, lo;            // last aligned word loaded from either window
     uint32_t wlast;             // smem offset of word L(0) of the previous period's window
     // constants of the lane
@@ -352,9 +354,9 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
         r.sel[g] = v;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { ring_acc_clear(r.n[k]); ring_acc_clear(r.p[k]); }
+    for (int k = 0; k < G::KF; ++k) { ring_acc_clear(r.n[k]); ring_acc_clear(r.p[k]); }
 #pragma unroll
-    for (int i = 0; i < G::QH; ++i) { r.qo[i] = 0u; r.qn[i] = 0u; }
+    for (int i = 0; i < G::QHA; ++i) { r.qo[i] = 0u; r.qn[i] = 0u; }
     r.lo = r.ln = 0u;
     r.wlast = 1024u;            // first period: the "previous window" is table bytes (finite garbage, never emitted)
     return a0 - 3 - phi;
@@ -363,11 +365,11 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
 // The 4-byte windows of the lane's four frames for one group: frame k reads NSTEP*k bytes further
 // on than frame 0, i.e. the word stream v = V(g), q[0..2] = V(g-1..g-3) shifted by NSTEP*k bytes.
 template <class G>
-RING_HD void ring_slot_words(uint32_t v, const uint32_t (&q)[G::QH], uint32_t (&x)[4]) {
-    if constexpr (G::NSTEP == 8) {
-        x[0] = v; x[1] = q[1]; x[2] = q[3]; x[3] = q[5];
-    } else if (G::NSTEP == 4) {
-        x[0] = v; x[1] = q[0]; x[2] = q[1]; x[3] = q[2];
+RING_HD void ring_slot_words(uint32_t v, const uint32_t (&q)[G::QHA], uint32_t (&x)[G::KF]) {
+    if constexpr (G::NSTEP >= 4) {
+        x[0] = v;
+#pragma unroll
+        for (int k = 1; k < G::KF; ++k) x[k] = q[G::NSTEP * k / 4 - 1];
     } else if (G::NSTEP == 2) {
         x[0] = v; x[1] = ring_funnel_r(v, q[0], 16u); x[2] = q[0]; x[3] = ring_funnel_r(q[0], q[1], 16u);
     } else {
@@ -400,7 +402,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             constexpr int q0 = G::EARLY_GROUPS + (late ? 6 : 1);       // group of the first quantise call
             if (late && g == G::EARLY_GROUPS + 1) emit.fetch();
             if (!late && g == q0) emit.fetch();
-            if (g >= q0 && g < q0 + 4) emit.quantise(g - q0, r.value(g - q0));
+            if (g >= q0 && g < q0 + G::KF) emit.quantise(g - q0, r.value(g - q0));
             if (g == q0 + 4) emit.store();
             if (g == q0 + 5) emit.prefetch();
         } else if (G::EMIT_SHORT) {
@@ -408,12 +410,12 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             if (g == G::EARLY_GROUPS) emit.fetch();
             if (g >= G::EARLY_GROUPS) {
 #pragma unroll
-                for (int k = (g - G::EARLY_GROUPS) * G::EMIT_PER_GROUP; k < (g - G::EARLY_GROUPS + 1) * G::EMIT_PER_GROUP && k < 4; ++k)
+                for (int k = (g - G::EARLY_GROUPS) * G::EMIT_PER_GROUP; k < (g - G::EARLY_GROUPS + 1) * G::EMIT_PER_GROUP && k < G::KF; ++k)
                     emit.quantise(k, r.value(k));
             }
         }
         // window words: v[0] = V(g), v[1..3] = V(g-1..g-3); frame k reads the 4 bytes NSTEP*k further on
-        uint32_t x[4];
+        uint32_t x[G::KF];
         {
             const uint32_t a = wnew - 4u * (uint32_t)g;
             const uint32_t w = ring_lds_u32(smem, a);
@@ -423,7 +425,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             ring_slot_words<G>(v, r.qn, x);
 #pragma unroll
             for (int i = G::QH - 1; i > 0; --i) r.qn[i] = r.qn[i - 1];
-            r.qn[0] = v;
+            if (G::QH > 0) r.qn[0] = v;
         }
         if (g < G::EARLY_GROUPS) {
             const uint32_t a = wold - 4u * (uint32_t)(G::GROUPS + g);
@@ -431,13 +433,13 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             tr.word(tid, period, 2 * g + 1, a);
             const uint32_t v = ring_funnel_r(w, r.lo, r.shift);
             r.lo = w;
-            uint32_t y[4];
+            uint32_t y[G::KF];
             ring_slot_words<G>(v, r.qo, y);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = ring_prmt(x[k], y[k], r.sel[g]);
+            for (int k = 0; k < G::KF; ++k) x[k] = ring_prmt(x[k], y[k], r.sel[g]);
 #pragma unroll
             for (int i = G::QH - 1; i > 0; --i) r.qo[i] = r.qo[i - 1];
-            r.qo[0] = v;
+            if (G::QH > 0) r.qo[0] = v;
         }
         int32_t pend[4] = {0, 0, 0, 0};
         RingI2 pend2[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
@@ -457,7 +459,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 to_p = 1 - to_n;
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < G::KF; ++k) {
                 uint32_t e;
                 if (u == 0) e = ring_byte<3>(x[k]);
                 else if (u == 1) e = ring_byte<2>(x[k]);
@@ -547,7 +549,7 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
     if constexpr (!G::EMIT_SPREAD && !G::EMIT_SHORT) {   // shortest periods: the whole emitter before the remaining steps
         emit.fetch();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) emit.quantise(k, r.value(k));
+        for (int k = 0; k < G::KF; ++k) emit.quantise(k, r.value(k));
         emit.store();
         emit.prefetch();
     }
@@ -557,7 +559,7 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
         emit.prefetch();
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < G::KF; ++k) {
         r.p[k] = r.n[k];
         if constexpr (G::PAIR) ring_acc_clear(r.n[k]);
         else r.n[k] = (typename RingLane<G>::acc_t)emit.init(k);

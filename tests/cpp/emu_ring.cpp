@@ -120,7 +120,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         void store(int q) { if ((got >> (4 * q) & 15) == 15) ++stored; }
     };
     // multi-pass geometry (NSTEP = 8): every frame's sum starts from a value left by "the previous pass"
-    const bool use_init = (G::NSTEP == 8) && !G::PAIR;
+    const bool use_init = (G::NSTEP >= 8) && !G::PAIR;
     auto init_of = [&](int c, long long f) -> double {
         if (!use_init || f >= nframes) return 0.0;
         unsigned x = (unsigned)(c * 2654435761u) ^ (unsigned)(f * 40503u + 17u);
@@ -163,7 +163,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
             const RingTile t0 = ring_tile_at<G>(tile, nframes, nch);
             for (int tid = 0; tid < G::NTHR; ++tid) {
                 const int l = tid & 31, w = tid >> 5, h = l >> 4;
-                for (int k = 0; k < 4; ++k) lanes[tid].n[k] = (typename RingLane<G>::acc_t)init_of(t0.c[h], t0.f0[h] + 4LL * (16 * w + (l & 15)) + k);
+                for (int k = 0; k < G::KF; ++k) lanes[tid].n[k] = (typename RingLane<G>::acc_t)init_of(t0.c[h], t0.f0[h] + (long long)FPL * (16 * w + (l & 15)) + k);
             }
         }
         while (tile < ntiles) {
@@ -189,7 +189,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                         long long fbn = nframes; int cn = 0;
                         if (n + 1 < G::KR) { fbn = tl.f0[h] + (long long)FPL * ((long long)(n + 1) * G::BLK_PER_ROUND + 16 * w + (l & 15)); cn = tl.c[h]; }
                         else if (next < ntiles) { const RingTile tn = ring_tile_at<G>(next, nframes, nch); fbn = tn.f0[h] + (long long)FPL * (16 * w + (l & 15)); cn = tn.c[h]; }
-                        for (int k = 0; k < 4; ++k) col.iv[k] = init_of(cn, fbn + k);
+                        for (int k = 0; k < G::KF; ++k) col.iv[k] = init_of(cn, fbn + k);
                     }
                     ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, col, rec);
                     if (col.got != (1 << FPL) - 1 || col.stored != G::FPC || col.fetched != 1 || col.early != G::FPC) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
@@ -249,6 +249,8 @@ int main(int argc, char** argv) {
     if (nwarp == 12 && kr == 2) return run<RingGeom<16, 2, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "12": /8 filter
     if (nwarp == 12 && kr == 16) return run<RingGeom<16, 16, false, 12, 1>>(nframes, nch, p0, in_first, in_count, seed, grid);  // its long-tile instance
     if (nwarp == 64 && kr == 1) return run<RingGeom<16, 1, false, 72, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "64": one pass of the /64 extension
+    if (nwarp == 128 && kr == 1) return run<RingGeom<16, 1, false, 72, 16>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "128": one pass of the /128 extension: two frames per lane
+    if (nwarp == 256 && kr == 1) return run<RingGeom<16, 1, false, 72, 32>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "256": one pass of the /256 extension: one frame per lane
     if (nwarp == 76 && kr == 1) return run<RingGeom<16, 1, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "76": the product's 32-bit geometry (frame pairs)
     if (nwarp == 76 && kr == 2) return run<RingGeom<16, 2, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);
     if (nwarp == 32 && kr == 1) return run<RingGeom<16, 1, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // the product's 32-bit geometry

@@ -47,6 +47,14 @@ EMU = os.path.join(os.path.dirname(__file__), "cpp", "_build", "emu_ring")
     (64, 1, 3000, 1, 72, 5, 24000, 2, 1),
     (64, 1, 9000, 6, 79, 16, 70000, 5, 2),
     (64, 1, 9000, 2, 72, 0, 73000, 4, 2),        # frame grid off by one byte: window loads two-way
+    (128, 1, 5000, 2, 75, 0, 81000, 4, 2),       # nwarp "128" = one pass of the divide-by-128 extension: 16-byte frame hop,
+    (128, 1, 3000, 3, -1, 0, 49000, 3, 3),       #   two frames per lane (lanes stay 32 bytes apart), four history words
+    (128, 1, 1500, 1, 72, 5, 24000, 2, 1),
+    (128, 1, 5000, 6, 79, 16, 80000, 5, 2),
+    (256, 1, 2500, 2, 75, 0, 81000, 4, 2),       # nwarp "256" = one pass of the divide-by-256 extension: 32-byte frame hop,
+    (256, 1, 1500, 3, -1, 0, 49000, 3, 3),       #   one frame per lane, no history words
+    (256, 1, 700, 1, 72, 5, 24000, 2, 1),
+    (256, 1, 2500, 6, 79, 16, 80000, 5, 2),
 ])
 def test_ring_lanes(nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid):
     r = subprocess.run([EMU, *map(str, (nwarp, kr, nframes, nch, p0, in_first, in_count, seed, grid))],
