@@ -49,13 +49,7 @@ namespace dsdgpu {
 //              for the reference's filters) and stored as int32; a frame's sum is then an EXACT
 //              integer sum -- order independent, so it does not depend on how frames are cut into
 //              tiles or shards -- converted to fp64 once per frame.  |error| <= 72 * 2^-31 before
-//              scaling (3e-8 of full scale; BASELINE's fp32 variant allows 1e-6).  A 4-byte entry
-//              halves the shared-memory traffic; all 32 lanes of a warp form one skew group (one
-//              LDS.32 = one 128-byte wavefront), rows are 96 slots = 384 B with THREE extra
-//              copies of taps 64..71: a wrapped lane whose lower neighbour in its residue class
-//              (j - 8) has already restarted reads slot tap + 8*(j >> 3), which puts it on the
-//              bank nobody else can be on.  Two images of the (half-size) tables, the second shifted by 16
-//              slots: 16 distinct skews instead of 32 (see "short filters" below), so 16 early steps of 72.
+//              scaling (3e-8 of full scale; BASELINE's fp32 variant allows 1e-6).
 //
 // Frame pairs (Q32 = true, NLUT = 76, NSTEP = 8: the product's 32-bit geometry).  Frame A + 1 of the divide-by-32 filter
 //              reads at its tap t + 4 the byte frame A reads at tap t, so ONE 8-byte entry
@@ -89,7 +83,7 @@ struct RingGeom {
     static constexpr bool Q32 = Q32_;
     static constexpr int NLUT = NLUT_;                // tables
     static constexpr int NSTEP = NSTEP_;              // bytes between successive frames
-    static constexpr bool PAIR = Q32 && NSTEP_ == 8;   // 32-bit tables, two frames per 8-byte entry (see "Frame pairs" above)
+    static constexpr bool PAIR = Q32;                 // 32-bit tables: two frames per 8-byte entry (see "Frame pairs" above)
     static constexpr int FPC = PAIR ? 2 : 1;          // output frames per chain (per sum a lane carries)
     // Exact integer sums do not care about the order of their terms: a lane that is j taps behind spends its first j
     // steps on the LAST j taps of the frames it is starting (bytes further back in its own window) instead of finishing
@@ -97,7 +91,7 @@ struct RingGeom {
     // early steps, no window shared between neighbouring tiles and no drain.
     static constexpr bool ROTATE = PAIR;
     static constexpr bool DUP = (NLUT == 72);         // 72-step periods with tail copies (see above)
-    static constexpr int COPIES = NLUT == 12 ? 4 : (NLUT == 30 || (Q32 && !PAIR)) ? 2 : 1;   // images of the tables (whatever fits shared memory)
+    static constexpr int COPIES = NLUT == 12 ? 4 : NLUT == 30 ? 2 : 1;   // images of the tables (whatever fits shared memory)
     static constexpr int PERIOD = DUP ? 72 : COPIES == 4 ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
     static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
     // consecutive chains (sums) per lane: four, or as many as keep neighbouring lanes 32 bytes apart (frame hops of 16 / 32 bytes)
@@ -108,13 +102,12 @@ struct RingGeom {
     static constexpr int KR = KR_;                    // rounds (periods) per tile
     static constexpr int NWARP = NWARP_;
     static constexpr int NTHR = 32 * NWARP;
-    static constexpr int ELEM = (Q32 && !PAIR) ? 4 : 8;   // bytes per table entry
-    static constexpr bool Q32_PAIRS = true;           // 32-bit tables: accumulate two lookups per IADD3 in the late steps
-    static constexpr int SKEW_LANES = (Q32 && !PAIR) ? 32 : 16;  // lanes of one conflict-free load
+    static constexpr int ELEM = 8;                    // bytes per table entry: a double, or the two int32 of a frame pair
+    static constexpr int SKEW_LANES = 16;             // lanes of one conflict-free load (LDS.64: a half-warp)
     static constexpr int NSKEW = SKEW_LANES / COPIES; // distinct skew values
     static constexpr int EARLY_GROUPS = (NSKEW + 3) / 4;  // 4-step groups in which some lane is still wrapped
     static constexpr int EARLY_STEPS = NSKEW;
-    static constexpr int ROW = (Q32 && !PAIR) ? 96 : (DUP ? 80 : (PERIOD + 15) / 16 * 16);   // slots per table row
+    static constexpr int ROW = DUP ? 80 : (PERIOD + 15) / 16 * 16;   // slots per table row
     static constexpr int ROW_BYTES = ROW * ELEM;      // a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
     static constexpr int COPY_STRIDE = 256 * ROW_BYTES + (COPIES > 1 ? 128 : 0);   // image a: + a * (COPY_STRIDE + ELEM * NSKEW)
@@ -139,7 +132,7 @@ struct RingGeom {
     static constexpr int LATE_GROUPS = GROUPS - EARLY_GROUPS;
     static constexpr bool EMIT_SHORT = !EMIT_SPREAD && LATE_GROUPS >= 1;     // quantise calls shared out over the late groups
     static constexpr int EMIT_PER_GROUP = EMIT_SHORT ? (4 + LATE_GROUPS - 1) / LATE_GROUPS : 0;
-    static_assert(!Q32 || DUP || (PAIR && NLUT == 76), "32-bit tables exist for the 72-table filter (as 76 pair tables with an 8-byte hop)");
+    static_assert(!Q32 || (NLUT == 76 && NSTEP == 8), "32-bit tables exist for the 72-table filter: 76 pair tables with an 8-byte hop");
     static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8 || NSTEP == 16 || NSTEP == 32, "frame hop of 8 ... 256 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
     static_assert(!PAIR || GROUPS >= EARLY_GROUPS + 15, "two emitter sequences fit the late groups");
@@ -182,24 +175,11 @@ RING_HD uint32_t ring_lds_u32(const unsigned char* smem, uint32_t off) {
 RING_HD double ring_lds_f64(const unsigned char* smem, uint32_t off) {
     return *reinterpret_cast<const double*>(smem + off);
 }
-RING_HD int32_t ring_lds_i32(const unsigned char* smem, uint32_t off) {
-    return *reinterpret_cast<const int32_t*>(smem + off);
-}
 RING_HD double ring_add(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(a, b);
 #else
     return a + b;
-#endif
-}
-// a * m + b on the integer multiply-add pipe (never rewritten into add / select by the compiler)
-RING_HD int32_t ring_imad(int32_t a, int32_t m, int32_t b) {
-#if defined(__CUDA_ARCH__)
-    int32_t r;
-    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(m), "r"(b));
-    return r;
-#else
-    return (int32_t)((uint32_t)a * (uint32_t)m + (uint32_t)b);
 #endif
 }
 RING_HD double ring_fma(double a, double m, double b) {
@@ -243,25 +223,9 @@ struct RingNoEmit {
 // LDS.64); across the warp the quarter (j >> 2) is arranged so that the 32 window words of one
 // LDS.32 -- lane stride 16 B plus j bytes -- fall in 32 distinct banks when the frame grid is 4-byte
 // aligned to the tile.
-// 32-bit tables: the 32 values are a permutation of 0..31.  Window word of lane l = 4*l + (j >> 2),
-// now with j >> 2 up to 7, i.e. possibly one 4-word group further on: in every group of four lanes
-// {g, g+8, g+16, g+24} two stay (j >> 2 in {0,1} or {2,3}) and two move on (j >> 2 in {4,5} or {6,7}),
-// alternating with g, so that each group of four banks receives exactly the columns the
-// neighbouring group vacates.
 template <class G>
 RING_HD int ring_lane_skew(int l) {
     const int h = (l >> 4) & 1, i = l & 15;
-    if (G::PAIR) return i;                              // lane stride of eight words, like the divide-by-64 pass
-    if (G::Q32 && G::COPIES > 1) {
-        // 16 skews, each used by one lane of either image (ring_lane_image); the window word of lane (h, i) is
-        // 4*i + (j >> 2): the four lanes that share 4*i mod 32 -- (h, i), (h, i ^ 8) for h = 0, 1 -- get the four values of j >> 2
-        return 4 * (2 * h + (i >> 3)) + (i & 3);
-    }
-    if (G::Q32) {
-        const int g = l & 7, r = (l >> 3) & 3;
-        const int q = ((g & 1) ? 2 : 0) + (r & 1) + ((r >> 1) ? 4 : 0);
-        return (g >> 1) + 4 * q;
-    }
     if (G::COPIES > 1) return i / G::COPIES;            // image i % COPIES (ring_lane_image); see the top of this file
     if (G::LANE_BYTES == 32) return i;                  // lane stride of eight words (see the top of this file)
     if (G::LANE_BYTES == 8) {
@@ -280,15 +244,13 @@ template <class G>
 RING_HD int ring_lane_image(int l) {
     const int i = l & 15;
     if (G::COPIES == 1) return 0;
-    return G::Q32 ? (i >> 2) & 1 : i % G::COPIES;
+    return i % G::COPIES;
 }
 
 struct RingI2 { int32_t x, y; };                      // the two sums of a chain of the pair geometry: frames A, A + 1
-template <bool Q32, bool PAIR> struct RingAcc { typedef double type; };
-template <> struct RingAcc<true, false> { typedef int32_t type; };
-template <> struct RingAcc<true, true> { typedef RingI2 type; };
+template <bool Q32> struct RingAcc { typedef double type; };
+template <> struct RingAcc<true> { typedef RingI2 type; };
 RING_HD void ring_acc_clear(double& a) { a = 0.0; }
-RING_HD void ring_acc_clear(int32_t& a) { a = 0; }
 RING_HD void ring_acc_clear(RingI2& a) { a.x = 0; a.y = 0; }
 RING_HD RingI2 ring_lds_i2(const unsigned char* smem, uint32_t off) {
 #if defined(__CUDACC__)
@@ -307,7 +269,7 @@ RING_HD RingI2 ring_lds_i2(const unsigned char* smem, uint32_t off) {
 // tiles, a lane finishes the last frames of one tile during the first steps of the next.
 template <class G>
 struct RingLane {
-    typedef typename RingAcc<G::Q32, G::PAIR>::type acc_t;
+    typedef typename RingAcc<G::Q32>::type acc_t;
     acc_t n[G::KF];             // sums of the frames started in the current period
     acc_t p[G::KF];             // sums of the frames started in the previous period (final after EARLY_STEPS)
     uint32_t qn[G::QHA], qo[G::QHA];   // previous window words of the current / the previous frame set
@@ -319,8 +281,6 @@ struct RingLane {
     uint32_t lnew, lwrap, lalt; // table offset at static step 0: current frames / wrapped frames; step to the tail copy
     uint32_t sel[G::EARLY_GROUPS];   // byte selectors mixing the two windows in the early groups
     double unit;                // value of one unit of acc_t (1.0, or 2^-qbits for 32-bit tables)
-    int one;                    // 1, in a register the compiler cannot see through: x * one + acc issues on
-                                // the multiply-add pipe instead of the integer ALU the byte extraction keeps busy
     // finished sum of output frame k of the lane (k < FPL), exact: |p| < 2^31
     RING_HD double value(int k) const {
         if constexpr (G::PAIR) return (double)((k & 1) ? p[k >> 1].y : p[k >> 1].x) * unit;
@@ -339,7 +299,6 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     const int phi = (a0 + 1) & 3;
     r.j = j;
     r.unit = unit;
-    r.one = unit > 0.0 ? 1 : 0;
     r.shift = 8u * (uint32_t)phi;
     const int image = ring_lane_image<G>(l);
     const int base = G::GUARD_BYTES + image * (G::COPY_STRIDE + G::ELEM * G::NSKEW);
@@ -441,13 +400,11 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             for (int i = G::QH - 1; i > 0; --i) r.qo[i] = r.qo[i - 1];
             if (G::QH > 0) r.qo[0] = v;
         }
-        int32_t pend[4] = {0, 0, 0, 0};
         RingI2 pend2[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
             bool cur = true;
-            int to_n = 1, to_p = 0;
             if (s < G::EARLY_STEPS) {
                 // wrapped lanes (s < j) still add to their previous frames; multipliers route each
                 // table value into exactly one of the two sums without a select: fma(x, 1, acc) is
@@ -455,8 +412,6 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 if (G::DUP && s + 8 < G::EARLY_STEPS && r.j == s + 8) loff += r.lalt;   // taps 64..71 from this lane's tail copy
                 cur = (s >= r.j);
                 if (r.j == s) loff = r.lnew;                     // tap 0 of the next frame set
-                to_n = cur ? 1 : 0;
-                to_p = 1 - to_n;
             }
 #pragma unroll
             for (int k = 0; k < G::KF; ++k) {
@@ -469,27 +424,11 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
                 tr.lut(tid, period, s, k, addr);
                 if constexpr (G::PAIR) {
                     const RingI2 v = ring_lds_i2(smem, addr);
-                    if (s < G::EARLY_STEPS && !G::ROTATE) {
-                        r.n[k].x = ring_imad(v.x, to_n, r.n[k].x); r.n[k].y = ring_imad(v.y, to_n, r.n[k].y);
-                        r.p[k].x = ring_imad(v.x, to_p, r.p[k].x); r.p[k].y = ring_imad(v.y, to_p, r.p[k].y);
-                    } else if ((u & 1) == 0) {
+                    if ((u & 1) == 0) {
                         pend2[k] = v;            // two entries per three-input add (exact integer sums: any order)
                     } else {
                         r.n[k].x = r.n[k].x + pend2[k].x + v.x;
                         r.n[k].y = r.n[k].y + pend2[k].y + v.y;
-                    }
-                } else if constexpr (G::Q32) {
-                    const int32_t v = ring_lds_i32(smem, addr);
-                    if (s < G::EARLY_STEPS) {
-                        r.n[k] = ring_imad(v, to_n, r.n[k]);
-                        r.p[k] = ring_imad(v, to_p, r.p[k]);
-                    } else if (G::Q32_PAIRS) {
-                        // two table values per three-input add: 3.5 instead of 4 instructions per lookup (the sums are
-                        // exact integers, so the order does not matter)
-                        if ((u & 1) == 0) pend[k] = v;
-                        else r.n[k] = r.n[k] + pend[k] + v;
-                    } else {
-                        r.n[k] = ring_imad(v, r.one, r.n[k]);
                     }
                 } else {
                     const double v = ring_lds_f64(smem, addr);
@@ -621,9 +560,7 @@ RING_HD RingTile ring_tile_at(long long tile, long long nframes, int nch) {
 template <class G>
 inline void ring_build_lut_image(const double* lut, unsigned char* image, double unit = 1.0) {
     for (int i = 0; i < G::LUT_BYTES; ++i) image[i] = 0;
-    if (!G::Q32)                                        // pad slots: -0.0, the identity of fp64 addition
-        for (int i = 0; i < G::LUT_BYTES / 8; ++i) reinterpret_cast<double*>(image)[i] = -0.0;
-    if constexpr (G::PAIR) {
+    if constexpr (G::Q32) {
         // lut is the filter's own [72][256]; slot tau of row e = (LUT[tau - 4][e], LUT[tau][e]), zero outside the filter
         for (int e = 0; e < 256; ++e)
             for (int tau = 0; tau < G::NLUT; ++tau) {
@@ -631,12 +568,12 @@ inline void ring_build_lut_image(const double* lut, unsigned char* image, double
                 at[0] = tau >= G::FBYTES ? (int32_t)(lut[(tau - G::FBYTES) * 256 + e] / unit) : 0;
                 at[1] = tau < G::NLUT - G::FBYTES ? (int32_t)(lut[tau * 256 + e] / unit) : 0;
             }
-        return;
+        return;                                           // (pad slots stay 0)
     }
+    for (int i = 0; i < G::LUT_BYTES / 8; ++i) reinterpret_cast<double*>(image)[i] = -0.0;   // pad slots: the identity of fp64 addition
     auto put = [&](int image_no, int e, int slot, double v) {
         unsigned char* at = image + G::GUARD_BYTES + image_no * (G::COPY_STRIDE + G::ELEM * G::NSKEW) + e * G::ROW_BYTES + slot * G::ELEM;
-        if (G::Q32) *reinterpret_cast<int32_t*>(at) = (int32_t)(v / unit);
-        else *reinterpret_cast<double*>(at) = v;
+        *reinterpret_cast<double*>(at) = v;
     };
     for (int c = 0; c < G::COPIES; ++c)
         for (int e = 0; e < 256; ++e) {

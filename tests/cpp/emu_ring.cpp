@@ -15,7 +15,7 @@
 // Prints one JSON line; exit code 0 iff all sums match, coverage is exact and every table load
 // is conflict free.
 //
-// usage: emu_ring <nwarp:16|8, or 32 = 16 warps with 32-bit tables> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed> <grid>
+// usage: emu_ring <geometry: 16|8 warps of the /32 filter, or 30, 12, 64, 128, 256 (other filters), 76 (32-bit tables)> <kr> <nframes> <nch> <p0> <in_first> <in_count> <seed> <grid>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -192,7 +192,7 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
                         for (int k = 0; k < G::KF; ++k) col.iv[k] = init_of(cn, fbn + k);
                     }
                     ring_tail<G>(lanes[tid], smem.data(), wnew, loff[tid], tid, period, col, rec);
-                    if (col.got != (1 << FPL) - 1 || col.stored != G::FPC || col.fetched != 1 || col.early != G::FPC) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
+                    if (col.got != (1 << FPL) - 1 || col.stored != G::FPC || col.fetched != (G::PAIR ? 0 : 1) || col.early != G::FPC) { fprintf(stderr, "emitter protocol broken\n"); return 2; }
                     if (have_prev) check(prev[tid], col.sums, tid);
                     prev[tid] = {tl.f0[h] + (long long)FPL * ((long long)n * G::BLK_PER_ROUND + 16 * w + (l & 15)), tl.c[h]};
                 }
@@ -253,9 +253,6 @@ int main(int argc, char** argv) {
     if (nwarp == 256 && kr == 1) return run<RingGeom<16, 1, false, 72, 32>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "256": one pass of the /256 extension: one frame per lane
     if (nwarp == 76 && kr == 1) return run<RingGeom<16, 1, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "76": the product's 32-bit geometry (frame pairs)
     if (nwarp == 76 && kr == 2) return run<RingGeom<16, 2, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);
-    if (nwarp == 32 && kr == 1) return run<RingGeom<16, 1, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // the product's 32-bit geometry
-    if (nwarp == 32 && kr == 2) return run<RingGeom<16, 2, true>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "32": 32-bit tables
-    if (nwarp == 32 && kr == 3) return run<RingGeom<16, 3, true>>(nframes, nch, p0, in_first, in_count, seed, grid);
     fprintf(stderr, "unsupported geometry\n");
     return 64;
 }

@@ -23,10 +23,6 @@ EMU = os.path.join(os.path.dirname(__file__), "cpp", "_build", "emu_ring")
     (8, 6, 9000, 6, 75, 3, 37000, 5, 2),         # 5.1, unaligned in_first, 8-warp geometry
     (16, 3, 1, 2, 72, 0, 100, 7, 4),             # a single frame
     (16, 2, 30000, 2, 75, 0, 121000, 8, 3),      # two rounds per tile, 5 tiles per CTA, aligned
-    (32, 2, 30000, 2, 75, 0, 121000, 8, 3),      # nwarp "32" = 32-bit tables: 32-lane skew, three tail copies
-    (32, 2, 20000, 2, 72, 0, 81000, 1, 2),
-    (32, 3, 15000, 3, -1, 0, 61000, 3, 3),
-    (32, 2, 9000, 6, 75, 3, 37000, 5, 2),
     (76, 1, 20000, 2, 75, 0, 81000, 8, 3),       # nwarp "76" = the product's 32-bit geometry: two frames per 8-byte entry,
     (76, 1, 20000, 2, 72, 0, 81000, 1, 2),       #   76 pair tables, chains 8 bytes apart, eight frames per lane
     (76, 1, 15000, 3, -1, 0, 61000, 3, 3),
