@@ -373,15 +373,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
 // bytes; the other 511 threads just arrive.  (What a tile costs a thread besides its table loads -- the staging loop,
 // its 64-bit geometry -- is per period for the instances with one round per tile.)  Other tiles: every thread copies its
 // 16-byte chunks (cp.async; edges byte by byte with the fill value) and arrives when they have landed.
+// rel0: source offset (from a.in_first) of byte 0 of a half buffer whose first frame is frame 0 -- a half that starts at
+// frame f0 lies f0 * FBYTES further on (whole 16-byte chunks: ring_half_origin).
 template <class G>
 __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const RingTile& tl, unsigned char* dst,
-                                                bool aligned16, uint64_t* full_bar) {
+                                                bool aligned16, uint64_t* full_bar, long long rel0) {
     constexpr int CHUNKS = G::HALF_BYTES / 16;
     if (aligned16 && a.block_shift < 0) {
-        long long t0[2]; int a_tile;
-        ring_half_origin<G>(a.p0, a.in_first, tl.f0[0], t0[0], a_tile);
-        ring_half_origin<G>(a.p0, a.in_first, tl.f0[1], t0[1], a_tile);
-        const long long o0 = t0[0] - a.in_first, o1 = t0[1] - a.in_first;
+        const long long o0 = rel0 + tl.f0[0] * G::FBYTES, o1 = rel0 + tl.f0[1] * G::FBYTES;
         if (o0 >= 0 && o1 >= 0 && o0 + G::HALF_BYTES <= a.in_count && o1 + G::HALF_BYTES <= a.in_count) {   // CTA-uniform
             if (threadIdx.x == 0) {
                 mbar_arrive_expect_tx(full_bar, 2u * G::HALF_BYTES);
@@ -396,10 +395,8 @@ __device__ __forceinline__ void ring_stage_tile(const DecimateArgs& a, const Rin
     for (int k = threadIdx.x; k < 2 * CHUNKS; k += G::NTHR) {
         const int h = k >= CHUNKS ? 1 : 0;
         const int kk = k - h * CHUNKS;
-        long long t0; int a_tile;
-        ring_half_origin<G>(a.p0, a.in_first, h ? tl.f0[1] : tl.f0[0], t0, a_tile);
         const int c = h ? tl.c[1] : tl.c[0];
-        const long long o = t0 - a.in_first + 16LL * kk;
+        const long long o = rel0 + (h ? tl.f0[1] : tl.f0[0]) * G::FBYTES + 16LL * kk;
         unsigned char* d = dst + h * G::HALF_BYTES + 16 * kk;
         stage_chunk16(a, c, o, d, aligned16);
     }
@@ -657,19 +654,31 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     const bool aligned16 = src_aligned16(a);
     const unsigned out_low_bits = (unsigned)(reinterpret_cast<unsigned long long>(a.out) & 15ULL);
     int a_tile;
+    long long rel0;                  // source offset of byte 0 of the half buffer of frame 0 (ring_stage_tile)
     {
         long long t0;
-        ring_half_origin<G>(a.p0, a.in_first, 0, t0, a_tile);   // the same for every half of the launch
+        ring_half_origin<G>(a.p0, a.in_first, 0, t0, a_tile);   // a_tile is the same for every half of the launch
+        rel0 = t0 - a.in_first;
     }
     const int l = tid & 31, w = tid >> 5, h = l >> 4;
     RingLane<G> lane;
     const uint32_t w0 = (uint32_t)(G::LUT_BYTES + h * G::HALF_BYTES + ring_lane_init<G>(lane, tid, a_tile, a.unit));
     uint32_t loff = 0;
 
+    // Tiles are staged LEAD = NBUF - 2 tiles ahead (one, or two where a period is too short to cover a load from DRAM):
+    // tq[0] is the current tile, tq[d] the tile d further on in this CTA's sequence.
+    constexpr int LEAD = NBUF - 2;
     long long tile = blockIdx.x;     // grid <= ntiles
-    RingTile tl = ring_tile_at<G>(tile, a.nframes, a.nch);
+    RingTile tq[LEAD + 1];
     cp_async_wait<0>();              // the table image of this thread (the tile's barrier may be a bulk-copy one)
-    ring_stage_tile<G>(a, tl, smem + G::LUT_BYTES, aligned16, &full[0]);
+#pragma unroll
+    for (int d = 0; d < LEAD; ++d) {
+        const long long t = tile + (long long)d * gridDim.x;
+        tq[d] = ring_tile_at<G>(t < ntiles ? t : tile, a.nframes, a.nch);
+        if (t < ntiles) ring_stage_tile<G>(a, tq[d], smem + G::LUT_BYTES + d * G::TILE_BYTES, aligned16, &full[d], rel0);
+    }
+    tq[LEAD] = tq[0];
+    const RingTile& tl = tq[0];
 
     RingDest prev;                   // nothing to emit in the very first period: every store is off
     prev.fb = a.nframes; prev.c = 0; prev.c0 = 0; prev.pair = false;
@@ -682,23 +691,25 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     }
     typedef typename RingEmitterOf<G, OUT, DITHER, INIT>::type Emitter;
     constexpr long long FPL = G::FPL;   // output frames per lane and period
-    int b = 0, use = 0;              // buffer of the current tile, how often it has been used before
-    for (long long i = 0; tile < ntiles; ++i) {
-        const long long next = tile + gridDim.x;
+    int b = 0;                       // buffer of the current tile (the i-th of this CTA): i % NBUF, used i / NBUF times before
+    for (int i = 0; tile < ntiles; ++i) {
+        const long long next = tile + gridDim.x, ahead = tile + (long long)LEAD * gridDim.x;
         const int bn = b + 1 == NBUF ? 0 : b + 1;
         RingDest after;              // first frames of the next tile (INIT: where the next period's sums start)
         after.fb = a.nframes; after.c = 0; after.c0 = 0; after.pair = false;
-        if (next < ntiles) {
-            // buffer bn last held tile i-2; its use count is `use` when bn > b, else use + 1, minus one
-            if (i + 1 >= NBUF) mbar_wait(&empty[bn], (unsigned)(((i + 1) / NBUF - 1) & 1));
-            const RingTile tn = ring_tile_at<G>(next, a.nframes, a.nch);
-            ring_stage_tile<G>(a, tn, smem + G::LUT_BYTES + bn * G::TILE_BYTES, aligned16, &full[bn]);
-            if (INIT || DITHER) {
-                after.c = h ? tn.c[1] : tn.c[0];
-                after.fb = (h ? tn.f0[1] : tn.f0[0]) + FPL * (16 * w + (l & 15));
-            }
+        if (ahead < ntiles) {
+            // the (i + LEAD)-th tile goes to the buffer that held the (i - 2)-th
+            const int bs = b + LEAD >= NBUF ? b + LEAD - NBUF : b + LEAD;
+            if (i + LEAD >= NBUF) mbar_wait(&empty[bs], (unsigned)(((i + LEAD) / NBUF - 1) & 1));
+            tq[LEAD] = ring_tile_at<G>(ahead, a.nframes, a.nch);
+            ring_stage_tile<G>(a, tq[LEAD], smem + G::LUT_BYTES + bs * G::TILE_BYTES, aligned16, &full[bs], rel0);
         }
-        mbar_wait(&full[b], (unsigned)(use & 1));
+        if (next < ntiles && (INIT || DITHER)) {
+            const RingTile& tn = tq[1];
+            after.c = h ? tn.c[1] : tn.c[0];
+            after.fb = (h ? tn.f0[1] : tn.f0[0]) + FPL * (16 * w + (l & 15));
+        }
+        mbar_wait(&full[b], (unsigned)((i / NBUF) & 1));
         RingDest cur;
         cur.c = h ? tl.c[1] : tl.c[0];
         cur.c0 = tl.c[0];
@@ -718,9 +729,9 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
             cur.fb += FPL * G::BLK_PER_ROUND;
         }
         tile = next;
-        if (bn == 0) ++use;
         b = bn;
-        if (tile < ntiles) tl = ring_tile_at<G>(tile, a.nframes, a.nch);
+#pragma unroll
+        for (int d = 0; d < LEAD; ++d) tq[d] = tq[d + 1];
     }
     // the one drain of this CTA: 16 more steps finish the last frames (ROTATE: they are finished, only the emitter is left)
     if constexpr (!G::ROTATE) ring_head<G>(lane, smem, lane.wlast, loff, tid, 0, RingNoTrace());

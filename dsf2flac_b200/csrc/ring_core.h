@@ -125,7 +125,9 @@ struct RingGeom {
     static constexpr int HALF_SHIFT = LANE_BYTES == 32 ? 16 : COPIES > 1 ? 64 : 0;   // bank offset of the upper half-warp's buffer
     static constexpr int HALF_BYTES = NSTEP * NTP + 256 + HALF_SHIFT;
     static constexpr int TILE_BYTES = 2 * HALF_BYTES;
-    static constexpr int NBUF = 3;                    // tile buffers: current, previous (still read), next
+    // tile buffers: current, previous (still read), next -- and the one after where a period (KF * 72 table loads per lane)
+    // is too short to cover a load from DRAM and a fourth buffer fits
+    static constexpr int NBUF = (NSTEP >= 16) ? 4 : 3;
     static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
     // where the emitter is called from: spread over the groups after the early ones if there are enough
     static constexpr bool EMIT_SPREAD = GROUPS >= EARLY_GROUPS + 7;   // fetch, four quantise calls, store, prefetch: one group each

@@ -158,7 +158,9 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
         bool have_prev = false;
         long long tile = cta;
         int buf = 0, period = 0;
-        if (stage(tile, 0)) return 2;
+        constexpr int LEAD = G::NBUF - 2;     // the kernel stages LEAD tiles ahead: the first LEAD tiles before the loop
+        for (int d = 0; d < LEAD; ++d)
+            if (tile + (long long)d * grid < ntiles && stage(tile + (long long)d * grid, d)) return 2;
         if constexpr (!G::PAIR) if (use_init) {   // the kernel loads these right after ring_lane_init
             const RingTile t0 = ring_tile_at<G>(tile, nframes, nch);
             for (int tid = 0; tid < G::NTHR; ++tid) {
@@ -170,9 +172,10 @@ static int run(long long nframes, int nch, long long p0, long long in_first, lon
             const long long next = tile + grid;
             const RingTile tl = ring_tile_at<G>(tile, nframes, nch);
             // top of the tile: the kernel refills the buffer that held the tile before the previous one
-            const int bn = (buf + 1) % G::NBUF;
-            if (next < ntiles) { if (stage(next, bn)) return 2; }
-            else for (int k = 0; k < G::TILE_BYTES; ++k) smem[(size_t)G::LUT_BYTES + bn * G::TILE_BYTES + k] = (unsigned char)(rand() & 0xff);
+            const int bn = (buf + 1) % G::NBUF, bs = (buf + LEAD) % G::NBUF;
+            const long long ahead = tile + (long long)LEAD * grid;
+            if (ahead < ntiles) { if (stage(ahead, bs)) return 2; }
+            else for (int k = 0; k < G::TILE_BYTES; ++k) smem[(size_t)G::LUT_BYTES + bs * G::TILE_BYTES + k] = (unsigned char)(rand() & 0xff);
             const bool trace = (cta == 0) && (tile == cta || next >= ntiles);
             for (int n = 0; n < G::KR; ++n, ++period) {
                 std::vector<Access> lut_log, word_log;
