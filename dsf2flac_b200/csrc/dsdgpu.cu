@@ -194,6 +194,8 @@ int launch_dither(dsdgpu_ctx* ctx, dsdgpu_slot& s, unsigned long long first_samp
     return DSDGPU_OK;
 }
 
+constexpr int DSDGPU_ERR_NOMEM_SOFT = -1000;   // internal: the dither plane could not grow (the caller falls back to a plane of its own)
+
 // Make samples [0, end) of the cached dither plane valid for work enqueued on `st` afterwards.
 int dither_cache_cover(dsdgpu_ctx* ctx, dsdgpu_slot& s, long long end, cudaStream_t st) {
     if (!ctx->dither_ready) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->dither_ready, cudaEventDisableTiming));
@@ -204,7 +206,11 @@ int dither_cache_cover(dsdgpu_ctx* ctx, dsdgpu_slot& s, long long end, cudaStrea
         while (cap < end) cap <<= 1;
         if (cap > ctx->dither_cache_limit) cap = ctx->dither_cache_limit;
         double* fresh = nullptr;
-        CUDA_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&fresh), (size_t)cap * sizeof(double)));
+        if (cudaMalloc(reinterpret_cast<void**>(&fresh), (size_t)cap * sizeof(double)) != cudaSuccess) {
+            (void)cudaGetLastError();               // no room for the plane: this call and the later ones make their own
+            ctx->dither_cache_limit = ctx->dither_len;
+            return DSDGPU_ERR_NOMEM_SOFT;
+        }
         if (ctx->dither_len > 0)
             CUDA_TRY(ctx, cudaMemcpyAsync(fresh, ctx->d_dither_cache, (size_t)ctx->dither_len * sizeof(double), cudaMemcpyDeviceToDevice, st));
         if (ctx->d_dither_cache) ctx->dither_retired.push_back(ctx->d_dither_cache);
@@ -430,9 +436,10 @@ int enqueue_decimate(dsdgpu_ctx* ctx, dsdgpu_slot& scratch, const uint8_t* d_in,
         if (dither_first_sample <= (uint64_t)ctx->dither_len &&
             dither_first_sample + (uint64_t)count <= (uint64_t)ctx->dither_cache_limit) {
             int rc = dither_cache_cover(ctx, scratch, (long long)dither_first_sample + count, st);
-            if (rc) return rc;
-            a.dither = ctx->d_dither_cache + dither_first_sample;
-        } else {
+            if (rc && rc != DSDGPU_ERR_NOMEM_SOFT) return rc;
+            if (rc == DSDGPU_OK) a.dither = ctx->d_dither_cache + dither_first_sample;
+        }
+        if (a.dither == nullptr) {
             int rc = ensure(ctx, &scratch.d_dither, &scratch.dither_cap, (size_t)count * sizeof(double));
             if (rc) return rc;
             rc = launch_dither(ctx, scratch, dither_first_sample, count, scratch.d_dither, st);
