@@ -78,6 +78,11 @@ namespace dsdgpu {
 // value (Emit::init) instead of 0.  Lanes are 32 bytes apart; the identity skew puts the 16 window
 // words of a half-warp in 16 distinct banks (8i + (i >> 2) mod 32), and the byte buffer of the upper
 // half starts 16 bytes further on so that its 16 words take the other 16 banks.
+//
+// NSTEP = 16 / 32 (EXTENSION, decimation by 128 / 256: 288 / 576 tables, four / eight passes of 72): what must not change
+// is the 32 bytes between neighbouring lanes, so a lane carries KF = 2 frames 16 bytes apart (frame 1 = the word stream
+// shifted by four words) or KF = 1 frame.  Tile bytes, skew and bank pattern are those of the NSTEP = 8 pass; periods are
+// short (72 * KF table loads per lane), so these instances keep four tile buffers and stage two tiles ahead.
 template <int NWARP_, int KR_, bool Q32_ = false, int NLUT_ = 72, int NSTEP_ = 4>
 struct RingGeom {
     static constexpr bool Q32 = Q32_;
