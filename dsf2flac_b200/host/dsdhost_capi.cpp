@@ -106,6 +106,8 @@ int dsdhost_run_raw_typed(const uint8_t* planar, int nch, int64_t nbytes, int64_
 // One whole track, --onefile bounds (reference main.cpp:249-258) and the loop of
 // main.cpp:169-191: creep with step(), blocks of 1024 frames, then single frames.
 // Returns frames written, -1 on error, -2 if `out` is too small.
+static volatile uint32_t g_consumed = 0;   // keeps the consumer of the out == NULL mode alive
+
 static int64_t run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t length_samples,
                        uint8_t idle, int msb_flag, uint32_t dsd_fs, uint32_t out_fs, double scale,
                        double dither, double clip, int lut_bits, uint32_t read_ahead, int32_t* out,
@@ -129,18 +131,30 @@ static int64_t run_app(const uint8_t* planar, int nch, int64_t nbytes, int64_t l
     while (dec.getPosition() < startPos) dec.step();
     int64_t done = 0;
     std::vector<int32_t> buf((size_t)nch * block);
+    // out == NULL: the caller only wants the loop run the way main.cpp runs it -- one block buffer, reused, handed to a
+    // consumer that reads it (main.cpp:173-178: the FLAC encoder) -- not a second copy of the whole PCM stream
+    uint32_t consumed = 0;
     while (dec.getPosition() <= endPos - block) {
         dec.getSamples(buf.data(), (dsf2flac_uint32)(nch * block), scale, dither, clip);
-        if (done + block > out_cap_frames) return -2;
-        std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch * block);
+        if (out) {
+            if (done + block > out_cap_frames) return -2;
+            std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch * block);
+        } else {
+            for (int32_t v : buf) consumed += (uint32_t)v;
+        }
         done += block;
     }
     while (dec.getPosition() <= endPos) {
         dec.getSamples(buf.data(), (dsf2flac_uint32)nch, scale, dither, clip);
-        if (done + 1 > out_cap_frames) return -2;
-        std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch);
+        if (out) {
+            if (done + 1 > out_cap_frames) return -2;
+            std::memcpy(out + done * nch, buf.data(), sizeof(int32_t) * nch);
+        } else {
+            for (int c = 0; c < nch; ++c) consumed += (uint32_t)buf[(size_t)c];
+        }
         done += 1;
     }
+    g_consumed = consumed;
     if (!dec.isValid()) { g_error = dec.getErrorMsg(); return -1; }
     return done;
 }
