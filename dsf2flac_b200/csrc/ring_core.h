@@ -60,9 +60,9 @@ namespace dsdgpu {
 //              4 chains = 8 output frames: half the table loads, byte extractions and address computations per
 //              frame of the one-entry-per-load layout, for 320 instead of 288 bytes of table reads.
 //
-// Other filters (NLUT = 30 tables, 2 bytes per frame; NLUT = 12, 1 byte per frame): the period is
-// NLUT rounded up to a multiple of 16 steps, the extra slots hold -0.0 (the identity of fp64
-// addition), so a wrapped lane needs no second copy: slot PERIOD + s - j is bank pair (s - j) mod 16.
+// Other geometries whose period is NLUT rounded up to a multiple of 16 steps: the extra slots hold -0.0 (the identity
+// of fp64 addition; 0 for integer tables), so a wrapped lane needs no second copy: slot PERIOD + s - j is bank pair
+// (s - j) mod 16.  The 30-table filter (2 bytes per frame) runs periods of exactly 30 steps instead (PADLESS below).
 //
 // Short filters (NLUT = 30, NLUT = 12) keep COPIES = 2 / 4 images of their (small) tables, image a shifted by
 // a * 16 / COPIES slots against the bank pattern.  Lane i of a half-warp reads image i % COPIES with skew
@@ -97,8 +97,13 @@ struct RingGeom {
     static constexpr bool ROTATE = PAIR;
     static constexpr bool DUP = (NLUT == 72);         // 72-step periods with tail copies (see above)
     static constexpr int COPIES = NLUT == 12 ? 4 : NLUT == 30 ? 2 : 1;   // images of the tables (whatever fits shared memory)
-    static constexpr int PERIOD = DUP ? 72 : COPIES == 4 ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
-    static constexpr int GROUPS = PERIOD / 4;         // 4-step groups = window words per period
+    // 30 tables: a period of exactly 30 steps.  A wrapped lane reads its last taps (23..29) from copies 18 slots further on
+    // (slot 48 + s - j: the bank pair it would have in a 32-step pattern), and the window of its previous frames goes on
+    // two bytes off the word grid (30 mod 4): one more funnel shift per early group.
+    static constexpr bool PADLESS = (NLUT == 30);
+    static constexpr int PERIOD = DUP ? 72 : (COPIES == 4 || PADLESS) ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
+    static constexpr int GROUPS = (PERIOD + 3) / 4;   // 4-step groups = window words per period (the last one may be short)
+    static constexpr int WRAP_SHIFT = 8 * (PERIOD % 4);   // bits by which the previous window's word stream is off the grid
     // consecutive chains (sums) per lane: four, or as many as keep neighbouring lanes 32 bytes apart (frame hops of 16 / 32 bytes)
     static constexpr int KF = NSTEP_ == 16 ? 2 : NSTEP_ == 32 ? 1 : 4;
     static constexpr int FPL = KF * FPC;              // consecutive output frames per lane
@@ -112,7 +117,8 @@ struct RingGeom {
     static constexpr int NSKEW = SKEW_LANES / COPIES; // distinct skew values
     static constexpr int EARLY_GROUPS = (NSKEW + 3) / 4;  // 4-step groups in which some lane is still wrapped
     static constexpr int EARLY_STEPS = NSKEW;
-    static constexpr int ROW = DUP ? 80 : (PERIOD + 15) / 16 * 16;   // slots per table row
+    static constexpr int ROW = DUP ? 80 : PADLESS ? 48 : (PERIOD + 15) / 16 * 16;   // slots per table row
+    static constexpr int WRAP = PADLESS ? ROW : PERIOD;   // a wrapped lane reads slot WRAP + s - j
     static constexpr int ROW_BYTES = ROW * ELEM;      // a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
     static constexpr int COPY_STRIDE = 256 * ROW_BYTES + (COPIES > 1 ? 128 : 0);   // image a: + a * (COPY_STRIDE + ELEM * NSKEW)
@@ -143,7 +149,7 @@ struct RingGeom {
     static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8 || NSTEP == 16 || NSTEP == 32, "frame hop of 8 ... 256 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
     static_assert(!PAIR || GROUPS >= EARLY_GROUPS + 15, "two emitter sequences fit the late groups");
-    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == HALF_SHIFT && ROW_BYTES % 128 == 0 && PERIOD % 4 == 0, "staging chunks / bank pattern");
+    static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == HALF_SHIFT && ROW_BYTES % 128 == 0 && (WRAP_SHIFT == 0 || (NSTEP == 2 && WRAP_SHIFT == 16)), "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
     static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
 };
@@ -281,6 +287,7 @@ struct RingLane {
     acc_t p[G::KF];             // sums of the frames started in the previous period (final after EARLY_STEPS)
     uint32_t qn[G::QHA], qo[G::QHA];   // previous window words of the current / the previous frame set
     uint32_t ln, lo;            // last aligned word loaded from either window
+    uint32_t vold;              // WRAP_SHIFT: the previous window's last grid-aligned word
     uint32_t wlast;             // smem offset of word L(0) of the previous period's window
     // constants of the lane
     int j;                      // skew
@@ -310,7 +317,8 @@ RING_HD int ring_lane_init(RingLane<G>& r, int tid, int a_tile, double unit = 1.
     const int image = ring_lane_image<G>(l);
     const int base = G::GUARD_BYTES + image * (G::COPY_STRIDE + G::ELEM * G::NSKEW);
     r.lnew = (uint32_t)(base - G::ELEM * j);
-    r.lwrap = (uint32_t)(base + G::ELEM * (G::PERIOD - j));
+    r.lwrap = (uint32_t)(base + G::ELEM * (G::WRAP - j));
+    r.vold = 0u;
     r.lalt = (uint32_t)(G::DUP ? G::ELEM * 8 * (j >> 3) : 0);
 #pragma unroll
     for (int g = 0; g < G::EARLY_GROUPS; ++g) {
@@ -397,8 +405,13 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             const uint32_t a = wold - 4u * (uint32_t)(G::GROUPS + g);
             const uint32_t w = ring_lds_u32(smem, a);
             tr.word(tid, period, 2 * g + 1, a);
-            const uint32_t v = ring_funnel_r(w, r.lo, r.shift);
+            uint32_t v = ring_funnel_r(w, r.lo, r.shift);
             r.lo = w;
+            if constexpr (G::WRAP_SHIFT != 0) {          // the previous frames' steps PERIOD + 4g ..: off the word grid
+                const uint32_t aligned = v;
+                v = ring_funnel_r(aligned, r.vold, (uint32_t)G::WRAP_SHIFT);
+                r.vold = aligned;
+            }
             uint32_t y[G::KF];
             ring_slot_words<G>(v, r.qo, y);
 #pragma unroll
@@ -411,6 +424,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int s = 4 * g + u;
+            if (s >= G::PERIOD) break;                   // (a period that is not a whole number of groups)
             bool cur = true;
             if (s < G::EARLY_STEPS) {
                 // wrapped lanes (s < j) still add to their previous frames; multipliers route each
@@ -512,6 +526,11 @@ RING_HD void ring_tail(RingLane<G>& r, const unsigned char* smem, uint32_t wnew,
     }
 #pragma unroll
     for (int i = 0; i < G::QH; ++i) r.qo[i] = r.qn[i];   // this window's last words = next period's history
+    if constexpr (G::WRAP_SHIFT != 0) {                  // ... in the shifted word stream the wrapped steps read
+        r.vold = r.qn[0];
+#pragma unroll
+        for (int i = 0; i + 1 < G::QH; ++i) r.qo[i] = ring_funnel_r(r.qn[i], r.qn[i + 1], (uint32_t)G::WRAP_SHIFT);
+    }
     r.lo = r.ln;
     r.wlast = wnew;
 }
@@ -587,6 +606,8 @@ inline void ring_build_lut_image(const double* lut, unsigned char* image, double
             for (int t = 0; t < G::NLUT; ++t) put(c, e, t, lut[t * 256 + e]);
             for (int copy = 1; G::DUP && G::NLUT + 8 * copy <= G::ROW; ++copy)      // tail copies: slot = tap + 8*copy
                 for (int m = 0; m < 8; ++m) put(c, e, 64 + m + 8 * copy, lut[(64 + m) * 256 + e]);
+            if (G::PADLESS)                                                          // tail copies: slot = tap + 18
+                for (int t = G::NLUT - G::NSKEW + 1; t < G::NLUT; ++t) put(c, e, t + G::ROW - G::NLUT, lut[t * 256 + e]);
         }
 }
 
