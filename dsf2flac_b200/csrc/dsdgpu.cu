@@ -93,7 +93,7 @@ namespace {
 using Ring16x2 = RingGeom<16, 2>;
 using Ring16x1 = RingGeom<16, 1>;               // the same kernel with one round per tile: half-size tiles for short launches
 static_assert(Ring16x1::LUT_BYTES == Ring16x2::LUT_BYTES, "both read the same table image");
-using Ring16x2Q = RingGeom<16, 1, true, 76, 8>;   // 32-bit tables: two frames per 8-byte entry (76 pair tables, chains 8 bytes apart)
+using Ring16x2Q = RingGeom<8, 1, true, 76, 8>;   // 32-bit tables: two frames per 8-byte entry (76 pair tables, chains 8 bytes apart)
 using Ring30 = RingGeom<16, 2, false, 30, 2>;   // divide-by-16 filter: 30 tables, 2 bytes per frame
 using Ring12 = RingGeom<16, 2, false, 12, 1>;   // divide-by-8 filter: 12 tables, 1 byte per frame
 using Ring12L = RingGeom<16, 16, false, 12, 1>; // the same with 16 rounds per tile: what a tile costs besides its table loads (geometry,

@@ -100,7 +100,7 @@ struct RingGeom {
     // 30 tables: a period of exactly 30 steps.  A wrapped lane reads its last taps (23..29) from copies 18 slots further on
     // (slot 48 + s - j: the bank pair it would have in a 32-step pattern), and the window of its previous frames goes on
     // two bytes off the word grid (30 mod 4): one more funnel shift per early group.
-    static constexpr bool PADLESS = (NLUT == 30);
+    static constexpr bool PADLESS = (NLUT == 30) || (Q32_ && NWARP_ == 8);   // (76 pair tables: the 96-slot rows fit beside the tiles of 8 warps)
     static constexpr int PERIOD = DUP ? 72 : (COPIES == 4 || PADLESS) ? NLUT : (NLUT + 15) / 16 * 16;     // steps per period
     static constexpr int GROUPS = (PERIOD + 3) / 4;   // 4-step groups = window words per period (the last one may be short)
     static constexpr int WRAP_SHIFT = 8 * (PERIOD % 4);   // bits by which the previous window's word stream is off the grid
@@ -117,7 +117,7 @@ struct RingGeom {
     static constexpr int NSKEW = SKEW_LANES / COPIES; // distinct skew values
     static constexpr int EARLY_GROUPS = (NSKEW + 3) / 4;  // 4-step groups in which some lane is still wrapped
     static constexpr int EARLY_STEPS = NSKEW;
-    static constexpr int ROW = DUP ? 80 : PADLESS ? 48 : (PERIOD + 15) / 16 * 16;   // slots per table row
+    static constexpr int ROW = DUP ? 80 : PADLESS ? (PERIOD + NSKEW - 1 + 15) / 16 * 16 : (PERIOD + 15) / 16 * 16;   // slots per table row
     static constexpr int WRAP = PADLESS ? ROW : PERIOD;   // a wrapped lane reads slot WRAP + s - j
     static constexpr int ROW_BYTES = ROW * ELEM;      // a multiple of 128
     static constexpr int GUARD_BYTES = 128;           // keeps every per-lane offset positive
@@ -149,6 +149,7 @@ struct RingGeom {
     static_assert(NSTEP == 1 || NSTEP == 2 || NSTEP == 4 || NSTEP == 8 || NSTEP == 16 || NSTEP == 32, "frame hop of 8 ... 256 DSD samples");
     static_assert(GROUPS >= EARLY_GROUPS, "every lane must restart within one period");
     static_assert(!PAIR || GROUPS >= EARLY_GROUPS + 15, "two emitter sequences fit the late groups");
+    static_assert(!PADLESS || ROW >= NLUT + NSKEW - 1, "tail copies behind the tables");
     static_assert(LUT_BYTES % 16 == 0 && HALF_BYTES % 128 == HALF_SHIFT && ROW_BYTES % 128 == 0 && (WRAP_SHIFT == 0 || (NSTEP == 2 && WRAP_SHIFT == 16)), "staging chunks / bank pattern");
     static_assert(HOP % 16 == 0, "windows of successive rounds share their byte phase");
     static_assert(GUARD_BYTES >= ELEM * (SKEW_LANES - 1), "per-lane table offsets stay positive");
@@ -362,7 +363,7 @@ RING_HD void ring_groups(RingLane<G>& r, const unsigned char* smem, uint32_t wne
             // eight finished frames per lane: two emitter sequences (frames 0..3, then 4..7), each fetch -> four quantise
             // calls -> store, staggered over the late groups (Emit is a RingEmitterPair-like object)
             constexpr int E = G::EARLY_GROUPS;
-            constexpr int LEAD = Emit::LATE ? 5 : 1;   // groups between a sequence's fetch (dither loads) and its first quantise
+            constexpr int LEAD = Emit::LATE ? (G::GROUPS >= E + 16 ? 5 : 4) : 1;   // groups between a sequence's fetch (dither loads) and its first quantise
             constexpr int F0 = E + 1, Q0 = F0 + LEAD, F1 = Q0 + 4 - LEAD + 1, Q1 = Q0 + 5;
             static_assert(Q1 + 5 <= G::GROUPS, "both sequences end inside the period");
             if (g == F0) emit.fetch(0);
@@ -593,6 +594,10 @@ inline void ring_build_lut_image(const double* lut, unsigned char* image, double
                 int32_t* at = reinterpret_cast<int32_t*>(image + G::GUARD_BYTES + e * G::ROW_BYTES + tau * G::ELEM);
                 at[0] = tau >= G::FBYTES ? (int32_t)(lut[(tau - G::FBYTES) * 256 + e] / unit) : 0;
                 at[1] = tau < G::NLUT - G::FBYTES ? (int32_t)(lut[tau * 256 + e] / unit) : 0;
+                if (G::PADLESS && tau > G::NLUT - G::NSKEW) {        // tail copies: slot = tau + (ROW - NLUT)
+                    int32_t* copy = at + 2 * (G::ROW - G::NLUT);
+                    copy[0] = at[0]; copy[1] = at[1];
+                }
             }
         return;                                           // (pad slots stay 0)
     }

@@ -254,6 +254,7 @@ int main(int argc, char** argv) {
     if (nwarp == 64 && kr == 1) return run<RingGeom<16, 1, false, 72, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "64": one pass of the /64 extension
     if (nwarp == 128 && kr == 1) return run<RingGeom<16, 1, false, 72, 16>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "128": one pass of the /128 extension: two frames per lane
     if (nwarp == 256 && kr == 1) return run<RingGeom<16, 1, false, 72, 32>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "256": one pass of the /256 extension: one frame per lane
+    if (nwarp == 768 && kr == 1) return run<RingGeom<8, 1, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "768": 8 warps, 76-step periods (no pad steps)
     if (nwarp == 76 && kr == 1) return run<RingGeom<16, 1, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);   // "76": the product's 32-bit geometry (frame pairs)
     if (nwarp == 76 && kr == 2) return run<RingGeom<16, 2, true, 76, 8>>(nframes, nch, p0, in_first, in_count, seed, grid);
     fprintf(stderr, "unsupported geometry\n");
