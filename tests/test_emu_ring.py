@@ -23,13 +23,19 @@ EMU = os.path.join(os.path.dirname(__file__), "cpp", "_build", "emu_ring")
     (8, 6, 9000, 6, 75, 3, 37000, 5, 2),         # 5.1, unaligned in_first, 8-warp geometry
     (16, 3, 1, 2, 72, 0, 100, 7, 4),             # a single frame
     (16, 2, 30000, 2, 75, 0, 121000, 8, 3),      # two rounds per tile, 5 tiles per CTA, aligned
-    (76, 1, 20000, 2, 75, 0, 81000, 8, 3),       # nwarp "76" = the product's 32-bit geometry: two frames per 8-byte entry,
+    (76, 1, 20000, 2, 75, 0, 81000, 8, 3),       # nwarp "76" = the 32-bit geometry on 16 warps (80-step periods): two frames per 8-byte entry,
     (76, 1, 20000, 2, 72, 0, 81000, 1, 2),       #   76 pair tables, chains 8 bytes apart, eight frames per lane
     (76, 1, 15000, 3, -1, 0, 61000, 3, 3),
     (76, 1, 9001, 6, 75, 3, 37000, 5, 2),        # odd frame count: the last chain has one frame
     (76, 1, 7001, 1, 72, 0, 29000, 2, 1),
     (76, 1, 1, 2, 72, 0, 100, 7, 4),
     (76, 2, 40000, 2, 75, 0, 161000, 8, 3),
+    (768, 1, 20000, 2, 75, 0, 81000, 8, 3),      # "768" = the product's 32-bit instance: 8 warps, 76-step periods (no pad steps,
+    (768, 1, 20000, 2, 72, 0, 81000, 1, 2),      #   wrapped lanes read tail copies 20 slots further on)
+    (768, 1, 15000, 3, -1, 0, 61000, 3, 3),
+    (768, 1, 9001, 6, 75, 3, 37000, 5, 2),
+    (768, 1, 7001, 1, 72, 0, 29000, 2, 1),
+    (768, 1, 1, 2, 72, 0, 100, 7, 4),
     (30, 2, 30000, 2, 31, 0, 61000, 8, 3),       # nwarp "30" = the divide-by-16 filter (30 tables, 32-step periods)
     (30, 2, 9000, 3, -1, 0, 19000, 3, 2),
     (30, 2, 9000, 1, 30, 2, 18000, 3, 2),
