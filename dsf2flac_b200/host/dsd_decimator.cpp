@@ -513,7 +513,14 @@ void widen24(dsf2flac_int32* dst, const dsf2flac_uint8* src, size_t count) {
 }
 struct WidenPcm24 {
     void operator()(dsf2flac_int32* dst, const void* blk, size_t first, size_t count) const {
-        widen24(dst, static_cast<const dsf2flac_uint8*>(blk) + 3 * first, count);
+        const dsf2flac_uint8* src = static_cast<const dsf2flac_uint8*>(blk) + 3 * first;
+        widen24(dst, src, count);
+#if defined(__x86_64__) && defined(__GNUC__)
+        // The next call reads the bytes that follow, cold: page-locked memory the copy engine has just written.  Ask
+        // for them now -- the caller is about to spend its time in the encoder (a prefetch never faults, so running
+        // past the end of the block is harmless).
+        for (size_t off = 3 * count; off < 6 * count; off += 64) __builtin_prefetch(src + off, 0, 3);
+#endif
     }
 };
 struct WidenPcm16 {
