@@ -368,3 +368,34 @@ def test_gpu_odd_geometries_and_limits():
     for nlut, nstep in ((641, 8), (72, 65), (0, 4)):
         with pytest.raises(capi.DsdGpuError):
             capi.DsdGpu(np.zeros((max(nlut, 1), 256)) if nlut else np.zeros((1, 256))[:0].reshape(0, 256), 2, nstep)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_extension_random_geometry(ext_oracle, seed):
+    """Random geometry for the ring passes (and the segmented kernel): 1-6 channels, windows that start before the data,
+    odd chunk sizes, dither on and off at random positions of the dither stream (tools/fuzz_more.py runs more of these)."""
+    rng = np.random.default_rng(5000 + seed)
+    ratio = int(rng.choice([64, 128, 256]))
+    fir = filters.EXTENSION_FILTERS[ratio]
+    msb = int(rng.integers(0, 2))
+    nch = int(rng.integers(1, 7))
+    nbytes = int(rng.integers(2000, 120000))
+    data = rng.integers(0, 256, size=(nch, nbytes), dtype=np.uint8)
+    p0 = int(rng.integers(-5, max(1, nbytes // 2)))
+    nframes = int(rng.integers(0, (nbytes - p0 + 500) // fir.nstep))
+    dither = bool(rng.integers(0, 2))
+    scale, amp, clip = filters.app_params(int(rng.choice([16, 20, 24])), dither=dither)
+    fill = int(rng.choice([0x69, 0x96, 0x00]))
+    kernel = str(rng.choice(["auto", "auto", "seg"]))
+    sample0 = int(rng.integers(0, 1_000_000)) if dither and rng.random() < 0.5 else 0
+    want = ext_oracle.use(ratio).run_raw(data, 1 << 40, msb, DSD512, DSD512 // ratio, p0 + 1, nframes, scale, amp, clip, idle=fill,
+                                         rand_skip=2 * sample0)
+    g = capi.DsdGpu(filters.build_lut(fir, msb), nch, fir.nstep)
+    g.set_option("kernel", {"auto": capi.KERNEL_AUTO, "seg": capi.KERNEL_SEGMENTED}[kernel])
+    g.set_option("chunk_frames", int(rng.integers(1, 9000)))
+    got = np.empty((nframes, nch), dtype=np.int32)
+    g.decimate_host_raw(data.ctypes.data, nbytes, 0, nbytes, fill, p0, nframes, scale, amp, clip, sample0, capi.OUT_INT32,
+                        got.ctypes.data)
+    g.close()
+    assert np.array_equal(got, want), dict(ratio=ratio, nch=nch, nbytes=nbytes, p0=p0, nframes=nframes, dither=dither, kernel=kernel)
