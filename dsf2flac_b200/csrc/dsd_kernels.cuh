@@ -641,14 +641,21 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     constexpr int NBUF = G::NBUF;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::LUT_BYTES + NBUF * G::TILE_BYTES);
     uint64_t* empty = full + NBUF;
+    uint64_t* lut_bar = empty + NBUF;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], G::NTHR); mbar_init(&empty[b], G::NTHR); }
+        mbar_init(lut_bar, 1);
     }
     __syncthreads();                 // barriers initialised before anybody arrives on them
-    {
+    if (tid == 0) {
+        // the table image: a handful of bulk copies (TMA) by one thread, counted in bytes on a barrier of their own
         const unsigned char* img = reinterpret_cast<const unsigned char*>(a.lut);
-        for (int k = tid; k < G::LUT_BYTES / 16; k += G::NTHR) cp_async16(smem + 16 * k, img + 16 * k);
+        constexpr int PART = 32768;
+        mbar_arrive_expect_tx(lut_bar, (unsigned)G::LUT_BYTES);
+#pragma unroll 1
+        for (int o = 0; o < G::LUT_BYTES; o += PART)
+            bulk_copy_g2s(smem + o, img + o, (unsigned)(G::LUT_BYTES - o < PART ? G::LUT_BYTES - o : PART), lut_bar);
     }
     const long long ntiles = ring_tile_count<G>(a.nframes, a.nch);
     const bool aligned16 = src_aligned16(a);
@@ -691,6 +698,7 @@ __global__ void __launch_bounds__(G::NTHR, 1) decimate_ring_kernel(DecimateArgs 
     }
     typedef typename RingEmitterOf<G, OUT, DITHER, INIT>::type Emitter;
     constexpr long long FPL = G::FPL;   // output frames per lane and period
+    mbar_wait(lut_bar, 0u);          // the table image has landed
     int b = 0;                       // buffer of the current tile (the i-th of this CTA): i % NBUF, used i / NBUF times before
     for (int i = 0; tile < ntiles; ++i) {
         const long long next = tile + gridDim.x, ahead = tile + (long long)LEAD * gridDim.x;

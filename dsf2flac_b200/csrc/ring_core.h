@@ -139,7 +139,7 @@ struct RingGeom {
     // tile buffers: current, previous (still read), next -- and the one after where a period (KF * 72 table loads per lane)
     // is too short to cover a load from DRAM and a fourth buffer fits
     static constexpr int NBUF = (NSTEP >= 16) ? 4 : 3;
-    static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8;   // + full/empty mbarriers
+    static constexpr int SMEM_BYTES = LUT_BYTES + NBUF * TILE_BYTES + 2 * NBUF * 8 + 8;   // + full/empty mbarriers, + the table image's
     // where the emitter is called from: spread over the groups after the early ones if there are enough
     static constexpr bool EMIT_SPREAD = GROUPS >= EARLY_GROUPS + 7;   // fetch, four quantise calls, store, prefetch: one group each
     static constexpr int LATE_GROUPS = GROUPS - EARLY_GROUPS;
